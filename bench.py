@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py -- rollout-collection throughput of the DPT hot path on B200.
+
+Workload (BASELINE.json configs[4] per-GPU shard, the configuration the env-steps/s target is quoted
+on): bandit rollin_bandit collection, H=500, dim=5, var=0.3, 125 000 envs per GPU (weak scaling:
+1M envs on 8 GPUs), Philox noise, outputs in the reference consumer's fp32 layout (32 B per
+env-step, 2 GB per step per GPU -- larger than the 126 MB L2, so no flush is needed between steps).
+A "step" is one pass of the fused kernel over the GPU's env shard.
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, DIM, VAR = 500, 5, 0.3
+ENVS_PER_GPU = int(os.environ.get("DPT_BENCH_ENVS", 125000))
+BYTES_PER_STEP = 4 * (2 * 1 + DIM + 1)          # four fp32 context rows per env-step
+METRIC = "env-steps/sec (bandit rollout collect, H=500 dim=5)"
+UNIT = "env-steps/s"
+
+
+def workload_name(n_gpus):
+    return ("bandit rollin_bandit collection H=%d dim=%d var=%.1f, %d envs/GPU x %d GPU (BASELINE configs[4] shard), "
+            "outputs %.2f GB/step/GPU > L2 (no flush needed)" % (H, DIM, VAR, ENVS_PER_GPU, n_gpus,
+                                                                  ENVS_PER_GPU * H * BYTES_PER_STEP / 1e9))
+
+
+# ----------------------------------------------------------------------------- clocks ---------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU via NVML while the timed region runs."""
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+            0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, uuid):
+        self.samples, self.reasons, self.max_mhz, self._stop, self.ok = [], set(), None, threading.Event(), False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if isinstance(uuid, str) else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(0)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:   # noqa: BLE001
+            self.err = repr(e)
+
+    def _once(self):
+        nv = self.nv
+        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            m = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            m = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for bit, name in self.BITS.items():
+            if m & bit:
+                self.reasons.add(name)
+
+    def _loop(self):
+        while not self._stop.is_set():
+            self._once()
+            time.sleep(0.002)
+
+    def start(self):
+        if self.ok:
+            self._once()
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+
+    def stop(self):
+        if self.ok:
+            self._stop.set()
+            self.t.join()
+            self._once()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "nvml unavailable"}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- reference arm --
+def reference_sample(pool, envs_per_core):
+    steps, wall = pool.run(envs_per_core, DIM, H, VAR)
+    return steps, wall
+
+
+def run_reference(args, rank):
+    """The reference's own CPU implementation of the path (its oracle port: the reference is pure
+    Python and cannot travel to the GPU box) on all host cores, one process per core."""
+    if rank != 0:
+        return
+    from oracle import cpu_bench
+    pool = cpu_bench.BanditRollinPool()
+    envs_per_core = int(os.environ.get("DPT_REF_ENVS_PER_CORE", 24))
+    for _ in range(args.warmup):
+        pool.run(envs_per_core, DIM, H, VAR)
+    tot_steps, t0 = 0, time.perf_counter()
+    for i in range(args.steps):
+        s, _ = pool.run(envs_per_core, DIM, H, VAR, seed0=1000 * (i + 1))
+        tot_steps += s
+    wall = time.perf_counter() - t0
+    pool.close()
+    v = tot_steps / wall
+    sample = "%d cores x %d envs x H=%d per step (oracle port of collect_data.generate_bandit_histories)" % (
+        pool.cores, envs_per_core, H)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.gpus), "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": pool.cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------- our arm --------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    assert args.warmup >= 3, "timing rules: W >= 3 warm-up steps"
+
+    # CPU baseline first (rank 0, N=1 only), before the GPU is busy: bounded sample on all host cores
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_bench
+        pool = cpu_bench.BanditRollinPool()
+        epc = int(os.environ.get("DPT_CPU_ENVS_PER_CORE", 300))
+        steps, wall = pool.run(epc, DIM, H, VAR)
+        pool.close()
+        cpu_baseline = {"value": steps / wall, "unit": UNIT, "cores": pool.cores, "kind": "port",
+                        "sample": "%d cores x %d envs x H=%d, oracle port of collect_data.generate_bandit_histories "
+                                  "(%.1f s wall)" % (pool.cores, epc, H, wall)}
+
+    import torch
+    import torch.distributed as dist
+    import dpt_b200
+    from dpt_b200 import kernels
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N = ENVS_PER_GPU
+    env_id0 = rank * N                        # contiguous global env ranges
+    seed = 0
+    means, _, _ = kernels.bandit_sample_means(N, DIM, seed, env_id0)
+    out = {"context_states": torch.empty((N, H, 1), device=dev), "context_actions": torch.empty((N, H, DIM), device=dev),
+           "context_next_states": torch.empty((N, H, 1), device=dev), "context_rewards": torch.empty((N, H, 1), device=dev)}
+    stats = torch.zeros(3, dtype=torch.float64, device=dev)
+    gathered = torch.zeros(3 * world, dtype=torch.float64, device=dev)
+
+    def step(i):
+        # one pass of the fused kernel over this rank's env shard; multi-GPU: + the NCCL stat gather
+        kernels.bandit_rollin(means, H, VAR, seed + i, env_id0, out=out, stats=stats)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, stats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    if sampler:
+        sampler.start()
+    ev[0].record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+        ev[i + 1].record()
+    barrier()
+    if sampler:
+        sampler.stop()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t[0])
+    value = world * N * H * args.steps / (total_ms * 1e-3)
+
+    # roofline of the dominant kernel (bandit_rollin_fast<5>): algorithmic bytes / mean launch duration.
+    # A step IS one launch of it, so the per-step event deltas are its launch durations.
+    kern_ms = statistics.mean(per)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = N * H * BYTES_PER_STEP / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "bandit_rollin_fast<5,PHILOX>", "algorithmic_bytes_per_launch": N * H * BYTES_PER_STEP,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "launch_ms_mean": kern_ms, "launch_ms_min": min(per)}
+    tfile = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tfile):
+        try:
+            roofline["traffic"] = json.load(open(tfile)).get("bandit_rollin_fast_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # e2e: the same collection through the host-buffer C-ABI call (means in pinned host memory,
+    # contexts returned to pinned host memory), copies inside the timed region.
+    e2e_steps = args.e2e_steps or max(3, min(args.steps, 10))
+    means_host = means.cpu().pin_memory()
+    host_out, scratch = kernels.bandit_rollin_host(means_host, H, VAR, seed, env_id0)
+    for i in range(2):
+        kernels.bandit_rollin_host(means_host, H, VAR, seed + i, env_id0, out=host_out, scratch=scratch)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(e2e_steps):
+        kernels.bandit_rollin_host(means_host, H, VAR, seed + 100 + i, env_id0, out=host_out, scratch=scratch)
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t[0])
+    e2e = {"value": world * N * H * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": N * DIM * 4,
+           "d2h_bytes_per_step": N * H * BYTES_PER_STEP, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+           "api": "dpt_bandit_rollin_host (pinned host buffers, chunked H2D/kernel/D2H pipeline)"}
+
+    if rank == 0:
+        st = gathered.view(world, 3).sum(0) if world > 1 else stats
+        n_tot = world * N * H * (args.steps + args.warmup)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(world), "envs_per_gpu": N, "H": H, "dim": DIM, "var": VAR,
+                       "noise": "philox4x32-10", "l2": "outputs larger than L2, no flush",
+                       "parallelism": "env-sharded x%d%s" % (world, ", NCCL all-gather of return stats per step" if world > 1 else "")},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": args.steps,
+            "clocks": sampler.summary() if sampler else None,
+            "return_stats": {"mean_reward": float(st[0]) / n_tot, "frac_optimal_arm": float(st[2]) / n_tot},
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,161 @@
+"""Rollout collection with the reference's interface (collect_data.py), backed by the CUDA path.
+
+Reference functions kept drop-in: ``rollin_bandit(env, cov, orig=False)``, ``rollin_mdp(env,
+rollin_type)``, ``rollin_linear_bandit_vec(envs)``, ``generate_*_histories*`` (same traj-dict keys,
+dtypes and shapes as collect_data.py:158-300).  Where the reference loops over env objects in
+Python, the ``generate_*`` functions here make ONE fused launch over all envs; the device-resident
+batch interface (``collect_bandit`` / ``collect_darkroom``) skips the host format entirely.
+"""
+import numpy as np
+import torch
+
+from . import kernels, rng
+
+
+# --------------------------------------------------------------------------- device batches ---
+def collect_bandit(n_envs, dim, horizon, var, seed=None, env_id0=0, means=None, device=None):
+    """Task draw + rollin_bandit for ``n_envs`` envs, all on the device.  Returns a dict of fp32
+    device tensors: means [N,d], opt_a_index [N], optimal_actions [N,d], context_* [N,H,.]."""
+    key = rng.next_key() if seed is None else seed
+    if means is None:
+        means, opt_idx, opt_a = kernels.bandit_sample_means(n_envs, dim, key, env_id0, device)
+    else:
+        means = kernels._as(means, torch.float32, kernels._dev(device))
+        opt_idx, opt_a = kernels.bandit_opt_action(means)
+    out = kernels.bandit_rollin(means, horizon, float(var), key, env_id0)
+    out.update(means=means, opt_a_index=opt_idx, optimal_actions=opt_a)
+    return out
+
+
+def collect_darkroom(goals, dim, horizon, rollin_type="uniform", perm_index=None, n_samples=1, seed=None, env_id0=0):
+    """rollin_mdp + query states / optimal actions for all envs in one launch (device tensors)."""
+    key = rng.next_key() if seed is None else seed
+    return kernels.darkroom_rollin(goals, dim, horizon, rollin_type, key, env_id0, perm_index, n_samples)
+
+
+# --------------------------------------------------------------------------- single-env API ---
+def rollin_bandit(env, cov, orig=False):
+    """collect_data.py:23-53.  ``cov`` is ignored exactly like the reference (overwritten at :30).
+    Returns xs (H,1) int64, us (H,d) f64, xps (H,1) int64, rs (H,) f64."""
+    H = env.H_context
+    out = kernels.bandit_rollin(torch.as_tensor(np.asarray(env.means)[None, :], dtype=torch.float32), H,
+                                float(env.var), rng.next_key(), 0)
+    xs = out["context_states"][0].cpu().numpy().astype(np.int64)
+    us = out["context_actions"][0].cpu().numpy().astype(np.float64)
+    xps = out["context_next_states"][0].cpu().numpy().astype(np.int64)
+    rs = out["context_rewards"][0, :, 0].cpu().numpy().astype(np.float64)
+    return xs, us, xps, rs
+
+
+def rollin_mdp(env, rollin_type):
+    """collect_data.py:83-111.  Returns states (H,2) int64, actions (H,5) f64, next_states (H,2)
+    int64, rewards (H,) int64."""
+    if rollin_type not in ("uniform", "expert"):
+        raise NotImplementedError
+    perm = None if getattr(env, "perm_index", None) is None else [env.perm_index]
+    out = kernels.darkroom_rollin(np.asarray(env.goal)[None, :], env.dim, env.horizon, rollin_type, rng.next_key(), 0,
+                                  perm, 0)
+    return (out["context_states"][0].cpu().numpy().astype(np.int64),
+            out["context_actions"][0].cpu().numpy().astype(np.float64),
+            out["context_next_states"][0].cpu().numpy().astype(np.int64),
+            out["context_rewards"][0, :, 0].cpu().numpy().astype(np.int64))
+
+
+# --------------------------------------------------------------------------- generate_* -------
+def _bandit_trajs(batch, n_samples):
+    cs = batch["context_states"].cpu().numpy().astype(np.int64)
+    ca = batch["context_actions"].cpu().numpy().astype(np.float64)
+    cns = batch["context_next_states"].cpu().numpy().astype(np.int64)
+    cr = batch["context_rewards"][:, :, 0].cpu().numpy().astype(np.float64)
+    means = batch["means"].cpu().numpy().astype(np.float64)
+    opt = batch["optimal_actions"].cpu().numpy().astype(np.float64)
+    trajs = []
+    for i in range(cs.shape[0]):
+        for _ in range(n_samples):
+            trajs.append({"query_state": np.array([1]), "optimal_action": opt[i], "context_states": cs[i],
+                          "context_actions": ca[i], "context_next_states": cns[i], "context_rewards": cr[i],
+                          "means": means[i]})
+    return trajs
+
+
+def generate_bandit_histories_from_envs(envs, n_hists, n_samples, cov, type):
+    """collect_data.py:158-182, one launch per history index for all envs."""
+    means = np.stack([np.asarray(e.means, dtype=np.float64) for e in envs])
+    per_hist = []
+    for _ in range(n_hists):
+        b = collect_bandit(len(envs), means.shape[1], envs[0].H_context, envs[0].var, means=means)
+        per_hist.append(_bandit_trajs(b, n_samples))
+    trajs = []
+    for i in range(len(envs)):           # env-major, then history, then sample -- the reference's order
+        for j in range(n_hists):
+            trajs.extend(per_hist[j][i * n_samples:(i + 1) * n_samples])
+    for k, t in enumerate(trajs):        # keep the envs' own float64 means / opt_a objects, like the reference
+        env = envs[k // (n_hists * n_samples)]
+        t["means"], t["optimal_action"] = env.means, env.opt_a
+    return trajs
+
+
+def generate_bandit_histories(n_envs, dim, horizon, var, **kwargs):
+    """collect_data.py:221-225.  Task draw and rollouts happen on the device."""
+    n_hists, n_samples = kwargs.get("n_hists", 1), kwargs.get("n_samples", 1)
+    if kwargs.get("type", "uniform") != "uniform":
+        raise NotImplementedError
+    key = rng.next_key()
+    means, opt_idx, opt_a = kernels.bandit_sample_means(n_envs, dim, key, 0)
+    per_hist = []
+    for j in range(n_hists):
+        b = kernels.bandit_rollin(means, horizon, float(var), rng.key_for(key, j + 1), 0)
+        b.update(means=means, optimal_actions=opt_a)
+        per_hist.append(_bandit_trajs(b, n_samples))
+    trajs = []
+    for i in range(n_envs):
+        for j in range(n_hists):
+            trajs.extend(per_hist[j][i * n_samples:(i + 1) * n_samples])
+    return trajs
+
+
+def _mdp_trajs(envs, out, n_samples):
+    cs = out["context_states"].cpu().numpy().astype(np.int64)
+    ca = out["context_actions"].cpu().numpy().astype(np.float64)
+    cns = out["context_next_states"].cpu().numpy().astype(np.int64)
+    cr = out["context_rewards"][:, :, 0].cpu().numpy().astype(np.int64)
+    q = out["query_states"].cpu().numpy().astype(np.int64)
+    oa = out["optimal_actions"].cpu().numpy().astype(np.float64)
+    trajs = []
+    for i, env in enumerate(envs):
+        per_env = []
+        for k in range(n_samples):
+            t = {"query_state": q[i, k], "optimal_action": oa[i, k], "context_states": cs[i], "context_actions": ca[i],
+                 "context_next_states": cns[i], "context_rewards": cr[i], "goal": env.goal}
+            if hasattr(env, "perm_index"):
+                t["perm_index"] = env.perm_index
+            per_env.append(t)
+        trajs.append(per_env)
+    return trajs
+
+
+def generate_mdp_histories_from_envs(envs, n_hists, n_samples, rollin_type):
+    """collect_data.py:189-218 (one fused launch per history index)."""
+    goals = np.stack([np.asarray(e.goal) for e in envs])
+    perm = [e.perm_index for e in envs] if hasattr(envs[0], "perm_index") else None
+    per_hist = [_mdp_trajs(envs, collect_darkroom(goals, envs[0].dim, envs[0].horizon, rollin_type, perm, n_samples),
+                           n_samples) for _ in range(n_hists)]
+    trajs = []
+    for i in range(len(envs)):
+        for j in range(n_hists):
+            trajs.extend(per_hist[j][i])
+    return trajs
+
+
+def generate_darkroom_histories(goals, dim, horizon, **kwargs):
+    """collect_data.py:290-293."""
+    from .envs import darkroom_env
+    envs = [darkroom_env.DarkroomEnv(dim, goal, horizon) for goal in goals]
+    return generate_mdp_histories_from_envs(envs, **kwargs)
+
+
+def generate_darkroom_permuted_histories(indices, dim, horizon, **kwargs):
+    """collect_data.py:296-300."""
+    from .envs import darkroom_env
+    envs = [darkroom_env.DarkroomEnvPermuted(dim, index, horizon) for index in indices]
+    return generate_mdp_histories_from_envs(envs, **kwargs)

@@ -1,0 +1,408 @@
+// Fused bandit rollout kernel: rollin_bandit (reference collect_data.py:23-53) + BanditEnv.transit
+// (envs/bandit_env.py:56-64) for N envs x H steps in one launch.
+//
+// Layout of work ("one warp per env batch"): a CTA owns `envs_per_cta` consecutive envs.
+//   1. setup, one thread per env: behaviour policy of rollin_bandit -- cov ~ U{0,.1,..,1},
+//      probs ~ Dirichlet(1_d), rand_index ~ U{0..d-1}, probs = (1-cov) probs + cov e_idx -- then the
+//      normalised cdf of np.random.choice(p=) computed with the SAME float64 operation sequence
+//      as numpy (no FMA contraction), turned into integer thresholds so the per-step categorical
+//      draw is (d-1) integer compares and bit-exact against the oracle;
+//   2. meanwhile the other warps stream the constant context_states / context_next_states (== 1);
+//   3. step loop: each warp takes 64-step chunks; a lane owns two consecutive steps and makes
+//      ONE Philox4x32-10 call for them (2 categorical uniforms + 1 Box-Muller pair).  Rewards go
+//      out as one coalesced float2 per lane; the one-hot action rows (d floats per step, 20 B for
+//      d=5) are re-tiled across the warp with shuffles of a 2d-bit one-hot mask so that every
+//      store is a full, 16 B-aligned float4 of a contiguous 64*d*4-byte run.
+// HBM traffic is write-only: 4*(2+d+1) B per env-step (32 B for d=5), inputs are < 0.1 B/step.
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace dpt {
+
+constexpr int RB_THREADS = 256;
+constexpr int RB_WARPS = RB_THREADS / 32;
+constexpr int RB_MAX_ENVS = 32;
+constexpr int RB_MAX_D = 32;
+
+enum { MODE_PHILOX = 0, MODE_PHILOX_DUMP = 1, MODE_INJECT = 2 };
+
+struct RollinParams {
+  const float* means;
+  float var;
+  Key key;
+  uint64_t env_id0;
+  int N, H, d, envs_per_cta;
+  float *ctx_s, *ctx_a, *ctx_ns, *ctx_r;
+  double* stats;  // nullable: += (sum r, sum r^2, #pulls of the optimal arm) over all env-steps
+  dpt_bandit_inject_t in;
+  dpt_bandit_dump_t out;
+};
+
+__constant__ double c_cov_grid[11] = {0.0, .1, .2, .3, .4, .5, .6, .7, .8, .9, 1.0};  // collect_data.py:30
+
+template <int MODE>
+struct Thr {
+  using type = uint32_t;
+};
+template <>
+struct Thr<MODE_INJECT> {
+  using type = double;
+};
+
+// Per-env behaviour policy -> thresholds of the categorical draw (thread-local, runs once per env).
+template <int MODE, int DMAX>
+__device__ __forceinline__ void rollin_setup_env(const RollinParams& p, int env, int D, float* s_means,
+                                                 typename Thr<MODE>::type* s_thr) {
+  const uint64_t gid = p.env_id0 + (uint64_t)env;
+  for (int j = 0; j < D; ++j) s_means[j] = p.means[(size_t)env * D + j];
+  if (MODE == MODE_INJECT && p.in.actions != nullptr) return;  // action stream injected
+  int cov_idx, ridx;
+  double probs[DMAX];
+  if (MODE == MODE_INJECT) {
+    cov_idx = p.in.cov_idx[env];
+    ridx = p.in.rand_idx[env];
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j)
+      if (j < D) probs[j] = p.in.dir_probs[(size_t)env * D + j];
+  } else {
+    const uint4 w = philox_words(p.key, gid, 0, STREAM_ROLLIN_SETUP);
+    cov_idx = (int)bounded(w.x, 11);
+    ridx = (int)bounded(w.y, (uint32_t)D);
+    double sum = 0.0;
+#pragma unroll
+    for (int b = 0; b < (DMAX + 3) / 4; ++b) {
+      if (4 * b < D) {
+        const uint4 g = philox_words(p.key, gid, 1 + b, STREAM_ROLLIN_SETUP);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = 4 * b + i;
+          if (j < DMAX && j < D) {  // Gamma(1) = -log U; Dirichlet(1_d) = normalised gammas
+            probs[j] = (double)(-__logf(u32_open0(word_of(g, i))));
+            sum += probs[j];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j)
+      if (j < D) probs[j] = probs[j] / sum;
+    if (MODE == MODE_PHILOX_DUMP) {
+      if (p.out.cov_idx) p.out.cov_idx[env] = cov_idx;
+      if (p.out.rand_idx) p.out.rand_idx[env] = ridx;
+      if (p.out.dir_probs)
+        for (int j = 0; j < D; ++j) p.out.dir_probs[(size_t)env * D + j] = probs[j];
+    }
+  }
+  // probs = (1 - cov) * probs + cov * onehot(rand_index)   (collect_data.py:36), then
+  // cdf = cumsum(probs); cdf /= cdf[-1]                    (numpy RandomState.choice)
+  const double cov = c_cov_grid[cov_idx];
+  const double omc = __dsub_rn(1.0, cov);
+  double acc = 0.0;
+#pragma unroll
+  for (int j = 0; j < DMAX; ++j) {
+    if (j < D) {
+      const double pm = __dadd_rn(__dmul_rn(omc, probs[j]), __dmul_rn(cov, j == ridx ? 1.0 : 0.0));
+      acc = (j == 0) ? pm : __dadd_rn(acc, pm);
+      probs[j] = acc;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < DMAX - 1; ++j) {
+    if (j < D - 1) {
+      const double c = __ddiv_rn(probs[j], acc);
+      if (MODE == MODE_INJECT) {
+        s_thr[j] = c;
+      } else {  // u = k * 2^-31 exactly, so  cdf_j <= u  <=>  ceil(cdf_j * 2^31) <= k
+        s_thr[j] = (typename Thr<MODE>::type)ceil(c * 2147483648.0);
+      }
+    }
+  }
+}
+
+// CTA-level reduction of the return statistics: warp shuffles, then one double atomic per CTA and
+// statistic (the only cross-env operation of the whole path; shards on other GPUs add theirs via
+// the NCCL gather on the host side).
+__device__ __forceinline__ void reduce_stats(double* stats, float sr, float sr2, float nopt) {
+  __shared__ float s_part[3][RB_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sr += __shfl_xor_sync(0xffffffffu, sr, o);
+    sr2 += __shfl_xor_sync(0xffffffffu, sr2, o);
+    nopt += __shfl_xor_sync(0xffffffffu, nopt, o);
+  }
+  if (lane == 0) s_part[0][warp] = sr, s_part[1][warp] = sr2, s_part[2][warp] = nopt;
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double acc = 0.0;
+    for (int w = 0; w < RB_WARPS; ++w) acc += (double)s_part[threadIdx.x][w];
+    atomicAdd(stats + threadIdx.x, acc);
+  }
+}
+
+__device__ __forceinline__ int argmax_first(const float* m, int D) {
+  int best = 0;
+  for (int j = 1; j < D; ++j)
+    if (m[j] > m[best]) best = j;
+  return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast path: compile-time d (2d <= 32), H % 4 == 0, 16 B-aligned outputs.
+// ---------------------------------------------------------------------------------------------
+template <int D, int MODE>
+__global__ void __launch_bounds__(RB_THREADS) bandit_rollin_fast(const RollinParams p) {
+  using thr_t = typename Thr<MODE>::type;
+  __shared__ float s_means[RB_MAX_ENVS][D];
+  __shared__ thr_t s_thr[RB_MAX_ENVS][D];
+  __shared__ int s_opt[RB_MAX_ENVS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int env0 = blockIdx.x * p.envs_per_cta;
+  const int ne = min(p.envs_per_cta, p.N - env0);
+  const int H = p.H;
+
+  if (warp == 0) {
+    if (lane < ne) {
+      rollin_setup_env<MODE, D>(p, env0 + lane, D, s_means[lane], s_thr[lane]);
+      s_opt[lane] = argmax_first(s_means[lane], D);
+    }
+  } else {  // bandit state is the constant [1] (envs/bandit_env.py:38): dx = 1
+    const size_t b = (size_t)env0 * H, e = (size_t)(env0 + ne) * H;
+    fill_range(p.ctx_s, b, e, 1.0f, tid - 32, RB_THREADS - 32);
+    fill_range(p.ctx_ns, b, e, 1.0f, tid - 32, RB_THREADS - 32);
+  }
+  __syncthreads();
+
+  const int chunks = (H + 63) >> 6;
+  const bool inj_actions = (MODE == MODE_INJECT) && p.in.actions != nullptr;
+  float st_r = 0.f, st_r2 = 0.f, st_opt = 0.f;
+  for (int task = warp; task < ne * chunks; task += RB_WARPS) {
+    const int e = task / chunks, c = task - e * chunks;
+    const int env = env0 + e;
+    const int h0 = c * 64 + 2 * lane;
+    const size_t row = (size_t)env * H + h0;
+    int a0 = 0, a1 = 0;
+    float z0 = 0.f, z1 = 0.f;
+    if (MODE != MODE_INJECT) {
+      const uint4 w = philox_words(p.key, p.env_id0 + (uint64_t)env, (uint32_t)(c * 32 + lane), STREAM_ROLLIN_STEP);
+      const uint32_t k0 = w.x >> 1, k1 = w.y >> 1;
+#pragma unroll
+      for (int j = 0; j < D - 1; ++j) {
+        const uint32_t t = s_thr[e][j];
+        a0 += (k0 >= t);
+        a1 += (k1 >= t);
+      }
+      box_muller(w.z, w.w, z0, z1);
+      if (MODE == MODE_PHILOX_DUMP && h0 < H) {
+        if (p.out.u) {
+          p.out.u[row] = (double)k0 * 4.656612873077392578125e-10;
+          p.out.u[row + 1] = (double)k1 * 4.656612873077392578125e-10;
+        }
+        if (p.out.z) p.out.z[row] = z0, p.out.z[row + 1] = z1;
+        if (p.out.actions) p.out.actions[row] = a0, p.out.actions[row + 1] = a1;
+      }
+    } else if (h0 < H) {
+      if (inj_actions) {
+        a0 = p.in.actions[row];
+        a1 = p.in.actions[row + 1];
+      } else {  // searchsorted(cdf, u, side='right') = #{j : cdf_j <= u}
+        const double u0 = p.in.u[row], u1 = p.in.u[row + 1];
+#pragma unroll
+        for (int j = 0; j < D - 1; ++j) {
+          const double t = s_thr[e][j];
+          a0 += (t <= u0);
+          a1 += (t <= u1);
+        }
+      }
+      z0 = p.in.z[row];
+      z1 = p.in.z[row + 1];
+    }
+    // r = means[a] + var * z   (envs/bandit_env.py:59)
+    if (h0 < H) {
+      const float r0 = fmaf(p.var, z0, s_means[e][a0]);
+      const float r1 = fmaf(p.var, z1, s_means[e][a1]);
+      st_stream(reinterpret_cast<float2*>(p.ctx_r + row), make_float2(r0, r1));
+      if (p.stats) {
+        const int oa = s_opt[e];
+        st_r += r0 + r1;
+        st_r2 = fmaf(r0, r0, fmaf(r1, r1, st_r2));
+        st_opt += (float)((a0 == oa) + (a1 == oa));
+      }
+    }
+    // one-hot rows: lane l holds flat elements [2D*l, 2D*(l+1)) of this chunk as a 2D-bit mask
+    const uint32_t m = (1u << a0) | (1u << (D + a1));
+    float4* abase = reinterpret_cast<float4*>(p.ctx_a + ((size_t)env * H + (size_t)c * 64) * D);
+    const int n_valid4 = (min(64, H - c * 64) * D) >> 2;
+#pragma unroll
+    for (int it = 0; it < (16 * D + 31) / 32; ++it) {
+      const int q = it * 32 + lane;
+      const int e0 = 4 * q;
+      const int l0 = e0 / (2 * D);
+      const int off = e0 - l0 * (2 * D);
+      const uint32_t mlo = __shfl_sync(0xffffffffu, m, l0 & 31);
+      const uint32_t mhi = __shfl_sync(0xffffffffu, m, (l0 + 1) & 31);
+      const uint32_t bits = (uint32_t)(((((uint64_t)mhi) << (2 * D)) | mlo) >> off);
+      const float4 v = make_float4((bits & 1u) ? 1.f : 0.f, (bits & 2u) ? 1.f : 0.f, (bits & 4u) ? 1.f : 0.f,
+                                   (bits & 8u) ? 1.f : 0.f);
+      if (q < n_valid4) st_stream(abase + q, v);
+    }
+  }
+  if (p.stats) reduce_stats(p.stats, st_r, st_r2, st_opt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic path: runtime d <= 32, any H, any alignment.  One lane per step; the SAME Philox
+// counters as the fast path (pair index = h / 2, component by parity), so both paths draw
+// identical noise.  All stores are coalesced 4 B scalars.
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(RB_THREADS) bandit_rollin_generic(const RollinParams p) {
+  using thr_t = typename Thr<MODE>::type;
+  __shared__ float s_means[RB_MAX_ENVS][RB_MAX_D];
+  __shared__ thr_t s_thr[RB_MAX_ENVS][RB_MAX_D];
+  __shared__ int s_opt[RB_MAX_ENVS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int env0 = blockIdx.x * p.envs_per_cta;
+  const int ne = min(p.envs_per_cta, p.N - env0);
+  const int H = p.H, D = p.d;
+
+  if (tid < ne) {
+    rollin_setup_env<MODE, RB_MAX_D>(p, env0 + tid, D, s_means[tid], s_thr[tid]);
+    s_opt[tid] = argmax_first(s_means[tid], D);
+  }
+  for (size_t i = (size_t)env0 * H + tid; i < (size_t)(env0 + ne) * H; i += RB_THREADS) {
+    st_stream(p.ctx_s + i, 1.0f);
+    st_stream(p.ctx_ns + i, 1.0f);
+  }
+  __syncthreads();
+
+  const int chunks = (H + 31) >> 5;
+  const bool inj_actions = (MODE == MODE_INJECT) && p.in.actions != nullptr;
+  float st_r = 0.f, st_r2 = 0.f, st_opt = 0.f;
+  for (int task = warp; task < ne * chunks; task += RB_WARPS) {
+    const int e = task / chunks, c = task - e * chunks;
+    const int env = env0 + e;
+    const int h = c * 32 + lane;
+    const size_t row = (size_t)env * H + h;
+    int a = 0;
+    float z = 0.f;
+    if (MODE != MODE_INJECT) {
+      const uint4 w = philox_words(p.key, p.env_id0 + (uint64_t)env, (uint32_t)(h >> 1), STREAM_ROLLIN_STEP);
+      const uint32_t k = ((h & 1) ? w.y : w.x) >> 1;
+      for (int j = 0; j < D - 1; ++j) a += (k >= s_thr[e][j]);
+      float z0, z1;
+      box_muller(w.z, w.w, z0, z1);
+      z = (h & 1) ? z1 : z0;
+      if (MODE == MODE_PHILOX_DUMP && h < H) {
+        if (p.out.u) p.out.u[row] = (double)k * 4.656612873077392578125e-10;
+        if (p.out.z) p.out.z[row] = z;
+        if (p.out.actions) p.out.actions[row] = a;
+      }
+    } else if (h < H) {
+      if (inj_actions) {
+        a = p.in.actions[row];
+      } else {
+        const double u = p.in.u[row];
+        for (int j = 0; j < D - 1; ++j) a += (s_thr[e][j] <= u);
+      }
+      z = p.in.z[row];
+    }
+    if (h < H) {
+      const float r = fmaf(p.var, z, s_means[e][a]);
+      st_stream(p.ctx_r + row, r);
+      if (p.stats) st_r += r, st_r2 = fmaf(r, r, st_r2), st_opt += (float)(a == s_opt[e]);
+    }
+    const int nvalid = min(32, H - c * 32) * D;
+    float* abase = p.ctx_a + ((size_t)env * H + (size_t)c * 32) * D;
+    for (int it = 0; it < D; ++it) {
+      const int i = it * 32 + lane;
+      const int s = i / D;
+      const int as = __shfl_sync(0xffffffffu, a, s & 31);
+      if (i < nvalid) st_stream(abase + i, (i - s * D) == as ? 1.f : 0.f);
+    }
+  }
+  if (p.stats) reduce_stats(p.stats, st_r, st_r2, st_opt);
+}
+
+template <int MODE>
+static void launch_mode(const RollinParams& p, bool fast, int grid, cudaStream_t st) {
+  if (fast) {
+    switch (p.d) {
+#define DPT_CASE(DD)                                              \
+  case DD:                                                        \
+    bandit_rollin_fast<DD, MODE><<<grid, RB_THREADS, 0, st>>>(p); \
+    return;
+      DPT_CASE(2)
+      DPT_CASE(3)
+      DPT_CASE(4)
+      DPT_CASE(5)
+      DPT_CASE(6)
+      DPT_CASE(8)
+      DPT_CASE(10)
+      DPT_CASE(16)
+#undef DPT_CASE
+      default:
+        break;
+    }
+  }
+  bandit_rollin_generic<MODE><<<grid, RB_THREADS, 0, st>>>(p);
+}
+
+// envs per CTA: as many as 32, but few enough that the grid covers the machine several times
+// (8 resident CTAs/SM) and ends close to a whole number of waves.
+int rollin_envs_per_cta(int N) {
+  const int slots = sm_count() * 8;
+  int waves = 4;
+  int e = (N + slots * waves - 1) / (slots * waves);
+  if (e > RB_MAX_ENVS) e = RB_MAX_ENVS;
+  if (e < 1) e = 1;
+  return e;
+}
+
+}  // namespace dpt
+
+using namespace dpt;
+
+extern "C" int dpt_bandit_rollin(const float* means, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
+                                 float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
+                                 double* return_stats, const dpt_bandit_inject_t* inject,
+                                 const dpt_bandit_dump_t* dump, void* stream) {
+  DPT_CHECK_ARG(N >= 0 && H >= 0, "dpt_bandit_rollin: N=%d H=%d must be >= 0", N, H);
+  DPT_CHECK_ARG(d >= 1 && d <= RB_MAX_D, "dpt_bandit_rollin: d=%d outside [1,%d]", d, RB_MAX_D);
+  if (N == 0 || H == 0) return DPT_OK;
+  DPT_CHECK_ARG(means && ctx_states && ctx_actions && ctx_next_states && ctx_rewards,
+                "dpt_bandit_rollin: null means/context pointer");
+  RollinParams p{};
+  p.means = means;
+  p.var = var;
+  p.key = Key{(uint32_t)seed, (uint32_t)(seed >> 32)};
+  p.env_id0 = env_id0;
+  p.N = N, p.H = H, p.d = d;
+  p.ctx_s = ctx_states, p.ctx_a = ctx_actions, p.ctx_ns = ctx_next_states, p.ctx_r = ctx_rewards;
+  p.stats = return_stats;
+  p.envs_per_cta = rollin_envs_per_cta(N);
+  int mode = MODE_PHILOX;
+  if (inject) {
+    DPT_CHECK_ARG(!dump, "dpt_bandit_rollin: inject and dump are mutually exclusive");
+    DPT_CHECK_ARG(inject->z, "dpt_bandit_rollin: inject->z is required");
+    DPT_CHECK_ARG(inject->actions || (inject->cov_idx && inject->dir_probs && inject->rand_idx && inject->u),
+                  "dpt_bandit_rollin: inject needs actions or (cov_idx, dir_probs, rand_idx, u)");
+    p.in = *inject;
+    mode = MODE_INJECT;
+  } else if (dump) {
+    p.out = *dump;
+    mode = MODE_PHILOX_DUMP;
+  }
+  const bool fast = (H % 4 == 0) && 2 * d <= 32 && aligned16(ctx_states) && aligned16(ctx_actions) &&
+                    aligned16(ctx_next_states) && aligned16(ctx_rewards);
+  const int grid = (N + p.envs_per_cta - 1) / p.envs_per_cta;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == MODE_PHILOX)
+    launch_mode<MODE_PHILOX>(p, fast, grid, st);
+  else if (mode == MODE_PHILOX_DUMP)
+    launch_mode<MODE_PHILOX_DUMP>(p, fast, grid, st);
+  else
+    launch_mode<MODE_INJECT>(p, fast, grid, st);
+  DPT_LAUNCH_CHECK();
+  return DPT_OK;
+}

@@ -1,0 +1,79 @@
+// Shared host/device helpers for libdpt_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/dpt_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libdpt_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace dpt {
+
+void set_error(const char* fmt, ...);
+int sm_count();
+
+#define DPT_CHECK_ARG(cond, ...)                \
+  do {                                          \
+    if (!(cond)) {                              \
+      dpt::set_error(__VA_ARGS__);              \
+      return DPT_ERR_INVALID_ARG;               \
+    }                                           \
+  } while (0)
+
+#define DPT_CUDA(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (call);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      dpt::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return DPT_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+#define DPT_LAUNCH_CHECK()                                                              \
+  do {                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      dpt::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return DPT_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+#ifdef __CUDACC__
+// Streaming (write-once) stores: keep them out of L1, they are never re-read by this kernel.
+__device__ __forceinline__ void st_stream(float4* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_stream(float2* p, float2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_stream(float* p, float v) {
+  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// Fill out[begin, end) (float indices relative to a 16B-aligned base) with `v`, cooperatively
+// by `nthreads` threads: scalar head/tail, float4 body.
+__device__ __forceinline__ void fill_range(float* base, size_t begin, size_t end, float v, int tid, int nthreads) {
+  size_t b4 = (begin + 3) & ~size_t(3);
+  size_t e4 = end & ~size_t(3);
+  if (b4 >= e4) {
+    for (size_t i = begin + tid; i < end; i += nthreads) st_stream(base + i, v);
+    return;
+  }
+  if (tid < (int)(b4 - begin)) st_stream(base + begin + tid, v);
+  if (tid < (int)(end - e4)) st_stream(base + e4 + tid, v);
+  float4 v4 = make_float4(v, v, v, v);
+  float4* p = reinterpret_cast<float4*>(base + b4);
+  size_t n4 = (e4 - b4) >> 2;
+  for (size_t i = tid; i < n4; i += nthreads) st_stream(p + i, v4);
+}
+#endif
+
+}  // namespace dpt

@@ -1,0 +1,73 @@
+"""GPUBanditEnv with the reference's interface (envs/gpu_bandit_env.py:8-82).
+
+The reference's step is ~6 small ATen launches plus a host sync on ``current_step.max()`` (:67);
+here the constructor is one launch (means + argmax + one-hot) and a step is ONE launch
+(argmax -> gather -> Philox normal / Bernoulli) with the step counter kept on the host, so there is
+no device->host synchronisation on the step path.
+"""
+import torch
+
+from .. import kernels, rng
+from .base_env import BaseEnv
+
+_TYPES = {"uniform": 0, "bernoulli": 1}
+
+
+class GPUBanditEnv(BaseEnv):
+    def __init__(self, dims, n_envs, H, var=0.0, type="uniform", device=None, seed=None, env_id0=0):
+        if type not in _TYPES:
+            raise NotImplementedError
+        self.dims = dims
+        self.dim = dims
+        self.n_envs = n_envs
+        self._device = kernels._dev(device)
+        self._key = rng.next_key() if seed is None else seed
+        self._env_id0 = env_id0
+        with torch.cuda.device(self._device):
+            # uniform: U[0,1) like torch.rand (:19); bernoulli: Beta(1,1) == U(0,1) (:21)
+            self.means, self.opt_a_index, self.opt_a = kernels.bandit_sample_means(n_envs, dims, self._key, env_id0,
+                                                                                   self._device)
+        self.opt_a_index = self.opt_a_index.long()
+        self.H_context = H
+        self.H = H
+        self.var = var
+        self.dx = 1
+        self.du = dims
+        self.topk = False
+        self.type = type
+        self.state = torch.ones((n_envs, 1), device=self._device)
+        self.current_step = torch.zeros(n_envs, device=self._device)
+        self._step = 0        # host mirror of current_step (all envs advance together)
+        self._draws = 0
+
+    def get_arm_value(self, actions):
+        return torch.sum(self.means * actions, dim=1)
+
+    def reset(self):
+        self.current_step = torch.zeros(self.n_envs, device=self._device)
+        self._step = 0
+        return self.state.detach()
+
+    def transit(self, x, us, inject=None):
+        us = us.to(self._device) if us.device != self._device else us
+        with torch.cuda.device(self._device):
+            r = kernels.gpu_bandit_step(self.means, us, float(self.var), _TYPES[self.type], self._key ^ 0x5DEECE66D,
+                                        self._env_id0, self._draws, inject=inject)
+        self._draws += 1
+        return self.state.detach(), r
+
+    def step(self, actions):
+        if self._step >= self.H:
+            raise ValueError("Episode has already ended")
+        _, r = self.transit(self.state, actions)
+        self._step += 1
+        self.current_step += 1
+        done = self.current_step >= self.H
+        return self.state.detach(), r, done, {}
+
+    def deploy_eval(self, ctrl):
+        tmp = self.var
+        self.var = 0.0
+        res = self.deploy(ctrl)
+        self.var = tmp
+        return res

@@ -1,0 +1,236 @@
+/*
+ * dpt_b200.h -- C ABI of the B200-native DPT rollout hot path (libdpt_b200.so).
+ *
+ * The reference (titanium-47/decision-pretrained-transformer) is 100 % Python and has no
+ * FFI layer; the drop-in boundary is its duck-typed Python API.  This header
+ * is the thin C ABI the Python mirror classes call through ctypes.  Every entry point cites
+ * the reference interface it replaces (file:line relative to the reference root).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; buffers are owned by
+ *     the caller (PyTorch); the library never allocates except opaque model handles;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it,
+ *     there are no hidden synchronisations;
+ *   - return value: 0 = ok, <0 = error (DPT_ERR_*); dpt_last_error() gives a thread-local
+ *     message; nothing throws or aborts;
+ *   - context tensors use the reference consumer's fp32 layout (dataset.py:54-61,
+ *     utils.py:193-197): [N,H,dx], [N,H,du], [N,H,dx], [N,H,1] row-major;
+ *   - randomness: Philox4x32-10, key = seed, counter = (index, env_lo, env_hi, stream) with the
+ *     GLOBAL env id (env_id0 + i), so results do not depend on launch geometry or on how the
+ *     env range is sharded over GPUs.  Every randomised entry point has an `inject` argument
+ *     (consume caller-provided noise instead -- used for parity against the reference) and a
+ *     `dump` argument (write out the noise that was used).
+ */
+#ifndef DPT_B200_H
+#define DPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPT_OK 0
+#define DPT_ERR_INVALID_ARG (-1)
+#define DPT_ERR_CUDA (-2)
+#define DPT_ERR_UNSUPPORTED (-3)
+
+#define DPT_ABI_VERSION 1
+
+int dpt_version(void);
+const char* dpt_last_error(void);
+/* sm count / compute capability of the current device (fails loudly if there is none). */
+int dpt_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------- E1: task draw ------------
+ * envs/bandit_env.py:10-18 (sample) + :29-34 (BanditEnv.__init__ argmax / one-hot) and
+ * envs/gpu_bandit_env.py:18-28.  means ~ U[0,1)^d (24-bit, fp32-exact).
+ * opt_a_index [N] int32 and opt_a [N,d] fp32 one-hot may be NULL. */
+int dpt_bandit_sample_means(uint64_t seed, uint64_t env_id0, int N, int d, float* means,
+                            int32_t* opt_a_index, float* opt_a, void* stream);
+/* argmax / one-hot for caller-provided means (BanditEnv.__init__, LinearBanditEnv.__init__ :162-165). */
+int dpt_bandit_opt_action(const float* means, int N, int d, int32_t* opt_a_index, float* opt_a, void* stream);
+
+/* ---------------------------------------------------------------- R1: rollin_bandit --------
+ * collect_data.py:23-53 fused with envs/bandit_env.py:56-64 (transit) for N envs x H steps.
+ * inject: either `actions` (int32 [N,H]) or all of (cov_idx [N], dir_probs f64 [N,d],
+ * rand_idx [N], u f64 [N,H]); `z` fp32 [N,H] always.  dump: any subset, NULL = skip.
+ * return_stats: NULL or f64 [3], += (sum of rewards, sum of squared rewards, number of pulls of
+ * the optimal arm) over all N*H env-steps (caller zeroes it; atomics, so shards may share it) --
+ * the small per-shard statistic that is gathered over NCCL in the multi-GPU collection. */
+typedef struct {
+  const int32_t* cov_idx;
+  const double* dir_probs;
+  const int32_t* rand_idx;
+  const double* u;
+  const int32_t* actions;
+  const float* z;
+} dpt_bandit_inject_t;
+
+typedef struct {
+  int32_t* cov_idx;
+  double* dir_probs;
+  int32_t* rand_idx;
+  double* u;
+  int32_t* actions;
+  float* z;
+} dpt_bandit_dump_t;
+
+int dpt_bandit_rollin(const float* means, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
+                      float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
+                      double* return_stats, const dpt_bandit_inject_t* inject, const dpt_bandit_dump_t* dump,
+                      void* stream);
+
+/* Host-buffer form of the same call (the e2e path): means_host [N,d] in, the four context
+ * arrays out, all HOST pointers (pinned for full speed).  Uses `scratch` (device, at least
+ * dpt_bandit_rollin_host_scratch_bytes(...) bytes) for double-buffered chunks so the D2H copies
+ * overlap the kernel.  Synchronises `stream` before returning. */
+uint64_t dpt_bandit_rollin_host_scratch_bytes(int N, int H, int d);
+int dpt_bandit_rollin_host(const float* means_host, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
+                           float* ctx_states_host, float* ctx_actions_host, float* ctx_next_states_host,
+                           float* ctx_rewards_host, void* scratch, uint64_t scratch_bytes, void* stream);
+
+/* ---------------------------------------------------------------- R3/R4: rollin_mdp --------
+ * collect_data.py:83-111 (rollin_mdp) fused with envs/darkroom_env.py:37-55 (transit), :69-82
+ * (opt_action), :96-111 (permuted variant) and collect_data.py:200-201 (query state + optimal
+ * action, n_samples per env).  goals int32 [N,2]; perm_index int32 [N] or NULL;
+ * mode 0 = 'uniform', 1 = 'expert'. */
+typedef struct {
+  const int32_t* states;   /* [N,H,2]  (uniform mode) */
+  const int32_t* actions;  /* [N,H]    (uniform mode) */
+  const int32_t* query;    /* [N,S,2] */
+} dpt_darkroom_inject_t;
+
+typedef struct {
+  int32_t* states;
+  int32_t* actions;
+  int32_t* query;
+} dpt_darkroom_dump_t;
+
+int dpt_darkroom_rollin(const int32_t* goals, const int32_t* perm_index, int dim, int mode, uint64_t seed,
+                        uint64_t env_id0, int N, int H, int n_samples, float* ctx_states, float* ctx_actions,
+                        float* ctx_next_states, float* ctx_rewards, float* query_states, float* optimal_actions,
+                        const dpt_darkroom_inject_t* inject, const dpt_darkroom_dump_t* dump, void* stream);
+
+/* One batched transition: DarkroomEnvVec.step (envs/darkroom_env.py:126-133 -> :57-64 -> :37-55).
+ * states int32 [N,2], actions fp32 one-hot [N,5] -> next_states int32 [N,2], rewards int32 [N]. */
+int dpt_darkroom_step(const int32_t* states, const float* actions, const int32_t* goals, const int32_t* perm_index,
+                      int dim, int N, int32_t* next_states, int32_t* rewards, void* stream);
+/* Batched DarkroomEnv.opt_action (envs/darkroom_env.py:69-82, :105-111): fp32 one-hot [N,5]. */
+int dpt_darkroom_opt_action(const int32_t* states, const int32_t* goals, const int32_t* perm_index, int N,
+                            float* actions, void* stream);
+
+/* ---------------------------------------------------------------- E5: GPUBanditEnv.step ----
+ * envs/gpu_bandit_env.py:53-63 (transit) in one launch: a = argmax(actions), r = means[a] +
+ * var * z (type 0, 'uniform') or Bernoulli(means[a]) (type 1).  `step` is the env's step
+ * counter (part of the Philox counter).  inject_noise: fp32 [N] standard normals (type 0) or
+ * uniforms in [0,1) (type 1); dump_noise likewise. */
+int dpt_gpu_bandit_step(const float* means, const float* actions, float var, int type, uint64_t seed,
+                        uint64_t env_id0, int64_t step, int N, int d, float* reward, const float* inject_noise,
+                        float* dump_noise, void* stream);
+
+/* ---------------------------------------------------------------- K2-K4 stats --------------
+ * Per-(env, arm) reward sums and pull counts of an arbitrary context prefix
+ * (ctrls/ctrl_bandit.py:95-104, :165-177, :355-364): ctx_actions fp32 [N,Hs,d] (row stride Hs
+ * steps, first h used), ctx_rewards fp32 [N,Hs,1] -> sums f64 [N,d], counts int32 [N,d]. */
+int dpt_arm_stats(const float* ctx_actions, const float* ctx_rewards, int N, int h, int H_stride, int d,
+                  double* sums, int32_t* counts, void* stream);
+
+/* ---------------------------------------------------------------- L1: deploy_online_vec ----
+ * evals/eval_bandit.py:56-103 fused with BanditEnvVec.deploy/step (envs/bandit_env.py:98-149) and
+ * the controller's set_batch_numpy_vec/act_numpy_vec, all H steps in ONE launch.
+ * ctrl kinds and the reference classes they replace (ctrls/ctrl_bandit.py):
+ *   0 OptPolicy :22-38 | 1 EmpMeanPolicy :57-118 (p0 = online flag) | 2 UCBPolicy :318-380 (p0 = const)
+ *   3 ThompsonSamplingPolicy sample=True :122-251 (p0 = std, p1 = prior_mean, p2 = prior_var)
+ *   4 LinUCBPolicy :447-528 (p0 = const; arms f64 [d,lin_d])
+ * Outputs: ctx_* (any may be NULL = not materialised), cum_means fp32 [H,N] (expected reward of
+ * the chosen arm, envs/bandit_env.py:151-153), regret_sums f64 [H,2] += (sum, sum of squares)
+ * over envs of (max(means) - cum_means) (evals/eval_bandit.py:169-178; NULL = skip; must be
+ * zeroed by the caller; accumulated with atomics so shards can share it). */
+typedef struct {
+  const float* reward_z;     /* [H,N] standard normals, env order per step (eval loop order) */
+  const float* ctrl_z;       /* Thompson: [H,N,d] standard normals */
+  const int32_t* first_arm;  /* LinUCB: [N] arm pulled at h = 0 */
+} dpt_online_inject_t;
+
+typedef struct {
+  float* reward_z;
+  float* ctrl_z;
+  int32_t* first_arm;
+} dpt_online_dump_t;
+
+int dpt_online_loop(int ctrl_kind, double p0, double p1, double p2, const float* means, const double* arms,
+                    int lin_d, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d, float* ctx_states,
+                    float* ctx_actions, float* ctx_next_states, float* ctx_rewards, float* cum_means,
+                    double* regret_sums, const dpt_online_inject_t* inject, const dpt_online_dump_t* dump,
+                    void* stream);
+
+/* ---------------------------------------------------------------- M1: Transformer ----------
+ * models/net.py:9-60 (GPT2Model trunk with n_head = 1, embed_transition, pred_actions).
+ * Weights are fp32 device pointers in the reference state_dict layout; they are repacked once
+ * into the handle. */
+typedef struct {
+  int horizon, state_dim, action_dim, n_layer, n_embd, n_positions;
+  const float* wpe;                 /* [n_positions, E] */
+  const float* embed_w;             /* embed_transition.weight [E, 2dx+du+1] */
+  const float* embed_b;             /* [E] */
+  const float* pred_w;              /* pred_actions.weight [du, E] */
+  const float* pred_b;              /* [du] */
+  const float* lnf_w;
+  const float* lnf_b;
+  /* per layer arrays of n_layer pointers (HOST arrays of DEVICE pointers) */
+  const float* const* ln1_w;
+  const float* const* ln1_b;
+  const float* const* attn_w;       /* c_attn.weight [E, 3E] */
+  const float* const* attn_b;       /* [3E] */
+  const float* const* proj_w;       /* attn.c_proj.weight [E, E] */
+  const float* const* proj_b;
+  const float* const* ln2_w;
+  const float* const* ln2_b;
+  const float* const* fc_w;         /* mlp.c_fc.weight [E, 4E] */
+  const float* const* fc_b;
+  const float* const* fc2_w;        /* mlp.c_proj.weight [4E, E] */
+  const float* const* fc2_b;
+} dpt_gpt2_weights_t;
+
+typedef struct dpt_gpt2 dpt_gpt2_t;
+
+int dpt_gpt2_create(const dpt_gpt2_weights_t* w, dpt_gpt2_t** out, void* stream);
+int dpt_gpt2_destroy(dpt_gpt2_t* m);
+
+/* Transformer.forward(x) (models/net.py:41-60): query_states [B,dx], context_* [B,T,.] fp32,
+ * context row stride `T_stride` steps (so views context[:, :h] of a [B,H,.] buffer can be passed
+ * without a copy, as evals/eval_bandit.py:71-76 does).  test != 0 -> out [B,du] (last position);
+ * test == 0 -> out [B,T,du] (positions 1..T).  precision: 0 = fp32, 1 = bf16 tensor-core
+ * contractions (fp32 accumulate). */
+int dpt_gpt2_forward(dpt_gpt2_t* m, const float* query_states, const float* ctx_states, const float* ctx_actions,
+                     const float* ctx_next_states, const float* ctx_rewards, int B, int T, int T_stride, int test,
+                     int precision, float* out, void* stream);
+
+/* Fused bandit online loop with the transformer controller: evals/eval_bandit.py:56-103 +
+ * ctrls/ctrl_bandit.py:383-444 (BanditTransformerController, sample != 0 -> softmax + categorical
+ * draw, else argmax) + env step, with a per-env KV cache (valid because the bandit query token is
+ * constant).  kv_cache: device scratch of dpt_gpt2_online_kv_bytes(...) bytes.
+ * inject: reward_z [H,N] fp32, ctrl_u f64 [H,N] (uniforms of the categorical draw). */
+typedef struct {
+  const float* reward_z;
+  const double* ctrl_u;
+} dpt_gpt2_online_inject_t;
+
+typedef struct {
+  float* reward_z;
+  double* ctrl_u;
+  float* logits;   /* [H,N,du] logits the controller saw at each step */
+} dpt_gpt2_online_dump_t;
+
+uint64_t dpt_gpt2_online_kv_bytes(const dpt_gpt2_t* m, int N, int H, int precision);
+int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, float var, int sample, uint64_t seed, uint64_t env_id0,
+                         int N, int H, int precision, void* kv_cache, uint64_t kv_bytes, float* ctx_states,
+                         float* ctx_actions, float* ctx_next_states, float* ctx_rewards, float* cum_means,
+                         double* regret_sums, const dpt_gpt2_online_inject_t* inject,
+                         const dpt_gpt2_online_dump_t* dump, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPT_B200_H */

@@ -28,11 +28,13 @@ DARKROOM_PERMS = list(itertools.permutations(range(5)))     # envs/darkroom_env.
 class GlobalNoise:
     """numpy legacy global stream, same calls as the reference; records every draw."""
 
-    def __init__(self):
+    def __init__(self, record=True):
         self.rec = {}
+        self.record = record
 
     def _r(self, name, v):
-        self.rec.setdefault(name, []).append(np.array(v))
+        if self.record:
+            self.rec.setdefault(name, []).append(np.array(v))
         return v
 
     def choice_index(self, n, name):            # np.random.choice(a) without p -> randint(0, len(a))

@@ -72,3 +72,46 @@ def bandit_means(seed, env_ids, dim):
     env_ids = np.asarray(env_ids, dtype=np.uint64)
     w = words(seed, env_ids[:, None], np.arange(nb)[None, :], STREAM_TASK)  # [N, nb, 4]
     return u24(w.reshape(len(env_ids), nb * 4)[:, :dim])
+
+
+def rollin_setup_ints(seed, env_ids, dim):
+    """cov_idx in [0,11) and rand_idx in [0,dim) of rollin_bandit (block 0 of STREAM_ROLLIN_SETUP)."""
+    w = words(seed, env_ids, 0, STREAM_ROLLIN_SETUP)
+    return mulhi(w[..., 0], 11), mulhi(w[..., 1], dim)
+
+
+def rollin_step_k(seed, env_ids, H):
+    """31-bit integers k of the per-step categorical uniforms u = k * 2^-31: pair p = h // 2 of
+    STREAM_ROLLIN_STEP, word 0 for even h, word 1 for odd h.  Returns [N,H] int64."""
+    env_ids = np.asarray(env_ids, dtype=np.uint64)
+    npair = (H + 1) // 2
+    w = words(seed, env_ids[:, None], np.arange(npair)[None, :], STREAM_ROLLIN_STEP)   # [N, npair, 4]
+    k = (w[..., :2] >> np.uint32(1)).reshape(len(env_ids), 2 * npair)[:, :H]
+    return k.astype(np.int64)
+
+
+def split_word(w, dim):
+    """One word -> (x, y, a): successive digits of w / 2^32 in the mixed radix (dim, dim, 5)."""
+    w = np.asarray(w).astype(np.uint64)
+    t = w * np.uint64(dim)
+    x = t >> np.uint64(32)
+    t = (t & MASK) * np.uint64(dim)
+    y = t >> np.uint64(32)
+    a = ((t & MASK) * np.uint64(5)) >> np.uint64(32)
+    return x.astype(np.int64), y.astype(np.int64), a.astype(np.int64)
+
+
+def darkroom_draws(seed, env_ids, H, dim):
+    """(states [N,H,2], actions [N,H]) of the 'uniform' rollin: word h % 4 of block h // 4."""
+    env_ids = np.asarray(env_ids, dtype=np.uint64)
+    nb = (H + 3) // 4
+    w = words(seed, env_ids[:, None], np.arange(nb)[None, :], STREAM_DARKROOM_STEP).reshape(len(env_ids), nb * 4)[:, :H]
+    x, y, a = split_word(w, dim)
+    return np.stack([x, y], -1), a
+
+
+def darkroom_query(seed, env_ids, n_samples, dim):
+    env_ids = np.asarray(env_ids, dtype=np.uint64)
+    w = words(seed, env_ids[:, None], np.arange(n_samples)[None, :], STREAM_DARKROOM_QUERY)[..., 0]
+    x, y, _ = split_word(w, dim)
+    return np.stack([x, y], -1)

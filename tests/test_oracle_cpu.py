@@ -1,0 +1,148 @@
+"""CPU tier: the oracle against the golden vectors produced from the live reference
+(oracle/make_golden.py), the Philox known-answer vectors, and the host-side logic."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import dpt_oracle as O
+from oracle import philox as P
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors for philox4x32_10
+    kat = [([0, 0, 0, 0], (0, 0), [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 4, (0xffffffff, 0xffffffff), [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], (0xa4093822, 0x299f31d0),
+            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, want in kat:
+        assert [int(x) for x in P.philox4x32_10(np.array(ctr, dtype=np.uint64), key)] == want
+
+
+def test_philox_bounded_draws_in_range():
+    st, a = P.darkroom_draws(3, np.arange(50), 37, 10)
+    assert st.min() >= 0 and st.max() <= 9 and a.min() >= 0 and a.max() <= 4
+    assert len(np.unique(st[..., 0])) == 10 and len(np.unique(a)) == 5
+    m = P.bandit_means(0, np.arange(1000), 5)
+    assert m.min() >= 0 and m.max() < 1 and abs(m.mean() - 0.5) < 0.02
+    assert np.array_equal(m.astype(np.float32).astype(np.float64), m)   # fp32-exact
+
+
+@pytest.mark.parametrize("name", ["bandit_rollin_d5", "bandit_rollin_d10", "bandit_rollin_d3"])
+def test_bandit_rollin_golden(name):
+    g = golden(name)
+    n, H = g["u"].shape
+    # loop form through ReplayNoise
+    noise = O.ReplayNoise({"cov_idx": g["cov_idx"], "dir_probs": g["dir_probs"], "rand_idx": g["rand_idx"],
+                           "u": g["u"].reshape(-1), "z": g["z"].reshape(-1)})
+    for e in range(n):
+        xs, us, xps, rs = O.rollin_bandit(g["means"][e], H, float(g["var"]), noise)
+        assert np.array_equal(us, g["ref_actions"][e]) and np.array_equal(rs, g["ref_rewards"][e])
+        assert np.array_equal(xs, g["ref_states"][e]) and xs.dtype == np.int64
+        assert np.array_equal(O.opt_action(g["means"][e]), g["ref_optimal_action"][e])
+    # vectorised form
+    xs, us, xps, rs, acts = O.rollin_bandit_batch(g["means"], float(g["var"]), g["cov_idx"], g["dir_probs"],
+                                                  g["rand_idx"], g["u"], g["z"])
+    assert np.array_equal(us, g["ref_actions"]) and np.array_equal(rs, g["ref_rewards"])
+
+
+@pytest.mark.parametrize("name", ["darkroom_uniform", "darkroom_expert", "darkroom_perm_uniform", "darkroom_perm_expert"])
+def test_darkroom_golden(name):
+    g = golden(name)
+    goals, H, dim = g["goals"], int(g["H"]), int(g["dim"])
+    perms = g["perm_indices"] if len(g["perm_indices"]) else None
+    mode = str(g["rollin_type"])
+    arrays = {"query": g["query"]}
+    if mode == "uniform":
+        arrays.update(state=g["state"].reshape(-1, 2), action=g["action"].reshape(-1))
+    # per-env replay: noise order is env-major (rollin then query)
+    for e in range(len(goals)):
+        a = {"query": g["query"][e:e + 1]}
+        if mode == "uniform":
+            a.update(state=g["state"][e], action=g["action"][e])
+        t = O.generate_mdp_histories([goals[e]], dim, H, mode, O.ReplayNoise(a),
+                                     None if perms is None else [perms[e]])[0]
+        assert np.array_equal(t["context_states"], g["ref_states"][e])
+        assert np.array_equal(t["context_actions"].argmax(-1), g["ref_actions"][e])
+        assert np.array_equal(t["context_next_states"], g["ref_next_states"][e])
+        assert np.array_equal(t["context_rewards"], g["ref_rewards"][e])
+        assert t["optimal_action"].argmax() == g["ref_optimal_action"][e]
+    if mode == "uniform":   # vectorised transit
+        pt = None if perms is None else np.asarray(O.DARKROOM_PERMS)[perms][:, None, :]
+        ns, r = O.darkroom_transit_batch(g["state"], g["action"], goals[:, None, :], dim, pt)
+        assert np.array_equal(ns, g["ref_next_states"]) and np.array_equal(r, g["ref_rewards"])
+
+
+def test_darkroom_exhaustive_table():
+    g = golden("darkroom_table")
+    dim = int(g["dim"])
+    assert np.array_equal(g["perm_table"], np.asarray(O.DARKROOM_PERMS))
+    xs, ys, acts = np.meshgrid(np.arange(dim), np.arange(dim), np.arange(5), indexing="ij")
+    st = np.stack([xs, ys], -1)
+    for i, goal in enumerate(g["goals"]):
+        ns, r = O.darkroom_transit_batch(st, acts, goal, dim)
+        assert np.array_equal(ns, g["next_state"][i]) and np.array_equal(r, g["reward"][i])
+    for i, pi in enumerate(g["perms"]):
+        ns, r = O.darkroom_transit_batch(st, acts, [dim - 1, dim - 1], dim, np.asarray(O.DARKROOM_PERMS[pi]))
+        assert np.array_equal(ns, g["p_next_state"][i]) and np.array_equal(r, g["p_reward"][i])
+
+
+@pytest.mark.parametrize("name,ctrls", [("online_d5_n200", ["opt", "emp", "emp_offline", "ucb", "thompson"]),
+                                        ("online_d10_n16", ["opt", "emp", "thompson"])])
+def test_online_golden(name, ctrls):
+    g = golden(name)
+    means, H, var = g["means"], int(g["H"]), float(g["var"])
+    N, d = means.shape
+    mk = {"opt": lambda: O.OptCtrl(means), "emp": lambda: O.EmpMeanCtrl(d, online=True),
+          "emp_offline": lambda: O.EmpMeanCtrl(d, online=False), "ucb": lambda: O.UCBCtrl(d, 1.0),
+          "thompson": lambda: O.ThompsonCtrl(d, std=var, sample=True, prior_mean=.5, prior_var=1 / 12.0)}
+    for c in ctrls:
+        arrays = {"reward_z": g[c + "_reward_z"]}
+        if c == "thompson":
+            arrays["thompson_z"] = g[c + "_thompson_z"]
+        cum, meta = O.deploy_online_vec(means, var, H, mk[c](), O.ReplayNoise(arrays))
+        assert np.array_equal(meta["context_actions"].argmax(-1), g[c + "_actions"]), c
+        assert np.array_equal(meta["context_rewards"][:, :, 0], g[c + "_rewards"]), c
+        assert np.array_equal(cum, g[c + "_cum_means"]), c
+
+
+def test_linear_bandit_golden():
+    g = golden("linear_bandit")
+    arms, means, H, var = g["arms"], g["means"], int(g["H"]), float(g["var"])
+    assert np.array_equal(arms, O.linear_bandit_arms(*arms.shape))
+    assert np.array_equal(means, np.stack([arms @ t for t in g["thetas"]]))
+    cum, meta = O.deploy_online_vec(means, var, H, O.ThompsonCtrl(arms.shape[0], std=var, sample=True, prior_mean=0.0, prior_var=1.0),
+                                    O.ReplayNoise({"reward_z": g["thompson_reward_z"], "thompson_z": g["thompson_thompson_z"]}))
+    assert np.array_equal(meta["context_actions"].argmax(-1), g["thompson_actions"])
+    assert np.array_equal(meta["context_rewards"][:, :, 0], g["thompson_rewards"])
+    cum, meta = O.deploy_online_vec(means, var, H, O.LinUCBCtrl(arms, 1.0),
+                                    O.ReplayNoise({"reward_z": g["linucb_reward_z"], "linucb_first": g["linucb_first"][None]}))
+    assert np.array_equal(meta["context_actions"].argmax(-1), g["linucb_actions"])
+    assert np.array_equal(cum, g["linucb_cum_means"])
+
+
+@pytest.mark.parametrize("name", ["transformer_l2", "transformer_l4"])
+def test_transformer_forward_golden(name):
+    g = golden(name)
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
+    H, L, d = int(g["H"]), int(g["n_layer"]), int(g["d"])
+    acts, rew = g["fwd_actions"].astype(np.int64), g["fwd_rewards"]
+    B = acts.shape[0]
+    ca, cs, q = np.eye(d)[acts], np.ones((B, H, 1)), np.ones((B, 1))
+    for t in (0, 1, 5, H):
+        o = O.transformer_forward(sd, q, cs[:, :t], ca[:, :t], cs[:, :t], rew[:, :t], L, test=True)
+        ref = g["logits_t%d" % t]
+        assert np.abs(o - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+        if t > 0:
+            o = O.transformer_forward(sd, q, cs[:, :t], ca[:, :t], cs[:, :t], rew[:, :t], L, test=False)
+            ref = g["logits_all_t%d" % t]
+            assert o.shape == ref.shape and np.abs(o - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_regret_stats_match_scipy():
+    import scipy.stats
+    rng = np.random.RandomState(0)
+    opt, alg = rng.rand(50, 20), rng.rand(50, 20)
+    m, s, cm, cs = O.regret_stats(opt, alg)
+    diff = opt - alg
+    assert np.allclose(m, diff.mean(0)) and np.allclose(s, scipy.stats.sem(diff, axis=0))
+    assert np.allclose(cs, scipy.stats.sem(np.cumsum(diff, axis=1), axis=0))
