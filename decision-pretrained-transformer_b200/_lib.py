@@ -80,7 +80,7 @@ PROTOTYPES = {
     "dpt_gpu_bandit_step": (c_int, [c_void_p, c_void_p, c_float, c_int, c_uint64, c_uint64, c_int64, c_int, c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "dpt_arm_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "dpt_online_loop": (c_int, [c_int, c_double, c_double, c_double, c_void_p, c_void_p, c_int, c_float, c_uint64,
+    "dpt_online_loop": (c_int, [c_int, c_double, c_double, c_double, c_void_p, c_void_p, c_int, c_double, c_uint64,
                                 c_uint64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, POINTER(OnlineInject), POINTER(OnlineDump), c_void_p]),
     "dpt_gpt2_create": (c_int, [POINTER(Gpt2Weights), POINTER(c_void_p), c_void_p]),
@@ -88,7 +88,7 @@ PROTOTYPES = {
     "dpt_gpt2_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p, c_void_p]),
     "dpt_gpt2_online_kv_bytes": (c_uint64, [c_void_p, c_int, c_int, c_int]),
-    "dpt_gpt2_online_loop": (c_int, [c_void_p, c_void_p, c_float, c_int, c_uint64, c_uint64, c_int, c_int, c_int,
+    "dpt_gpt2_online_loop": (c_int, [c_void_p, c_void_p, c_double, c_int, c_uint64, c_uint64, c_int, c_int, c_int,
                                      c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      POINTER(Gpt2OnlineInject), POINTER(Gpt2OnlineDump), c_void_p]),
 }

@@ -159,3 +159,51 @@ def generate_darkroom_permuted_histories(indices, dim, horizon, **kwargs):
     from .envs import darkroom_env
     envs = [darkroom_env.DarkroomEnvPermuted(dim, index, horizon) for index in indices]
     return generate_mdp_histories_from_envs(envs, **kwargs)
+
+
+# --------------------------------------------------------------------------- linear bandit ----
+def rollin_linear_bandit_vec(envs):
+    """collect_data.py:56-80: Thompson(prior_mean=0, prior_var=1, std=env.var, sample=True) driven
+    through deploy_online_vec with include_meta=True -- here one fused launch."""
+    from .ctrls.ctrl_bandit import ThompsonSamplingPolicy
+    from .envs import bandit_env
+    from .evals import eval_bandit
+    H = envs[0].H_context
+    thmp = ThompsonSamplingPolicy(envs[0], std=envs[0].var, sample=True, prior_mean=0.0, prior_var=1.0,
+                                  warm_start=False, batch_size=len(envs))
+    vec_env = bandit_env.BanditEnvVec(envs)
+    _, meta = eval_bandit.deploy_online_vec(vec_env, thmp, H, include_meta=True)
+    return (meta["context_states"], meta["context_actions"], meta["context_next_states"],
+            meta["context_rewards"][:, :, 0])
+
+
+def generate_linear_bandit_histories(n_envs, dim, lin_d, horizon, var, **kwargs):
+    """collect_data.py:228-284.  (The reference reads n_hists / n_samples from module globals set in
+    __main__, :241,:268 vs :363-364; here they are keyword arguments with the same names.)"""
+    from .envs import bandit_env
+    n_hists, n_samples = kwargs.get("n_hists", 1), kwargs.get("n_samples", 1)
+    data_type = kwargs["data_type"]
+    arms = np.random.RandomState(seed=1234).normal(size=(dim, lin_d)) / np.sqrt(lin_d)   # :230-231
+    envs = [bandit_env.sample_linear(arms, horizon, var) for _ in range(n_envs)]
+    if data_type == "thompson":
+        per_hist = [rollin_linear_bandit_vec(envs) for _ in range(n_hists)]
+    elif data_type == "uniform":
+        means = np.stack([e.means for e in envs])
+        per_hist = []
+        for _ in range(n_hists):
+            b = collect_bandit(n_envs, dim, horizon, var, means=means)
+            per_hist.append((b["context_states"].cpu().numpy().astype(np.int64),
+                             b["context_actions"].cpu().numpy().astype(np.float64),
+                             b["context_next_states"].cpu().numpy().astype(np.int64),
+                             b["context_rewards"][:, :, 0].cpu().numpy().astype(np.float64)))
+    else:
+        raise ValueError("Invalid data type")
+    trajs = []
+    for i, env in enumerate(envs):
+        for j in range(n_hists):
+            cs, ca, cns, cr = (x[i] for x in per_hist[j])
+            for _ in range(n_samples):
+                trajs.append({"query_state": np.array([1]), "optimal_action": env.opt_a, "context_states": cs,
+                              "context_actions": ca, "context_next_states": cns, "context_rewards": cr,
+                              "means": env.means, "arms": arms, "theta": env.theta, "var": env.var})
+    return trajs

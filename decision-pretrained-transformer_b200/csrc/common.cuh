@@ -58,20 +58,18 @@ __device__ __forceinline__ void st_stream(float* p, float v) {
   asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
-// Fill out[begin, end) (float indices relative to a 16B-aligned base) with `v`, cooperatively
-// by `nthreads` threads: scalar head/tail, float4 body.
+// Fill base[begin, end) (float indices) with `v`, cooperatively by `nthreads` threads: scalar head
+// up to the first 16 B-aligned address, float4 body, scalar tail.  Works for any alignment of base.
 __device__ __forceinline__ void fill_range(float* base, size_t begin, size_t end, float v, int tid, int nthreads) {
-  size_t b4 = (begin + 3) & ~size_t(3);
-  size_t e4 = end & ~size_t(3);
-  if (b4 >= e4) {
-    for (size_t i = begin + tid; i < end; i += nthreads) st_stream(base + i, v);
-    return;
-  }
+  const size_t mis = (reinterpret_cast<uintptr_t>(base + begin) >> 2) & 3;   // floats past a 16 B boundary
+  size_t b4 = begin + ((4 - mis) & 3);
+  if (b4 > end) b4 = end;
+  const size_t e4 = b4 + ((end - b4) & ~size_t(3));
   if (tid < (int)(b4 - begin)) st_stream(base + begin + tid, v);
   if (tid < (int)(end - e4)) st_stream(base + e4 + tid, v);
-  float4 v4 = make_float4(v, v, v, v);
+  const float4 v4 = make_float4(v, v, v, v);
   float4* p = reinterpret_cast<float4*>(base + b4);
-  size_t n4 = (e4 - b4) >> 2;
+  const size_t n4 = (e4 - b4) >> 2;
   for (size_t i = tid; i < n4; i += nthreads) st_stream(p + i, v4);
 }
 #endif

@@ -1,0 +1,451 @@
+// Fused online evaluation loop for the classical bandit controllers, and the stand-alone
+// per-arm statistics kernel.
+//
+//   dpt_online_loop : deploy_online_vec (reference evals/eval_bandit.py:56-103) + BanditEnvVec.deploy /
+//                     step / transit (envs/bandit_env.py:98-149, :56-64) + the controller's
+//                     set_batch_numpy_vec / act_numpy_vec (ctrls/ctrl_bandit.py) for all H steps in ONE
+//                     launch.  The reference recounts every arm from the whole context at every step
+//                     (O(N d h) Python per step, O(H^2) per trajectory); here one thread owns one env and
+//                     keeps the per-arm (count, reward sum) in registers, so a step is O(d).
+//                     All controller statistics are float64 like the reference, so the chosen arm is the
+//                     reference's arm unless two arms tie to ~1e-16.
+//   dpt_arm_stats   : the same statistics from an arbitrary pre-filled context (offline evaluation /
+//                     set_batch on a given context), one warp per env with warp-shuffle reductions.
+//
+// HBM traffic of the loop: 4*(2+d+1) B of context rows + 4 B of cum_means per env-step (36 B for d=5).
+// A thread's own rows are strided by H*d*4 B, so rows are staged per warp in shared memory (1 B per
+// action, 4 B per reward, 32 envs x 32 steps) and flushed as contiguous, 16 B-aligned float4 runs
+// (32 steps * d * 4 B per env).
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace dpt {
+
+constexpr int OL_WARPS = 4;
+constexpr int OL_THREADS = OL_WARPS * 32;
+constexpr int OL_T = 32;       // steps buffered per flush
+constexpr int OL_MAX_LD = 8;   // max lin_d
+
+enum { K_OPT = 0, K_EMP = 1, K_UCB = 2, K_THOMPSON = 3, K_LINUCB = 4 };
+
+struct OnlineParams {
+  double p0, p1, p2, var;
+  const float* means;
+  const double* arms;
+  int lin_d;
+  Key key;
+  uint64_t env_id0;
+  int N, H, d;
+  uint32_t magic_d;  // ceil(2^32 / d): floor(x / d) == umulhi(x, magic_d) for the small x used here
+  float *ctx_s, *ctx_a, *ctx_ns, *ctx_r, *cum_means;
+  double* regret;
+  dpt_online_inject_t in;
+  dpt_online_dump_t out;
+  bool vec;  // float4 flush allowed
+};
+
+struct WarpTile {
+  unsigned char acts[32][OL_T];
+  float rew[32][OL_T + 1];
+};
+
+template <int DMAX>
+struct ArmState {
+  double sum[DMAX];   // reward sum b
+  double aux0[DMAX];  // EMP/UCB: mean; THOMPSON: posterior mean
+  double aux1[DMAX];  // UCB: bonus; THOMPSON: posterior std
+  int cnt[DMAX];
+};
+
+// 4 standard normals per Philox block (two Box-Muller pairs)
+__device__ __forceinline__ void normals4(uint4 w, float z[4]) {
+  box_muller(w.x, w.y, z[0], z[1]);
+  box_muller(w.z, w.w, z[2], z[3]);
+}
+
+template <int LD>
+__device__ __forceinline__ void inv_small(const double* S, double* Si, int ld) {
+  // Gauss-Jordan with partial pivoting on [S | I] (S is SPD = I + A^T A, so it never fails)
+  double a[OL_MAX_LD][2 * OL_MAX_LD];
+  for (int i = 0; i < ld; ++i)
+    for (int j = 0; j < ld; ++j) a[i][j] = S[i * ld + j], a[i][ld + j] = (i == j) ? 1.0 : 0.0;
+  for (int c = 0; c < ld; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < ld; ++r)
+      if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+    if (piv != c)
+      for (int j = 0; j < 2 * ld; ++j) {
+        const double t = a[c][j];
+        a[c][j] = a[piv][j];
+        a[piv][j] = t;
+      }
+    const double inv = 1.0 / a[c][c];
+    for (int j = 0; j < 2 * ld; ++j) a[c][j] *= inv;
+    for (int r = 0; r < ld; ++r)
+      if (r != c) {
+        const double f = a[r][c];
+        for (int j = 0; j < 2 * ld; ++j) a[r][j] -= f * a[c][j];
+      }
+  }
+  for (int i = 0; i < ld; ++i)
+    for (int j = 0; j < ld; ++j) Si[i * ld + j] = a[i][ld + j];
+}
+
+template <int DMAX, int KIND>
+__global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlineParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WarpTile* tiles = reinterpret_cast<WarpTile*>(smem_raw);
+  float* s_means_all = reinterpret_cast<float*>(smem_raw + sizeof(WarpTile) * OL_WARPS);  // [OL_THREADS][DMAX]
+  double* s_arms = reinterpret_cast<double*>(s_means_all + OL_THREADS * DMAX);            // [d][lin_d]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  WarpTile& tile = tiles[warp];
+  float(*s_means)[DMAX] = reinterpret_cast<float(*)[DMAX]>(s_means_all) + warp * 32;
+  const int env0w = (blockIdx.x * OL_WARPS + warp) * 32;  // first env of this warp
+  const int env = env0w + lane;
+  const bool live = env < p.N;
+  const int N = p.N, H = p.H, d = p.d;
+  const uint64_t gid = p.env_id0 + (uint64_t)env;
+  const bool materialise = p.ctx_a != nullptr;
+
+  if (KIND == K_LINUCB) {
+    for (int i = tid; i < d * p.lin_d; i += OL_THREADS) s_arms[i] = p.arms[i];
+  }
+  float m[DMAX];
+  float mmax = -INFINITY;
+  int opt = 0;
+#pragma unroll
+  for (int j = 0; j < DMAX; ++j) {
+    m[j] = (live && j < d) ? p.means[(size_t)env * d + j] : -INFINITY;
+    if (m[j] > mmax) mmax = m[j], opt = j;
+    s_means[lane][j] = m[j];
+  }
+  __syncthreads();
+
+  // constant states (bandit dx = 1): this warp's envs are one contiguous run
+  if (p.ctx_s) {
+    const int nl = min(32, N - env0w);
+    if (nl > 0) {
+      fill_range(p.ctx_s, (size_t)env0w * H, (size_t)(env0w + nl) * H, 1.0f, lane, 32);
+      fill_range(p.ctx_ns, (size_t)env0w * H, (size_t)(env0w + nl) * H, 1.0f, lane, 32);
+    }
+  }
+
+  ArmState<DMAX> st;
+#pragma unroll
+  for (int j = 0; j < DMAX; ++j) {
+    st.sum[j] = 0.0, st.cnt[j] = 0;
+    st.aux0[j] = (KIND == K_THOMPSON) ? p.p1 : 0.0;                  // prior mean | empirical mean 0
+    st.aux1[j] = (KIND == K_THOMPSON) ? sqrt(p.p2) : p.p0;           // prior std  | UCB bonus const/max(1,0)
+  }
+  // LinUCB: S = I + sum x x^T, bvec = sum x r  (ctrls/ctrl_bandit.py:510-513)
+  double S[KIND == K_LINUCB ? OL_MAX_LD * OL_MAX_LD : 1], bv[KIND == K_LINUCB ? OL_MAX_LD : 1];
+  if (KIND == K_LINUCB) {
+    for (int i = 0; i < p.lin_d; ++i) {
+      bv[i] = 0.0;
+      for (int j = 0; j < p.lin_d; ++j) S[i * p.lin_d + j] = (i == j) ? 1.0 : 0.0;
+    }
+  }
+  const double sigma2 = p.p0 * p.p0;  // Thompson: std^2 (ctrls/ctrl_bandit.py:126)
+  float z_next = 0.f;
+  const int nb_ctrl = (d + 3) >> 2;
+
+  for (int h0 = 0; h0 < H; h0 += OL_T) {
+    const int T = min(OL_T, H - h0);
+    for (int t = 0; t < T; ++t) {
+      const int h = h0 + t;
+      int a = 0;
+      // ------------------------------------------------ controller: pick an arm ------------
+      if (KIND == K_OPT) {
+        a = opt;                                                        // :35-37
+      } else if (KIND == K_EMP || KIND == K_UCB) {
+        double best = -INFINITY;
+        int first_untried = -1;
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j) {
+          if (j < d) {
+            const double v = (KIND == K_UCB) ? st.aux0[j] + st.aux1[j] : st.aux0[j];   // :106 | :369-370
+            if (v > best) best = v, a = j;                              // np.argmax: first maximum
+            if (st.cnt[j] == 0 && first_untried < 0) first_untried = j; // np.argmin(counts) when min == 0
+          }
+        }
+        if ((KIND == K_UCB || p.p0 != 0.0) && first_untried >= 0) a = first_untried;   // :110-113 | :373-375
+      } else if (KIND == K_THOMPSON) {
+        double best = -INFINITY;
+        float zz[4];
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j) {
+          if (j < d) {
+            float zj;
+            if (p.in.ctrl_z) {
+              zj = live ? p.in.ctrl_z[((size_t)h * N + env) * d + j] : 0.f;
+            } else {
+              if ((j & 3) == 0) normals4(philox_words(p.key, gid, (uint32_t)(h * nb_ctrl + (j >> 2)), STREAM_CTRL), zz);
+              zj = zz[j & 3];
+            }
+            if (p.out.ctrl_z && live) p.out.ctrl_z[((size_t)h * N + env) * d + j] = zj;
+            const double v = st.aux0[j] + st.aux1[j] * (double)zj;      // np.random.normal(means, sqrt(variances)) :234
+            if (v > best) best = v, a = j;
+          }
+        }
+      } else {  // LinUCB
+        if (h == 0) {                                                   // :496-500 uniform random first arm
+          if (p.in.first_arm)
+            a = live ? p.in.first_arm[env] : 0;
+          else
+            a = (int)bounded(philox_words(p.key, gid, 0u, STREAM_CTRL).x, (uint32_t)d);
+          if (p.out.first_arm && live) p.out.first_arm[env] = a;
+        } else {
+          const int ld = p.lin_d;
+          double Si[OL_MAX_LD * OL_MAX_LD], theta[OL_MAX_LD];
+          if (ld == 2) {
+            const double det = S[0] * S[3] - S[1] * S[2];
+            Si[0] = S[3] / det, Si[1] = -S[1] / det, Si[2] = -S[2] / det, Si[3] = S[0] / det;
+          } else {
+            inv_small<OL_MAX_LD>(S, Si, ld);
+          }
+          for (int i = 0; i < ld; ++i) {
+            double acc = 0.0;
+            for (int j = 0; j < ld; ++j) acc += Si[i * ld + j] * bv[j];
+            theta[i] = acc;                                             // cov_inv @ A^T r  :513
+          }
+          double best = -INFINITY;
+          for (int j = 0; j < d; ++j) {
+            const double* x = s_arms + j * ld;
+            double mean = 0.0, q = 0.0;
+            for (int i = 0; i < ld; ++i) {
+              mean += theta[i] * x[i];
+              double row = 0.0;
+              for (int k = 0; k < ld; ++k) row += Si[i * ld + k] * x[k];
+              q += x[i] * row;
+            }
+            const double v = mean + p.p0 * sqrt(q);                     // :519
+            if (v > best) best = v, a = j;                              // strict >: first maximum :520
+          }
+        }
+      }
+      // ------------------------------------------------ env step ---------------------------
+      float z;
+      if (p.in.reward_z) {
+        z = live ? p.in.reward_z[(size_t)h * N + env] : 0.f;
+      } else if ((h & 1) == 0) {
+        const uint4 w = philox_words(p.key, gid, (uint32_t)(h >> 1), STREAM_ENV_REWARD);
+        box_muller(w.z, w.w, z, z_next);
+      } else {
+        z = z_next;
+      }
+      if (p.out.reward_z && live) p.out.reward_z[(size_t)h * N + env] = z;
+      const float ma = s_means[lane][a];
+      const double r = (double)ma + (0.0 + p.var * (double)z);          // envs/bandit_env.py:59
+      // ------------------------------------------------ controller statistics --------------
+      if (KIND == K_EMP || KIND == K_UCB || KIND == K_THOMPSON) {
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j) {
+          if (j == a) {
+            st.sum[j] += r;
+            st.cnt[j] += 1;
+            const double n = (double)st.cnt[j];
+            if (KIND == K_THOMPSON) {                                   // update_posterior_all :196-203
+              const double arm_mean = st.sum[j] / n;
+              const double pw = sigma2 / (sigma2 + n * p.p2);
+              st.aux0[j] = pw * p.p1 + (1.0 - pw) * arm_mean;
+              st.aux1[j] = sqrt(1.0 / (1.0 / p.p2 + n / sigma2));
+            } else {
+              st.aux0[j] = st.sum[j] / n;                               // b / max(1, counts)
+              if (KIND == K_UCB) st.aux1[j] = p.p0 / fmax(1.0, sqrt(n));  // const / max(1, sqrt(counts)) :366
+            }
+          }
+        }
+      } else if (KIND == K_LINUCB) {
+        const int ld = p.lin_d;
+        const double* x = s_arms + a * ld;
+        for (int i = 0; i < ld; ++i) {
+          bv[i] += x[i] * r;
+          for (int j = 0; j < ld; ++j) S[i * ld + j] += x[i] * x[j];
+        }
+      }
+      // ------------------------------------------------ outputs ----------------------------
+      if (live && p.cum_means) st_stream(p.cum_means + (size_t)h * N + env, ma);   // get_arm_value :151-153
+      tile.acts[lane][t] = (unsigned char)a;
+      tile.rew[lane][t] = (float)r;
+    }
+    __syncwarp();
+    // ------------------------------------------------ flush 32 envs x T steps ----------------
+    const int nl = min(32, N - env0w);
+    if (nl > 0 && p.regret && lane < T) {     // per-step regret sums over this warp's envs (evals/eval_bandit.py:169-178)
+      double s1 = 0.0, s2 = 0.0;
+      for (int e = 0; e < nl; ++e) {
+        const int ae = tile.acts[e][lane];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j) mx = fmaxf(mx, s_means[e][j]);
+        const double reg = (double)mx - (double)s_means[e][ae];
+        s1 += reg, s2 += reg * reg;
+      }
+      atomicAdd(p.regret + 2 * (size_t)(h0 + lane), s1);
+      atomicAdd(p.regret + 2 * (size_t)(h0 + lane) + 1, s2);
+    }
+    if (nl > 0 && materialise) {
+      for (int e = 0; e < nl; ++e)
+        if (lane < T) st_stream(p.ctx_r + (size_t)(env0w + e) * H + h0 + lane, tile.rew[e][lane]);
+      if (p.vec) {
+        const int nq = (T * d) >> 2;   // float4 per env in this flush
+        const int total = nl * nq;
+        for (int i = lane; i < total; i += 32) {
+          const int e = i / nq, q = i - e * nq;
+          float v[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int el = 4 * q + c;
+            const int t = (d == 1) ? el : (int)__umulhi((uint32_t)el, p.magic_d);
+            v[c] = (tile.acts[e][t] == el - t * d) ? 1.f : 0.f;
+          }
+          st_stream(reinterpret_cast<float4*>(p.ctx_a + ((size_t)(env0w + e) * H + h0) * d) + q,
+                    make_float4(v[0], v[1], v[2], v[3]));
+        }
+      } else {
+        const int per = T * d;
+        for (int e = 0; e < nl; ++e)
+          for (int el = lane; el < per; el += 32) {
+            const int t = (d == 1) ? el : (int)__umulhi((uint32_t)el, p.magic_d);
+            st_stream(p.ctx_a + ((size_t)(env0w + e) * H + h0) * d + el, (tile.acts[e][t] == el - t * d) ? 1.f : 0.f);
+          }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dpt_arm_stats: one warp per env, lanes stride over the context steps, per-arm partials in
+// registers, warp-shuffle reductions.
+// ---------------------------------------------------------------------------------------------
+template <int DMAX>
+__global__ void __launch_bounds__(256) arm_stats_kernel(const float* __restrict__ ctx_a, const float* __restrict__ ctx_r,
+                                                        int N, int h, int Hs, int d, double* __restrict__ sums,
+                                                        int32_t* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int env = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (env >= N) return;
+  double s[DMAX];
+  int c[DMAX];
+#pragma unroll
+  for (int j = 0; j < DMAX; ++j) s[j] = 0.0, c[j] = 0;
+  for (int t = lane; t < h; t += 32) {
+    const float* row = ctx_a + ((size_t)env * Hs + t) * d;
+    int a = 0;
+    float bv = row[0];
+    for (int j = 1; j < d; ++j) {
+      const float v = row[j];
+      if (v > bv) bv = v, a = j;       // np.argmax(actions, axis=-1)
+    }
+    const double r = (double)ctx_r[(size_t)env * Hs + t];
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j)
+      if (j == a) s[j] += r, c[j] += 1;
+  }
+#pragma unroll
+  for (int j = 0; j < DMAX; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+      c[j] += __shfl_xor_sync(0xffffffffu, c[j], o);
+    }
+    if (lane == 0 && j < d) sums[(size_t)env * d + j] = s[j], counts[(size_t)env * d + j] = c[j];
+  }
+}
+
+template <int DMAX, int KIND>
+static cudaError_t launch_online(const OnlineParams& p, cudaStream_t st) {
+  const size_t smem = sizeof(WarpTile) * OL_WARPS + sizeof(float) * OL_THREADS * DMAX +
+                      sizeof(double) * (KIND == K_LINUCB ? p.d * p.lin_d : 0) + 16;
+  auto kern = online_loop_kernel<DMAX, KIND>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const int grid = (p.N + OL_THREADS - 1) / OL_THREADS;
+  kern<<<grid, OL_THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int DMAX>
+static cudaError_t launch_online_kind(int kind, const OnlineParams& p, cudaStream_t st) {
+  switch (kind) {
+    case K_OPT: return launch_online<DMAX, K_OPT>(p, st);
+    case K_EMP: return launch_online<DMAX, K_EMP>(p, st);
+    case K_UCB: return launch_online<DMAX, K_UCB>(p, st);
+    case K_THOMPSON: return launch_online<DMAX, K_THOMPSON>(p, st);
+    default: return launch_online<DMAX, K_LINUCB>(p, st);
+  }
+}
+
+}  // namespace dpt
+
+using namespace dpt;
+
+extern "C" int dpt_online_loop(int ctrl_kind, double p0, double p1, double p2, const float* means, const double* arms,
+                               int lin_d, double var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
+                               float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
+                               float* cum_means, double* regret_sums, const dpt_online_inject_t* inject,
+                               const dpt_online_dump_t* dump, void* stream) {
+  DPT_CHECK_ARG(ctrl_kind >= K_OPT && ctrl_kind <= K_LINUCB, "dpt_online_loop: unknown controller kind %d", ctrl_kind);
+  DPT_CHECK_ARG(N >= 0 && H >= 0, "dpt_online_loop: N=%d H=%d must be >= 0", N, H);
+  DPT_CHECK_ARG(d >= 1 && d <= 32, "dpt_online_loop: d=%d outside [1,32]", d);
+  if (N == 0 || H == 0) return DPT_OK;
+  DPT_CHECK_ARG(means, "dpt_online_loop: null means");
+  const bool any = ctx_states || ctx_actions || ctx_next_states || ctx_rewards;
+  DPT_CHECK_ARG(!any || (ctx_states && ctx_actions && ctx_next_states && ctx_rewards),
+                "dpt_online_loop: context pointers must be all NULL or all non-NULL");
+  if (ctrl_kind == K_LINUCB) {
+    DPT_CHECK_ARG(arms && lin_d >= 1 && lin_d <= OL_MAX_LD, "dpt_online_loop: LinUCB needs arms and 1 <= lin_d <= %d",
+                  OL_MAX_LD);
+  }
+  if (ctrl_kind == K_THOMPSON) DPT_CHECK_ARG(p0 > 0.0 && p2 > 0.0, "dpt_online_loop: Thompson needs std > 0 and prior_var > 0");
+  OnlineParams p{};
+  p.p0 = p0, p.p1 = p1, p.p2 = p2, p.var = var;
+  p.means = means, p.arms = arms, p.lin_d = lin_d;
+  p.key = Key{(uint32_t)seed, (uint32_t)(seed >> 32)};
+  p.env_id0 = env_id0;
+  p.N = N, p.H = H, p.d = d;
+  p.magic_d = (uint32_t)((0x100000000ull + (uint64_t)d - 1) / (uint64_t)d);
+  p.ctx_s = ctx_states, p.ctx_a = ctx_actions, p.ctx_ns = ctx_next_states, p.ctx_r = ctx_rewards;
+  p.cum_means = cum_means, p.regret = regret_sums;
+  if (inject) p.in = *inject;
+  if (dump) p.out = *dump;
+  p.vec = any && ((size_t)H * d) % 4 == 0 && (OL_T * d) % 4 == 0 && aligned16(ctx_actions);
+  cudaError_t e;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d <= 5)
+    e = launch_online_kind<5>(ctrl_kind, p, st);
+  else if (d <= 10)
+    e = launch_online_kind<10>(ctrl_kind, p, st);
+  else if (d <= 16)
+    e = launch_online_kind<16>(ctrl_kind, p, st);
+  else
+    e = launch_online_kind<32>(ctrl_kind, p, st);
+  if (e != cudaSuccess) {
+    set_error("dpt_online_loop launch failed: %s", cudaGetErrorString(e));
+    return DPT_ERR_CUDA;
+  }
+  return DPT_OK;
+}
+
+extern "C" int dpt_arm_stats(const float* ctx_actions, const float* ctx_rewards, int N, int h, int H_stride, int d,
+                             double* sums, int32_t* counts, void* stream) {
+  DPT_CHECK_ARG(N >= 0 && h >= 0 && H_stride >= h, "dpt_arm_stats: N=%d h=%d H_stride=%d", N, h, H_stride);
+  DPT_CHECK_ARG(d >= 1 && d <= 32, "dpt_arm_stats: d=%d outside [1,32]", d);
+  if (N == 0) return DPT_OK;
+  DPT_CHECK_ARG(sums && counts && (h == 0 || (ctx_actions && ctx_rewards)), "dpt_arm_stats: null pointer");
+  const int grid = (N + 7) / 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d <= 5)
+    arm_stats_kernel<5><<<grid, 256, 0, st>>>(ctx_actions, ctx_rewards, N, h, H_stride, d, sums, counts);
+  else if (d <= 10)
+    arm_stats_kernel<10><<<grid, 256, 0, st>>>(ctx_actions, ctx_rewards, N, h, H_stride, d, sums, counts);
+  else if (d <= 16)
+    arm_stats_kernel<16><<<grid, 256, 0, st>>>(ctx_actions, ctx_rewards, N, h, H_stride, d, sums, counts);
+  else
+    arm_stats_kernel<32><<<grid, 256, 0, st>>>(ctx_actions, ctx_rewards, N, h, H_stride, d, sums, counts);
+  DPT_LAUNCH_CHECK();
+  return DPT_OK;
+}

@@ -1,0 +1,109 @@
+"""Online in-context evaluation with the reference's interface (evals/eval_bandit.py).
+
+``deploy_online_vec(vec_env, controller, horizon, include_meta=False)`` keeps its signature and
+return values (cum_means [H,N] float64, meta = four [N,H,.] float64 arrays).  When the env is this
+package's ``BanditEnvVec`` and the controller exposes ``fused_spec()`` the whole loop -- controller
+statistics, arm choice, env step, context rows, expected reward of the chosen arm, per-step regret
+sums -- runs in ONE fused launch (dpt_online_loop / dpt_gpt2_online_loop) instead of H Python
+iterations over N env objects.  Anything else takes the generic loop below, which is the reference's
+loop verbatim in structure and drives ``vec_env.deploy`` one step at a time.
+"""
+import numpy as np
+import torch
+
+from .. import kernels, rng
+from ..ctrls.ctrl_bandit import (BanditTransformerController, EmpMeanPolicy, OptPolicy, ThompsonSamplingPolicy,  # noqa: F401
+                                 UCBPolicy)
+from ..envs.bandit_env import BanditEnv, BanditEnvVec
+
+
+def _fusable(vec_env, controller):
+    if not isinstance(vec_env, BanditEnvVec) or not hasattr(controller, "fused_spec"):
+        return None
+    if len({float(e.var) for e in vec_env.envs}) != 1 or any(e.type != "uniform" for e in vec_env.envs):
+        return None
+    return controller.fused_spec()
+
+
+def deploy_online_vec_device(vec_env, controller, horizon, include_meta=False, regret=True, seed=None, env_id0=0,
+                             inject=None, dump=False):
+    """Fused loop, results left on the device (dict of torch tensors, see kernels.online_loop)."""
+    spec = _fusable(vec_env, controller)
+    if spec is None:
+        raise NotImplementedError("controller / env pair has no fused path")
+    key = rng.next_key() if seed is None else seed
+    var = float(vec_env.envs[0].var)
+    if spec["kind"] == "transformer":
+        return controller.fused_online_loop(vec_env.means, horizon, var, key, env_id0, include_meta, regret, inject, dump)
+    return kernels.online_loop(spec["kind"], vec_env.means, horizon, var, key, env_id0, spec.get("p0", 0.0),
+                               spec.get("p1", 0.0), spec.get("p2", 0.0), spec.get("arms"), include_meta, regret,
+                               inject, dump)
+
+
+def deploy_online_vec(vec_env, controller, horizon, include_meta=False):
+    """evals/eval_bandit.py:56-103."""
+    if _fusable(vec_env, controller) is not None:
+        out = deploy_online_vec_device(vec_env, controller, horizon, include_meta, regret=False)
+        cum_means = out["cum_means"].cpu().numpy().astype(np.float64)
+        if not include_meta:
+            return cum_means
+        meta = {k: out[k].cpu().numpy().astype(np.float64) for k in
+                ("context_states", "context_actions", "context_next_states", "context_rewards")}
+        return cum_means, meta
+
+    num_envs = vec_env.num_envs
+    context_states = np.zeros((num_envs, horizon, vec_env.dx))
+    context_actions = np.zeros((num_envs, horizon, vec_env.du))
+    context_next_states = np.zeros((num_envs, horizon, vec_env.dx))
+    context_rewards = np.zeros((num_envs, horizon, 1))
+    cum_means = []
+    for h in range(horizon):
+        batch = {"context_states": context_states[:, :h, :], "context_actions": context_actions[:, :h, :],
+                 "context_next_states": context_next_states[:, :h, :], "context_rewards": context_rewards[:, :h, :]}
+        controller.set_batch_numpy_vec(batch)
+        states_lnr, actions_lnr, next_states_lnr, rewards_lnr = vec_env.deploy(controller)
+        context_states[:, h, :] = states_lnr
+        context_actions[:, h, :] = actions_lnr
+        context_next_states[:, h, :] = next_states_lnr
+        context_rewards[:, h, :] = rewards_lnr[:, None]
+        cum_means.append(vec_env.get_arm_value(actions_lnr))
+    cum_means = np.array(cum_means)
+    if not include_meta:
+        return cum_means
+    return cum_means, {"context_states": context_states, "context_actions": context_actions,
+                       "context_next_states": context_next_states, "context_rewards": context_rewards}
+
+
+def regret_stats(all_means):
+    """evals/eval_bandit.py:169-178: dict name -> [N,H] expected reward -> per-step and cumulative
+    regret mean / standard error (scipy.stats.sem, ddof=1) against all_means['opt']."""
+    opt = np.asarray(all_means["opt"])
+    n = opt.shape[0]
+    out = {}
+    for k, v in all_means.items():
+        diff = opt - np.asarray(v)
+        cr = np.cumsum(diff, axis=1)
+        out[k] = {"mean": diff.mean(0), "sem": diff.std(0, ddof=1) / np.sqrt(n),
+                  "regret_mean": cr.mean(0), "regret_sem": cr.std(0, ddof=1) / np.sqrt(n)}
+    return out
+
+
+def online(eval_trajs, model, n_eval, horizon, var, bandit_type="uniform"):
+    """evals/eval_bandit.py:107-178 without the matplotlib part: runs Opt, the transformer (if a
+    model is given), EmpMean(online), UCB(1.0) and Thompson on the same tasks and returns
+    (all_means dict of [n_eval,H], regret statistics)."""
+    envs = [BanditEnv(eval_trajs[i]["means"], horizon, var=var) for i in range(n_eval)]
+    vec_env = BanditEnvVec(envs)
+    ctrls = {"opt": OptPolicy(envs, batch_size=len(envs))}
+    if model is not None:
+        ctrls["Lnr"] = BanditTransformerController(model, sample=True, batch_size=len(envs))
+    ctrls["Emp"] = EmpMeanPolicy(envs[0], online=True, batch_size=len(envs))
+    ctrls["UCB1.0"] = UCBPolicy(envs[0], const=1.0, batch_size=len(envs))
+    ctrls["Thomp"] = ThompsonSamplingPolicy(envs[0], std=var, sample=True, prior_mean=0.5, prior_var=1 / 12.0,
+                                            warm_start=False, batch_size=len(envs))
+    all_means = {}
+    for name, c in ctrls.items():
+        cm = deploy_online_vec(vec_env, c, horizon).T
+        assert cm.shape[0] == n_eval
+        all_means[name] = cm
+    return all_means, regret_stats(all_means)

@@ -202,3 +202,72 @@ def gpu_bandit_step(means, actions, var, type_id, seed, env_id0, step, inject=No
     check(lib().dpt_gpu_bandit_step(ptr(means), ptr(actions), var, type_id, seed, env_id0, step, N, d, ptr(reward),
                                     ptr(inj), ptr(dmp), stream_ptr()), "dpt_gpu_bandit_step")
     return (reward, dmp) if dump else reward
+
+
+# ------------------------------------------------------------------ controllers ----------------
+CTRL_KINDS = {"opt": 0, "emp": 1, "ucb": 2, "thompson": 3, "linucb": 4}
+
+
+def arm_stats(ctx_actions, ctx_rewards, h=None):
+    """Per-(env, arm) reward sums (f64) and pull counts (int32) of the first ``h`` context steps
+    (ctrls/ctrl_bandit.py:95-104).  ctx_actions [N,Hs,d], ctx_rewards [N,Hs,1] or [N,Hs] fp32 device."""
+    dev = _dev(ctx_actions.device if torch.is_tensor(ctx_actions) and ctx_actions.is_cuda else None)
+    ctx_actions, ctx_rewards = _as(ctx_actions, F32, dev), _as(ctx_rewards, F32, dev)
+    N, Hs, d = ctx_actions.shape
+    h = Hs if h is None else h
+    sums = torch.empty((N, d), dtype=F64, device=dev)
+    counts = torch.empty((N, d), dtype=I32, device=dev)
+    check(lib().dpt_arm_stats(ptr(ctx_actions), ptr(ctx_rewards), N, h, Hs, d, ptr(sums), ptr(counts), stream_ptr()),
+          "dpt_arm_stats")
+    return sums, counts
+
+
+def online_loop(kind, means, H, var, seed, env_id0=0, p0=0.0, p1=0.0, p2=0.0, arms=None, materialise=True,
+                regret=True, inject=None, dump=False):
+    """Fused deploy_online_vec for a classical controller (evals/eval_bandit.py:56-103).
+
+    Returns dict: cum_means [H,N] fp32, regret_sums [H,2] f64 (sum, sum of squares over envs of
+    max(means) - cum_means), and, if materialise, context_* [N,H,.] fp32 [+ 'noise' if dump]."""
+    dev = _dev(means.device if torch.is_tensor(means) and means.is_cuda else None)
+    means = _as(means, F32, dev)
+    N, d = means.shape
+    out = {"cum_means": torch.empty((H, N), dtype=F32, device=dev)}
+    if regret:
+        out["regret_sums"] = torch.zeros((H, 2), dtype=F64, device=dev)
+    if materialise:
+        out.update(context_states=torch.empty((N, H, 1), dtype=F32, device=dev),
+                   context_actions=torch.empty((N, H, d), dtype=F32, device=dev),
+                   context_next_states=torch.empty((N, H, 1), dtype=F32, device=dev),
+                   context_rewards=torch.empty((N, H, 1), dtype=F32, device=dev))
+    arms_t, lin_d = None, 0
+    if arms is not None:
+        arms_t = _as(arms, F64, dev)
+        lin_d = arms_t.shape[1]
+    inj_p, dump_p, keep = None, None, []
+    if inject is not None:
+        s = _lib.OnlineInject()
+        for k, dt in (("reward_z", F32), ("ctrl_z", F32), ("first_arm", I32)):
+            if inject.get(k) is not None:
+                t = _as(inject[k], dt, dev)
+                keep.append(t)
+                setattr(s, k, ptr(t))
+        inj_p = ctypes.byref(s)
+    noise = None
+    if dump:
+        noise = {"reward_z": torch.empty((H, N), dtype=F32, device=dev)}
+        if kind == "thompson":
+            noise["ctrl_z"] = torch.empty((H, N, d), dtype=F32, device=dev)
+        if kind == "linucb":
+            noise["first_arm"] = torch.empty((N,), dtype=I32, device=dev)
+        s2 = _lib.OnlineDump()
+        for k, t in noise.items():
+            setattr(s2, k, ptr(t))
+        dump_p = ctypes.byref(s2)
+    check(lib().dpt_online_loop(CTRL_KINDS[kind], p0, p1, p2, ptr(means), ptr(arms_t), lin_d, float(var), seed, env_id0,
+                                N, H, d, ptr(out.get("context_states")), ptr(out.get("context_actions")),
+                                ptr(out.get("context_next_states")), ptr(out.get("context_rewards")),
+                                ptr(out["cum_means"]), ptr(out.get("regret_sums")), inj_p, dump_p, stream_ptr()),
+          "dpt_online_loop")
+    if noise is not None:
+        out["noise"] = noise
+    return out

@@ -160,7 +160,7 @@ typedef struct {
 } dpt_online_dump_t;
 
 int dpt_online_loop(int ctrl_kind, double p0, double p1, double p2, const float* means, const double* arms,
-                    int lin_d, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d, float* ctx_states,
+                    int lin_d, double var, uint64_t seed, uint64_t env_id0, int N, int H, int d, float* ctx_states,
                     float* ctx_actions, float* ctx_next_states, float* ctx_rewards, float* cum_means,
                     double* regret_sums, const dpt_online_inject_t* inject, const dpt_online_dump_t* dump,
                     void* stream);
@@ -224,7 +224,7 @@ typedef struct {
 } dpt_gpt2_online_dump_t;
 
 uint64_t dpt_gpt2_online_kv_bytes(const dpt_gpt2_t* m, int N, int H, int precision);
-int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, float var, int sample, uint64_t seed, uint64_t env_id0,
+int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, double var, int sample, uint64_t seed, uint64_t env_id0,
                          int N, int H, int precision, void* kv_cache, uint64_t kv_bytes, float* ctx_states,
                          float* ctx_actions, float* ctx_next_states, float* ctx_rewards, float* cum_means,
                          double* regret_sums, const dpt_gpt2_online_inject_t* inject,
