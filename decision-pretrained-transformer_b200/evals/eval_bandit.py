@@ -18,7 +18,7 @@ from ..envs.bandit_env import BanditEnv, BanditEnvVec
 
 
 def _fusable(vec_env, controller):
-    if not isinstance(vec_env, BanditEnvVec) or not hasattr(controller, "fused_spec"):
+    if not isinstance(vec_env, BanditEnvVec) or not callable(getattr(controller, "fused_spec", None)):
         return None
     if len({float(e.var) for e in vec_env.envs}) != 1 or any(e.type != "uniform" for e in vec_env.envs):
         return None
