@@ -13,6 +13,8 @@ from .envs import base_env, bandit_env, gpu_bandit_env, darkroom_env   # noqa: F
 from . import ctrls, evals                # noqa: F401
 from .ctrls import ctrl_bandit            # noqa: F401
 from .evals import eval_bandit, eval_linear_bandit   # noqa: F401
+from . import models                      # noqa: F401
+from .models import net                   # noqa: F401
 
 __all__ = ["seed", "kernels", "envs", "collect_data", "install_dropin"]
 

@@ -1,0 +1,514 @@
+// GPT-2 trunk of the DPT Transformer (reference models/net.py:9-60 over transformers GPT2Model with
+// n_head = 1): embed_transition -> +wpe -> L x [LN -> c_attn -> causal softmax(QK^T/sqrt(E)) V ->
+// c_proj -> +res; LN -> c_fc -> gelu_new -> c_proj -> +res] -> ln_f -> pred_actions.
+//
+// Both entry points run the model one token at a time with a per-sequence K/V cache, one WARP per
+// sequence, lane = channel (n_embd = 32 = warp width, head_dim = 32):
+//   dpt_gpt2_online_loop : the bandit in-context evaluation loop (evals/eval_bandit.py:56-103 +
+//       ctrls/ctrl_bandit.py:383-444 + env step) fused into one launch.  The reference re-runs the
+//       whole (h+1)-token forward at every step (O(H^2) token-forwards, plus a full host->device copy
+//       of the context each step); because the bandit query token is constant and sits at position 0
+//       of a causal model, appending one token per step to a K/V cache is mathematically identical
+//       (SURVEY.md §3.3), so a step is ONE token-forward + softmax/categorical draw + env step.
+//   dpt_gpt2_forward     : Transformer.forward(x) for an arbitrary context (dense semantics, computed
+//       causally token by token with a scratch K/V cache).
+// Layout: K is kept transposed, K^T[layer][channel][t] (a lane scores key t = blk*32+lane with 32
+// coalesced loads), V natural [layer][t][channel] (a lane accumulates its channel over t with
+// coalesced 128 B rows).  K/V reads bypass L1 (ld.global.cg) so L1 keeps the ~200 KB of weights that
+// every warp re-reads; weights are read through the read-only path.  fp32 everywhere, accurate
+// expf/tanhf/sqrtf (the 1e-5 logit parity bar excludes TF32 and .approx forms).
+// Bound: K/V bytes read per token-forward = n_layer * 2 * t * 32 * 4 (HBM once the in-flight caches
+// exceed L2), ~0.9 FLOP/B -- HBM-bound, not tensor-bound.
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace dpt {
+
+constexpr int G_E = 32;
+constexpr int G_FF = 128;
+constexpr int G_MAX_L = 8;
+constexpr int G_WARPS = 4;
+constexpr int G_THREADS = G_WARPS * 32;
+
+struct LayerW {
+  const float *ln1_w, *ln1_b, *attn_w, *attn_b, *proj_w, *proj_b, *ln2_w, *ln2_b, *fc_w, *fc_b, *fc2_w, *fc2_b;
+};
+
+struct Gpt2Dev {
+  int L, dx, du, din, H, n_pos;
+  const float *wpe, *embed_wT, *embed_b, *pred_wT, *pred_b, *lnf_w, *lnf_b;
+  LayerW layer[G_MAX_L];
+};
+
+}  // namespace dpt
+
+struct dpt_gpt2 {
+  dpt::Gpt2Dev dev;
+  float* blob;
+};
+
+namespace dpt {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float layer_norm(float x, const float* w, const float* b, int lane) {
+  const float mean = warp_sum(x) * (1.0f / G_E);
+  const float dv = x - mean;
+  const float var = warp_sum(dv * dv) * (1.0f / G_E);
+  return dv * (1.0f / sqrtf(var + 1e-5f)) * __ldg(w + lane) + __ldg(b + lane);
+}
+
+__device__ __forceinline__ float gelu_new(float x) {  // transformers NewGELUActivation
+  return 0.5f * x * (1.0f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
+}
+
+// One token through all layers.  x: this lane's channel of the embedded token (+wpe).  kv: this
+// sequence's cache, [L][2][32][Tpad] floats.  sx[32], sh[128], ssc[Tpad]: per-warp shared scratch.
+__device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int pos, float* kv, int Tpad, float* sx,
+                                               float* sh, float* ssc, int lane) {
+  for (int l = 0; l < m.L; ++l) {
+    const LayerW& w = m.layer[l];
+    float* kT = kv + (size_t)(l * 2) * G_E * Tpad;
+    float* V = kT + (size_t)G_E * Tpad;
+    // ---- attention ----
+    sx[lane] = layer_norm(x, w.ln1_w, w.ln1_b, lane);
+    __syncwarp();
+    float q = __ldg(w.attn_b + lane), k = __ldg(w.attn_b + G_E + lane), v = __ldg(w.attn_b + 2 * G_E + lane);
+#pragma unroll 8
+    for (int i = 0; i < G_E; ++i) {
+      const float hv = sx[i];
+      const float* row = w.attn_w + i * 3 * G_E;
+      q = fmaf(hv, __ldg(row + lane), q);
+      k = fmaf(hv, __ldg(row + G_E + lane), k);
+      v = fmaf(hv, __ldg(row + 2 * G_E + lane), v);
+    }
+    __syncwarp();
+    kT[(size_t)lane * Tpad + pos] = k;
+    V[(size_t)pos * G_E + lane] = v;
+    q *= 0.17677669529663687f;  // 1/sqrt(head_dim = 32)
+    sx[lane] = q;
+    __syncwarp();
+    float qs[G_E];
+#pragma unroll
+    for (int i = 0; i < G_E / 4; ++i) {
+      const float4 t4 = reinterpret_cast<const float4*>(sx)[i];
+      qs[4 * i] = t4.x, qs[4 * i + 1] = t4.y, qs[4 * i + 2] = t4.z, qs[4 * i + 3] = t4.w;
+    }
+    __syncwarp();
+    float lmax = -INFINITY;
+    for (int k0 = 0; k0 < pos; k0 += 32) {  // cached keys 0..pos-1, one key per lane
+      const int key = k0 + lane;
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < G_E; ++c) s = fmaf(qs[c], __ldcg(kT + (size_t)c * Tpad + key), s);
+      if (key < pos) {
+        ssc[key] = s;
+        lmax = fmaxf(lmax, s);
+      }
+    }
+    const float s_self = warp_sum(q * k);  // the token attends to itself (causal mask keeps keys <= pos)
+    lmax = fmaxf(warp_max(lmax), s_self);
+    __syncwarp();
+    float lsum = 0.f;
+    for (int key = lane; key < pos; key += 32) {
+      const float pr = expf(ssc[key] - lmax);
+      ssc[key] = pr;
+      lsum += pr;
+    }
+    const float p_self = expf(s_self - lmax);
+    const float inv = 1.0f / (warp_sum(lsum) + p_self);
+    __syncwarp();
+    float o0 = p_self * v, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+    int key = 0;
+    for (; key + 4 <= pos; key += 4) {
+      const float4 p4 = *reinterpret_cast<const float4*>(ssc + key);
+      const float* vr = V + (size_t)key * G_E + lane;
+      o0 = fmaf(p4.x, __ldcg(vr), o0);
+      o1 = fmaf(p4.y, __ldcg(vr + G_E), o1);
+      o2 = fmaf(p4.z, __ldcg(vr + 2 * G_E), o2);
+      o3 = fmaf(p4.w, __ldcg(vr + 3 * G_E), o3);
+    }
+    for (; key < pos; ++key) o0 = fmaf(ssc[key], __ldcg(V + (size_t)key * G_E + lane), o0);
+    const float o = ((o0 + o1) + (o2 + o3)) * inv;
+    __syncwarp();
+    sx[lane] = o;
+    __syncwarp();
+    float y = __ldg(w.proj_b + lane);
+#pragma unroll 8
+    for (int i = 0; i < G_E; ++i) y = fmaf(sx[i], __ldg(w.proj_w + i * G_E + lane), y);
+    x += y;
+    __syncwarp();
+    // ---- MLP ----
+    sx[lane] = layer_norm(x, w.ln2_w, w.ln2_b, lane);
+    __syncwarp();
+    float h0 = __ldg(w.fc_b + lane), h1 = __ldg(w.fc_b + 32 + lane), h2 = __ldg(w.fc_b + 64 + lane),
+          h3 = __ldg(w.fc_b + 96 + lane);
+#pragma unroll 8
+    for (int i = 0; i < G_E; ++i) {
+      const float hv = sx[i];
+      const float* row = w.fc_w + i * G_FF;
+      h0 = fmaf(hv, __ldg(row + lane), h0);
+      h1 = fmaf(hv, __ldg(row + 32 + lane), h1);
+      h2 = fmaf(hv, __ldg(row + 64 + lane), h2);
+      h3 = fmaf(hv, __ldg(row + 96 + lane), h3);
+    }
+    sh[lane] = gelu_new(h0), sh[32 + lane] = gelu_new(h1), sh[64 + lane] = gelu_new(h2), sh[96 + lane] = gelu_new(h3);
+    __syncwarp();
+    float y2 = __ldg(w.fc2_b + lane);
+#pragma unroll 8
+    for (int j = 0; j < G_FF; ++j) y2 = fmaf(sh[j], __ldg(w.fc2_w + j * G_E + lane), y2);
+    x += y2;
+    __syncwarp();
+  }
+  return x;
+}
+
+// ln_f + pred_actions: returns logit[lane] for lane < du (others 0)
+__device__ __forceinline__ float head_logits(const Gpt2Dev& m, float x, float* sx, int lane) {
+  sx[lane] = layer_norm(x, m.lnf_w, m.lnf_b, lane);
+  __syncwarp();
+  float lg = 0.f;
+  if (lane < m.du) {
+    lg = __ldg(m.pred_b + lane);
+    for (int c = 0; c < G_E; ++c) lg = fmaf(sx[c], __ldg(m.pred_wT + c * m.du + lane), lg);
+  }
+  __syncwarp();
+  return lg;
+}
+
+struct WarpScratch {
+  float* sx;
+  float* sh;
+  float* ssc;
+};
+__device__ __forceinline__ WarpScratch warp_scratch(float* smem, int warp, int Tpad) {
+  float* base = smem + (size_t)warp * (G_E + G_FF + Tpad);
+  return WarpScratch{base, base + G_E, base + G_E + G_FF};
+}
+
+// ---------------------------------------------------------------------------------------------
+// Transformer.forward(x)
+// ---------------------------------------------------------------------------------------------
+struct ForwardParams {
+  Gpt2Dev m;
+  const float *query, *cs, *ca, *cns, *cr;
+  int B, T, Ts, test, Tpad;
+  float* out;
+  float* kv;
+};
+
+__global__ void __launch_bounds__(G_THREADS) gpt2_forward_kernel(const ForwardParams p) {
+  extern __shared__ __align__(16) float g_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * G_WARPS + warp;
+  if (b >= p.B) return;
+  const Gpt2Dev& m = p.m;
+  const WarpScratch ws = warp_scratch(g_smem, warp, p.Tpad);
+  float* kv = p.kv + (size_t)b * m.L * 2 * G_E * p.Tpad;
+  const int dx = m.dx, du = m.du, din = m.din;
+  for (int pos = 0; pos <= p.T; ++pos) {
+    // token = [state | action | next_state | reward]; position 0 = query state, zeros elsewhere (models/net.py:45-53)
+    float tok = 0.f;
+    if (lane < din) {
+      if (pos == 0) {
+        tok = lane < dx ? p.query[(size_t)b * dx + lane] : 0.f;
+      } else {
+        const size_t row = (size_t)b * p.Ts + (pos - 1);
+        if (lane < dx)
+          tok = p.cs[row * dx + lane];
+        else if (lane < dx + du)
+          tok = p.ca[row * du + (lane - dx)];
+        else if (lane < 2 * dx + du)
+          tok = p.cns[row * dx + (lane - dx - du)];
+        else
+          tok = p.cr[row];
+      }
+    }
+    float x = __ldg(m.embed_b + lane) + __ldg(m.wpe + (size_t)pos * G_E + lane);
+    for (int i = 0; i < din; ++i) x = fmaf(__shfl_sync(0xffffffffu, tok, i), __ldg(m.embed_wT + i * G_E + lane), x);
+    x = token_forward(m, x, pos, kv, p.Tpad, ws.sx, ws.sh, ws.ssc, lane);
+    if (p.test ? (pos == p.T) : (pos >= 1)) {
+      const float lg = head_logits(m, x, ws.sx, lane);
+      if (lane < du) {
+        if (p.test)
+          p.out[(size_t)b * du + lane] = lg;
+        else
+          p.out[((size_t)b * p.T + (pos - 1)) * du + lane] = lg;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused bandit online loop with the transformer controller
+// ---------------------------------------------------------------------------------------------
+struct OnlineGptParams {
+  Gpt2Dev m;
+  const float* means;
+  double var;
+  int sample;
+  Key key;
+  uint64_t env_id0;
+  int N, H, Tpad;
+  float* kv;
+  float *ctx_s, *ctx_a, *ctx_ns, *ctx_r, *cum_means;
+  double* regret;
+  dpt_gpt2_online_inject_t in;
+  dpt_gpt2_online_dump_t out;
+};
+
+__global__ void __launch_bounds__(G_THREADS) gpt2_online_kernel(const OnlineGptParams p) {
+  extern __shared__ __align__(16) float g_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int env = blockIdx.x * G_WARPS + warp;
+  if (env >= p.N) return;
+  const Gpt2Dev& m = p.m;
+  const WarpScratch ws = warp_scratch(g_smem, warp, p.Tpad);
+  float* kv = p.kv + (size_t)env * m.L * 2 * G_E * p.Tpad;
+  const int du = m.du, H = p.H, N = p.N;
+  const uint64_t gid = p.env_id0 + (uint64_t)env;
+  const float mean_l = lane < du ? p.means[(size_t)env * du + lane] : -INFINITY;
+  const float mmax = warp_max(mean_l);
+  if (p.ctx_s) {
+    for (int h = lane; h < H; h += 32) {
+      p.ctx_s[(size_t)env * H + h] = 1.0f;
+      p.ctx_ns[(size_t)env * H + h] = 1.0f;
+    }
+  }
+  // constant part of every token: bias + state (== 1) column (+ next_state column for context tokens)
+  const float e_state = __ldg(m.embed_wT + 0 * G_E + lane);
+  const float e_next = __ldg(m.embed_wT + (1 + du) * G_E + lane);
+  const float e_rew = __ldg(m.embed_wT + (2 + du) * G_E + lane);
+  const float e_bias = __ldg(m.embed_b + lane);
+  int a_prev = 0;
+  float r_prev = 0.f, z_next = 0.f;
+  for (int h = 0; h < H; ++h) {
+    float x = e_bias + e_state + __ldg(m.wpe + (size_t)h * G_E + lane);
+    if (h > 0) x += __ldg(m.embed_wT + (1 + a_prev) * G_E + lane) + e_next + e_rew * r_prev;
+    x = token_forward(m, x, h, kv, p.Tpad, ws.sx, ws.sh, ws.ssc, lane);
+    const float lg = head_logits(m, x, ws.sx, lane);
+    if (p.out.logits && lane < du) p.out.logits[((size_t)h * N + env) * du + lane] = lg;
+    int a;
+    if (p.sample) {
+      // scipy.special.softmax (float64) + np.random.choice(p): cdf = cumsum(p) / cdf[-1]; searchsorted(u, 'right')
+      const float lm = warp_max(lane < du ? lg : -INFINITY);
+      const double pe = lane < du ? exp((double)lg - (double)lm) : 0.0;
+      double tot = 0.0;
+      for (int j = 0; j < du; ++j) tot = __dadd_rn(tot, __shfl_sync(0xffffffffu, pe, j));
+      const double pj = __ddiv_rn(pe, tot);
+      double acc = 0.0, cdf = 0.0;
+      for (int j = 0; j < du; ++j) {
+        const double v = __shfl_sync(0xffffffffu, pj, j);
+        acc = (j == 0) ? v : __dadd_rn(acc, v);
+        if (j == lane) cdf = acc;
+      }
+      const double last = __shfl_sync(0xffffffffu, cdf, du - 1);
+      cdf = __ddiv_rn(cdf, last);
+      double u;
+      if (p.in.ctrl_u) {
+        u = p.in.ctrl_u[(size_t)h * N + env];
+      } else {  // 53-bit uniform in [0,1) from two words, like numpy's random_sample
+        const uint4 w = philox_words(p.key, gid, (uint32_t)h, STREAM_CTRL);
+        u = ((double)(w.x >> 5) * 67108864.0 + (double)(w.y >> 6)) * (1.0 / 9007199254740992.0);
+      }
+      if (p.out.ctrl_u && lane == 0) p.out.ctrl_u[(size_t)h * N + env] = u;
+      a = __popc(__ballot_sync(0xffffffffu, lane < du - 1 && cdf <= u));
+    } else {  // np.argmax: first maximum
+      const float lm = warp_max(lane < du ? lg : -INFINITY);
+      a = __ffs(__ballot_sync(0xffffffffu, lane < du && lg == lm)) - 1;
+    }
+    float z;
+    if (p.in.reward_z) {
+      z = p.in.reward_z[(size_t)h * N + env];
+    } else if ((h & 1) == 0) {
+      const uint4 w = philox_words(p.key, gid, (uint32_t)(h >> 1), STREAM_ENV_REWARD);
+      box_muller(w.z, w.w, z, z_next);
+    } else {
+      z = z_next;
+    }
+    const float ma = __shfl_sync(0xffffffffu, mean_l, a);
+    const float r = (float)((double)ma + (0.0 + p.var * (double)z));   // envs/bandit_env.py:59
+    if (lane == 0) {
+      if (p.out.reward_z) p.out.reward_z[(size_t)h * N + env] = z;
+      if (p.cum_means) p.cum_means[(size_t)h * N + env] = ma;
+      if (p.regret) {
+        const double reg = (double)mmax - (double)ma;
+        atomicAdd(p.regret + 2 * (size_t)h, reg);
+        atomicAdd(p.regret + 2 * (size_t)h + 1, reg * reg);
+      }
+      if (p.ctx_r) p.ctx_r[(size_t)env * H + h] = r;
+    }
+    if (p.ctx_a && lane < du) p.ctx_a[((size_t)env * H + h) * du + lane] = (lane == a) ? 1.f : 0.f;
+    a_prev = a;
+    r_prev = r;
+  }
+}
+
+__global__ void transpose_kernel(const float* src, float* dst, int rows, int cols) {  // dst[c][r] = src[r][c]
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * cols) dst[(i % cols) * rows + i / cols] = src[i];
+}
+
+static int tpad_for(int T1) { return (T1 + 31) & ~31; }
+
+}  // namespace dpt
+
+using namespace dpt;
+
+extern "C" int dpt_gpt2_create(const dpt_gpt2_weights_t* w, dpt_gpt2_t** out, void* stream) {
+  DPT_CHECK_ARG(w && out, "dpt_gpt2_create: null argument");
+  DPT_CHECK_ARG(w->n_embd == G_E, "dpt_gpt2_create: n_embd=%d, this build supports n_embd == %d (head_dim == warp width)",
+                w->n_embd, G_E);
+  DPT_CHECK_ARG(w->n_layer >= 1 && w->n_layer <= G_MAX_L, "dpt_gpt2_create: n_layer=%d outside [1,%d]", w->n_layer, G_MAX_L);
+  const int din = 2 * w->state_dim + w->action_dim + 1;
+  DPT_CHECK_ARG(w->state_dim >= 1 && w->action_dim >= 1 && din <= 32,
+                "dpt_gpt2_create: token width 2*state_dim+action_dim+1 = %d must be <= 32", din);
+  DPT_CHECK_ARG(w->n_positions >= 1 && w->wpe && w->embed_w && w->embed_b && w->pred_w && w->pred_b && w->lnf_w && w->lnf_b,
+                "dpt_gpt2_create: null weight pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int L = w->n_layer, du = w->action_dim;
+  const size_t per_layer = 4 * G_E + G_E * 3 * G_E + 3 * G_E + G_E * G_E + G_E + G_E * G_FF + G_FF + G_FF * G_E + G_E;
+  const size_t total = (size_t)w->n_positions * G_E + (size_t)din * G_E + G_E + (size_t)G_E * du + du + 2 * G_E + L * per_layer + 4 * (16 + 12 * (size_t)L);
+  dpt_gpt2* m = new dpt_gpt2();
+  DPT_CUDA(cudaMalloc(&m->blob, total * sizeof(float)));
+  float* cur = m->blob;
+  auto take = [&](size_t n) {
+    float* p = cur;
+    cur += (n + 3) & ~size_t(3);
+    return p;
+  };
+  auto copy = [&](const float* src, size_t n) {
+    float* d = take(n);
+    cudaMemcpyAsync(d, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    return (const float*)d;
+  };
+  Gpt2Dev& d = m->dev;
+  d.L = L, d.dx = w->state_dim, d.du = du, d.din = din, d.H = w->horizon, d.n_pos = w->n_positions;
+  d.wpe = copy(w->wpe, (size_t)w->n_positions * G_E);
+  float* ewT = take((size_t)din * G_E);  // embed_transition.weight [E, din] -> [din, E]
+  transpose_kernel<<<(G_E * din + 255) / 256, 256, 0, st>>>(w->embed_w, ewT, G_E, din);
+  d.embed_wT = ewT;
+  d.embed_b = copy(w->embed_b, G_E);
+  float* pwT = take((size_t)G_E * du);   // pred_actions.weight [du, E] -> [E, du]
+  transpose_kernel<<<(G_E * du + 255) / 256, 256, 0, st>>>(w->pred_w, pwT, du, G_E);
+  d.pred_wT = pwT;
+  d.pred_b = copy(w->pred_b, du);
+  d.lnf_w = copy(w->lnf_w, G_E);
+  d.lnf_b = copy(w->lnf_b, G_E);
+  for (int l = 0; l < L; ++l) {
+    LayerW& lw = d.layer[l];
+    DPT_CHECK_ARG(w->ln1_w[l] && w->attn_w[l] && w->proj_w[l] && w->fc_w[l] && w->fc2_w[l], "dpt_gpt2_create: null layer %d weight", l);
+    lw.ln1_w = copy(w->ln1_w[l], G_E), lw.ln1_b = copy(w->ln1_b[l], G_E);
+    lw.attn_w = copy(w->attn_w[l], G_E * 3 * G_E), lw.attn_b = copy(w->attn_b[l], 3 * G_E);
+    lw.proj_w = copy(w->proj_w[l], G_E * G_E), lw.proj_b = copy(w->proj_b[l], G_E);
+    lw.ln2_w = copy(w->ln2_w[l], G_E), lw.ln2_b = copy(w->ln2_b[l], G_E);
+    lw.fc_w = copy(w->fc_w[l], G_E * G_FF), lw.fc_b = copy(w->fc_b[l], G_FF);
+    lw.fc2_w = copy(w->fc2_w[l], G_FF * G_E), lw.fc2_b = copy(w->fc2_b[l], G_E);
+  }
+  DPT_LAUNCH_CHECK();
+  *out = m;
+  return DPT_OK;
+}
+
+extern "C" int dpt_gpt2_destroy(dpt_gpt2_t* m) {
+  if (!m) return DPT_OK;
+  cudaFree(m->blob);
+  delete m;
+  return DPT_OK;
+}
+
+extern "C" uint64_t dpt_gpt2_forward_workspace_bytes(const dpt_gpt2_t* m, int B, int T) {
+  if (!m || B <= 0 || T < 0) return 0;
+  return (uint64_t)B * m->dev.L * 2 * G_E * tpad_for(T + 1) * sizeof(float);
+}
+
+static int launch_smem(const void* kern, size_t smem) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("sequence too long for the per-warp score scratch (%zu B of shared memory): %s", smem, cudaGetErrorString(e));
+      return DPT_ERR_INVALID_ARG;
+    }
+  }
+  return DPT_OK;
+}
+
+extern "C" int dpt_gpt2_forward(dpt_gpt2_t* m, const float* query_states, const float* ctx_states,
+                                const float* ctx_actions, const float* ctx_next_states, const float* ctx_rewards, int B,
+                                int T, int T_stride, int test, int precision, float* out, void* workspace,
+                                uint64_t workspace_bytes, void* stream) {
+  DPT_CHECK_ARG(m, "dpt_gpt2_forward: null model");
+  if (precision != 0) {
+    set_error("dpt_gpt2_forward: precision %d not built in this round (0 = fp32 only)", precision);
+    return DPT_ERR_UNSUPPORTED;
+  }
+  DPT_CHECK_ARG(B >= 0 && T >= 0 && T_stride >= T, "dpt_gpt2_forward: B=%d T=%d T_stride=%d", B, T, T_stride);
+  DPT_CHECK_ARG(T + 1 <= m->dev.n_pos, "dpt_gpt2_forward: sequence %d exceeds n_positions %d", T + 1, m->dev.n_pos);
+  if (B == 0 || (!test && T == 0)) return DPT_OK;
+  DPT_CHECK_ARG(query_states && out && (T == 0 || (ctx_states && ctx_actions && ctx_next_states && ctx_rewards)),
+                "dpt_gpt2_forward: null pointer");
+  DPT_CHECK_ARG(workspace && workspace_bytes >= dpt_gpt2_forward_workspace_bytes(m, B, T),
+                "dpt_gpt2_forward: workspace too small");
+  ForwardParams p{};
+  p.m = m->dev;
+  p.query = query_states, p.cs = ctx_states, p.ca = ctx_actions, p.cns = ctx_next_states, p.cr = ctx_rewards;
+  p.B = B, p.T = T, p.Ts = T_stride, p.test = test, p.Tpad = tpad_for(T + 1);
+  p.out = out, p.kv = reinterpret_cast<float*>(workspace);
+  const size_t smem = (size_t)G_WARPS * (G_E + G_FF + p.Tpad) * sizeof(float);
+  int rc = launch_smem((const void*)gpt2_forward_kernel, smem);
+  if (rc != DPT_OK) return rc;
+  gpt2_forward_kernel<<<(B + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
+  DPT_LAUNCH_CHECK();
+  return DPT_OK;
+}
+
+extern "C" uint64_t dpt_gpt2_online_kv_bytes(const dpt_gpt2_t* m, int N, int H, int precision) {
+  if (!m || N <= 0 || H <= 0 || precision != 0) return 0;
+  return (uint64_t)N * m->dev.L * 2 * G_E * tpad_for(H) * sizeof(float);
+}
+
+extern "C" int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, double var, int sample, uint64_t seed,
+                                    uint64_t env_id0, int N, int H, int precision, void* kv_cache, uint64_t kv_bytes,
+                                    float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
+                                    float* cum_means, double* regret_sums, const dpt_gpt2_online_inject_t* inject,
+                                    const dpt_gpt2_online_dump_t* dump, void* stream) {
+  DPT_CHECK_ARG(m, "dpt_gpt2_online_loop: null model");
+  if (precision != 0) {
+    set_error("dpt_gpt2_online_loop: precision %d not built in this round (0 = fp32 only)", precision);
+    return DPT_ERR_UNSUPPORTED;
+  }
+  DPT_CHECK_ARG(m->dev.dx == 1, "dpt_gpt2_online_loop: bandit loop needs state_dim == 1 (got %d)", m->dev.dx);
+  DPT_CHECK_ARG(N >= 0 && H >= 0, "dpt_gpt2_online_loop: N=%d H=%d", N, H);
+  DPT_CHECK_ARG(H <= m->dev.n_pos, "dpt_gpt2_online_loop: H=%d exceeds n_positions %d", H, m->dev.n_pos);
+  if (N == 0 || H == 0) return DPT_OK;
+  DPT_CHECK_ARG(means && kv_cache && kv_bytes >= dpt_gpt2_online_kv_bytes(m, N, H, 0), "dpt_gpt2_online_loop: null means or kv cache too small");
+  const bool any = ctx_states || ctx_actions || ctx_next_states || ctx_rewards;
+  DPT_CHECK_ARG(!any || (ctx_states && ctx_actions && ctx_next_states && ctx_rewards),
+                "dpt_gpt2_online_loop: context pointers must be all NULL or all non-NULL");
+  OnlineGptParams p{};
+  p.m = m->dev;
+  p.means = means, p.var = var, p.sample = sample;
+  p.key = Key{(uint32_t)seed, (uint32_t)(seed >> 32)};
+  p.env_id0 = env_id0;
+  p.N = N, p.H = H, p.Tpad = tpad_for(H);
+  p.kv = reinterpret_cast<float*>(kv_cache);
+  p.ctx_s = ctx_states, p.ctx_a = ctx_actions, p.ctx_ns = ctx_next_states, p.ctx_r = ctx_rewards;
+  p.cum_means = cum_means, p.regret = regret_sums;
+  if (inject) p.in = *inject;
+  if (dump) p.out = *dump;
+  const size_t smem = (size_t)G_WARPS * (G_E + G_FF + p.Tpad) * sizeof(float);
+  int rc = launch_smem((const void*)gpt2_online_kernel, smem);
+  if (rc != DPT_OK) return rc;
+  gpt2_online_kernel<<<(N + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
+  DPT_LAUNCH_CHECK();
+  return DPT_OK;
+}

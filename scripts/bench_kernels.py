@@ -77,6 +77,24 @@ def main():
                 m, mn = timeit(lambda: kernels.online_loop(kind, means, H, 0.3, 2, 0, materialise=mat, **par), max(3, R // 4))
                 report("online_loop %s N=%d H=%d d=%d materialise=%s" % (kind, N, H, d, mat), N * H, (4 * (3 + d) if mat else 0) + 4, m, mn,
                        trajs_per_s=N / (m * 1e-3))
+    if want("gpt2"):
+        from dpt_b200.models.net import Transformer
+        torch.manual_seed(0)
+        for N, H in [(10000, 500), (2000, 500), (10000, 100)]:
+            m = Transformer({"horizon": H, "state_dim": 1, "action_dim": 5, "n_layer": 4, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True})
+            means, _, _ = kernels.bandit_sample_means(N, 5, 0, 0)
+            m.online_loop(means, H, 0.3, True, 0, 0)
+            mm, mn = timeit(lambda: m.online_loop(means, H, 0.3, True, 1, 0), max(2, R // 4), warm=1)
+            kv_bytes = 4 * 2 * 32 * 4 * (H * (H - 1) / 2) / H        # K/V bytes read per env-step (fp32, mean over t)
+            flops = (4 * (24576 * 2) + 832) + 4 * 128 * (H / 2)        # per env-step
+            report("gpt2_online_loop fp32 N=%d H=%d L=4 E=32 sample" % (N, H), N * H, kv_bytes + 36, mm, mn, trajs_per_s=N / (mm * 1e-3),
+                   kv_cache_gb=N * 4 * 2 * 32 * ((H + 31) // 32 * 32) * 4 / 1e9, gflops=N * H * flops / (mm * 1e-3) / 1e9)
+        m = Transformer({"horizon": 100, "state_dim": 2, "action_dim": 5, "n_layer": 4, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True})
+        B, T = 4096, 100
+        x = {"query_states": torch.rand(B, 2, device="cuda"), "zeros": torch.zeros(B, 10, device="cuda"), "context_states": torch.rand(B, T, 2, device="cuda"),
+             "context_actions": torch.rand(B, T, 5, device="cuda"), "context_next_states": torch.rand(B, T, 2, device="cuda"), "context_rewards": torch.rand(B, T, 1, device="cuda")}
+        mm, mn = timeit(lambda: m(x), max(2, R // 4), warm=1)
+        report("gpt2_forward fp32 B=%d T=%d (darkroom token layout, test=True)" % (B, T), B * (T + 1), 40, mm, mn, tokens_per_s=B * (T + 1) / (mm * 1e-3))
     if want("gpu_bandit_step"):
         N, d = 100000, 5
         means, _, opt_a = kernels.bandit_sample_means(N, d, 0, 0)
