@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(G_THREADS) gpt2_online_kernel(const OnlineGptP
   const float e_bias = __ldg(m.embed_b + lane);
   int a_prev = 0;
   float r_prev = 0.f, z_next = 0.f;
+  double creg = 0.0;
   for (int h = 0; h < H; ++h) {
     float x = e_bias + e_state + __ldg(m.wpe + (size_t)h * G_E + lane);
     if (h > 0) x += __ldg(m.embed_wT + (1 + a_prev) * G_E + lane) + e_next + e_rew * r_prev;
@@ -342,8 +343,9 @@ __global__ void __launch_bounds__(G_THREADS) gpt2_online_kernel(const OnlineGptP
       if (p.cum_means) p.cum_means[(size_t)h * N + env] = ma;
       if (p.regret) {
         const double reg = (double)mmax - (double)ma;
-        atomicAdd(p.regret + 2 * (size_t)h, reg);
-        atomicAdd(p.regret + 2 * (size_t)h + 1, reg * reg);
+        creg += reg;
+        double* dst = p.regret + 4 * (size_t)h;
+        atomicAdd(dst, reg), atomicAdd(dst + 1, reg * reg), atomicAdd(dst + 2, creg), atomicAdd(dst + 3, creg * creg);
       }
       if (p.ctx_r) p.ctx_r[(size_t)env * H + h] = r;
     }

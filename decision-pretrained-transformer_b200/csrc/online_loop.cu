@@ -47,6 +47,7 @@ struct OnlineParams {
 struct WarpTile {
   unsigned char acts[32][OL_T];
   float rew[32][OL_T + 1];
+  float creg[32][OL_T + 1];   // cumulative regret of each env after each buffered step
 };
 
 template <int DMAX>
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
   }
   const double sigma2 = p.p0 * p.p0;  // Thompson: std^2 (ctrls/ctrl_bandit.py:126)
   float z_next = 0.f;
+  double creg = 0.0;  // this env's cumulative regret (evals/eval_bandit.py:176)
   const int nb_ctrl = (d + 3) >> 2;
 
   for (int h0 = 0; h0 < H; h0 += OL_T) {
@@ -267,22 +269,25 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
       if (live && p.cum_means) st_stream(p.cum_means + (size_t)h * N + env, ma);   // get_arm_value :151-153
       tile.acts[lane][t] = (unsigned char)a;
       tile.rew[lane][t] = (float)r;
+      creg += (double)mmax - (double)ma;
+      tile.creg[lane][t] = (float)creg;
     }
     __syncwarp();
     // ------------------------------------------------ flush 32 envs x T steps ----------------
     const int nl = min(32, N - env0w);
-    if (nl > 0 && p.regret && lane < T) {     // per-step regret sums over this warp's envs (evals/eval_bandit.py:169-178)
-      double s1 = 0.0, s2 = 0.0;
+    if (nl > 0 && p.regret && lane < T) {     // per-step sums over this warp's envs (evals/eval_bandit.py:169-178)
+      double s1 = 0.0, s2 = 0.0, c1 = 0.0, c2 = 0.0;
       for (int e = 0; e < nl; ++e) {
         const int ae = tile.acts[e][lane];
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < DMAX; ++j) mx = fmaxf(mx, s_means[e][j]);
         const double reg = (double)mx - (double)s_means[e][ae];
-        s1 += reg, s2 += reg * reg;
+        const double cr = (double)tile.creg[e][lane];
+        s1 += reg, s2 += reg * reg, c1 += cr, c2 += cr * cr;
       }
-      atomicAdd(p.regret + 2 * (size_t)(h0 + lane), s1);
-      atomicAdd(p.regret + 2 * (size_t)(h0 + lane) + 1, s2);
+      double* dst = p.regret + 4 * (size_t)(h0 + lane);
+      atomicAdd(dst, s1), atomicAdd(dst + 1, s2), atomicAdd(dst + 2, c1), atomicAdd(dst + 3, c2);
     }
     if (nl > 0 && materialise) {
       for (int e = 0; e < nl; ++e)

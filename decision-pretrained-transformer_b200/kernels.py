@@ -226,14 +226,14 @@ def online_loop(kind, means, H, var, seed, env_id0=0, p0=0.0, p1=0.0, p2=0.0, ar
                 regret=True, inject=None, dump=False):
     """Fused deploy_online_vec for a classical controller (evals/eval_bandit.py:56-103).
 
-    Returns dict: cum_means [H,N] fp32, regret_sums [H,2] f64 (sum, sum of squares over envs of
-    max(means) - cum_means), and, if materialise, context_* [N,H,.] fp32 [+ 'noise' if dump]."""
+    Returns dict: cum_means [H,N] fp32, regret_sums [H,4] f64 (sums over envs of reg, reg^2, cumreg, cumreg^2 with
+    reg = max(means) - cum_means), and, if materialise, context_* [N,H,.] fp32 [+ 'noise' if dump]."""
     dev = _dev(means.device if torch.is_tensor(means) and means.is_cuda else None)
     means = _as(means, F32, dev)
     N, d = means.shape
     out = {"cum_means": torch.empty((H, N), dtype=F32, device=dev)}
     if regret:
-        out["regret_sums"] = torch.zeros((H, 2), dtype=F64, device=dev)
+        out["regret_sums"] = torch.zeros((H, 4), dtype=F64, device=dev)
     if materialise:
         out.update(context_states=torch.empty((N, H, 1), dtype=F32, device=dev),
                    context_actions=torch.empty((N, H, d), dtype=F32, device=dev),

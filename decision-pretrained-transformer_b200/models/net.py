@@ -189,7 +189,7 @@ class Transformer(nn.Module):
         H = horizon
         out = {"cum_means": torch.empty((H, N), dtype=torch.float32, device=dev)}
         if regret:
-            out["regret_sums"] = torch.zeros((H, 2), dtype=torch.float64, device=dev)
+            out["regret_sums"] = torch.zeros((H, 4), dtype=torch.float64, device=dev)
         if materialise:
             out.update(context_states=torch.empty((N, H, 1), dtype=torch.float32, device=dev),
                        context_actions=torch.empty((N, H, d), dtype=torch.float32, device=dev),

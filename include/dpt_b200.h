@@ -144,9 +144,10 @@ int dpt_arm_stats(const float* ctx_actions, const float* ctx_rewards, int N, int
  *   3 ThompsonSamplingPolicy sample=True :122-251 (p0 = std, p1 = prior_mean, p2 = prior_var)
  *   4 LinUCBPolicy :447-528 (p0 = const; arms f64 [d,lin_d])
  * Outputs: ctx_* (any may be NULL = not materialised), cum_means fp32 [H,N] (expected reward of
- * the chosen arm, envs/bandit_env.py:151-153), regret_sums f64 [H,2] += (sum, sum of squares)
- * over envs of (max(means) - cum_means) (evals/eval_bandit.py:169-178; NULL = skip; must be
- * zeroed by the caller; accumulated with atomics so shards can share it). */
+ * the chosen arm, envs/bandit_env.py:151-153), regret_sums f64 [H,4] += over envs of (reg, reg^2,
+ * cumreg, cumreg^2) with reg = max(means) - cum_means and cumreg its running sum over steps
+ * (evals/eval_bandit.py:169-178: enough for the per-step and cumulative regret mean / sem; NULL =
+ * skip; zeroed by the caller; accumulated with atomics; the [H,4] block is what crosses NVLink). */
 typedef struct {
   const float* reward_z;     /* [H,N] standard normals, env order per step (eval loop order) */
   const float* ctrl_z;       /* Thompson: [H,N,d] standard normals */

@@ -45,6 +45,9 @@ def test_online_loop_injected_matches_reference(dpt, name, ctrls):
         opt = means.max(1)[None, :] - g[c + "_cum_means"]
         _close(_np(out["regret_sums"])[:, 0], opt.sum(1), 1e-6)
         _close(_np(out["regret_sums"])[:, 1], (opt ** 2).sum(1), 1e-6)
+        cr = np.cumsum(opt, axis=0)
+        _close(_np(out["regret_sums"])[:, 2], cr.sum(1), 1e-6)
+        _close(_np(out["regret_sums"])[:, 3], (cr ** 2).sum(1), 1e-6)
 
 
 def test_linear_bandit_injected_matches_reference(dpt):

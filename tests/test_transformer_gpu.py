@@ -123,6 +123,7 @@ def test_online_loop_injected_matches_reference(dpt, name):
     assert bool((out["context_states"] == 1).all()) and bool((out["context_next_states"] == 1).all())
     reg = g["online_means"].max(1)[None] - g["online_cum_means"]
     _close(_np(out["regret_sums"])[:, 0], reg.sum(1), 1e-6)
+    _close(_np(out["regret_sums"])[:, 3], (np.cumsum(reg, axis=0) ** 2).sum(1), 1e-6)
     # KV-cached logits at step h == dense forward over the first h context rows
     for h in (0, 3, H - 1):
         b = {k: out[k][:, :h] for k in ("context_states", "context_actions", "context_next_states", "context_rewards")}
