@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Run ONE kernel target a few times (for ncu captures): python scripts/profile_target.py <target>"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import dpt_b200  # noqa: E402
+from dpt_b200 import kernels  # noqa: E402
+
+t = sys.argv[1]
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+if t == "darkroom":
+    goals = torch.randint(0, 10, (100000, 2), dtype=torch.int32, device="cuda")
+    for i in range(reps):
+        kernels.darkroom_rollin(goals, 10, 100, "uniform", i, 0, None, 1)
+elif t.startswith("online_"):
+    kind = t.split("_")[1]
+    par = {"opt": {}, "emp": dict(p0=1.0), "ucb": dict(p0=1.0), "thompson": dict(p0=0.3, p1=0.5, p2=1 / 12.0),
+           "linucb": dict(p0=1.0, arms=np.random.RandomState(1234).normal(size=(10, 2)) / np.sqrt(2))}[kind]
+    d, H = (10, 200) if kind == "linucb" else (5, 500)
+    means, _, _ = kernels.bandit_sample_means(100000, d, 0, 0)
+    for i in range(reps):
+        kernels.online_loop(kind, means, H, 0.3, i, 0, **par)
+elif t == "gpt2":
+    from dpt_b200.models.net import Transformer
+    torch.manual_seed(0)
+    H = 200
+    m = Transformer({"horizon": H, "state_dim": 1, "action_dim": 5, "n_layer": 4, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True})
+    means, _, _ = kernels.bandit_sample_means(4000, 5, 0, 0)
+    for i in range(reps):
+        m.online_loop(means, H, 0.3, True, i, 0)
+elif t == "bandit":
+    means, _, _ = kernels.bandit_sample_means(125000, 5, 0, 0)
+    out = kernels.bandit_rollin(means, 500, 0.3, 0, 0)
+    for i in range(reps):
+        kernels.bandit_rollin(means, 500, 0.3, i, 0, out=out)
+torch.cuda.synchronize()
+print("done", t)
