@@ -12,9 +12,10 @@
 //       (SURVEY.md §3.3), so a step is ONE token-forward + softmax/categorical draw + env step.
 //   dpt_gpt2_forward     : Transformer.forward(x) for an arbitrary context (dense semantics, computed
 //       causally token by token with a scratch K/V cache).
-// Layout: K is kept transposed, K^T[layer][channel][t] (a lane scores key t = blk*32+lane with 32
-// coalesced loads), V natural [layer][t][channel] (a lane accumulates its channel over t with
-// coalesced 128 B rows).  K/V reads bypass L1 (ld.global.cg) so L1 keeps the ~200 KB of weights that
+// Layout: K and V are both [layer][t][channel] (128 B rows, appended coalesced).  Attention maps a
+// lane to (key group lane/8, channel quad lane%8): one LDG.128 instruction covers 4 keys x 32 channels,
+// 8 are kept in flight per lane (32 keys), the 8-lane dot products are combined by a 7-shuffle
+// butterfly transpose-reduce, softmax is a warp reduction, and PV accumulates float4 channel quads.  K/V reads bypass L1 (ld.global.cg) so L1 keeps the ~200 KB of weights that
 // every warp re-reads; weights are read through the read-only path.  fp32 everywhere, accurate
 // expf/tanhf/sqrtf (the 1e-5 logit parity bar excludes TF32 and .approx forms).
 // Bound: K/V bytes read per token-forward = n_layer * 2 * t * 32 * 4 (HBM once the in-flight caches
@@ -77,8 +78,8 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
                                                float* sh, float* ssc, int lane) {
   for (int l = 0; l < m.L; ++l) {
     const LayerW& w = m.layer[l];
-    float* kT = kv + (size_t)(l * 2) * G_E * Tpad;
-    float* V = kT + (size_t)G_E * Tpad;
+    float* K = kv + (size_t)(l * 2) * G_E * Tpad;
+    float* V = K + (size_t)G_E * Tpad;
     // ---- attention ----
     sx[lane] = layer_norm(x, w.ln1_w, w.ln1_b, lane);
     __syncwarp();
@@ -92,27 +93,43 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
       v = fmaf(hv, __ldg(row + 2 * G_E + lane), v);
     }
     __syncwarp();
-    kT[(size_t)lane * Tpad + pos] = k;
+    K[(size_t)pos * G_E + lane] = k;   // both caches are [t][channel]: appends are coalesced 128 B rows
     V[(size_t)pos * G_E + lane] = v;
     q *= 0.17677669529663687f;  // 1/sqrt(head_dim = 32)
     sx[lane] = q;
     __syncwarp();
-    float qs[G_E];
-#pragma unroll
-    for (int i = 0; i < G_E / 4; ++i) {
-      const float4 t4 = reinterpret_cast<const float4*>(sx)[i];
-      qs[4 * i] = t4.x, qs[4 * i + 1] = t4.y, qs[4 * i + 2] = t4.z, qs[4 * i + 3] = t4.w;
-    }
+    // lane = (key group g = lane/8, channel quad c4 = 4*(lane%8)): one LDG.128 instruction covers 4 keys
+    const int g = lane >> 3, b8 = lane & 7;
+    const float4 q4 = reinterpret_cast<const float4*>(sx)[b8];
+    const float4* K4 = reinterpret_cast<const float4*>(K) + b8;   // row stride = 8 float4
+    const float4* V4 = reinterpret_cast<const float4*>(V) + b8;
     __syncwarp();
     float lmax = -INFINITY;
-    for (int k0 = 0; k0 < pos; k0 += 32) {  // cached keys 0..pos-1, one key per lane
-      const int key = k0 + lane;
-      float s = 0.f;
+    for (int k0 = 0; k0 < pos; k0 += 32) {  // cached keys 0..pos-1, 32 per iteration: 8 row loads in flight per lane
+      float4 kk[8];
 #pragma unroll
-      for (int c = 0; c < G_E; ++c) s = fmaf(qs[c], __ldcg(kT + (size_t)c * Tpad + key), s);
+      for (int i = 0; i < 8; ++i) kk[i] = __ldcg(K4 + (size_t)(k0 + 4 * i + g) * 8);   // in bounds (Tpad % 32 == 0)
+      float pv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pv[i] = fmaf(q4.x, kk[i].x, fmaf(q4.y, kk[i].y, fmaf(q4.z, kk[i].z, q4.w * kk[i].w)));
+      // butterfly transpose-reduce over the 8 lanes of a key group: lane b8 ends with the full dot of chunk i = b8
+      float w4[4], w2[2];
+      const bool u4 = b8 & 4, u2 = b8 & 2, u1 = b8 & 1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float send = u4 ? pv[j] : pv[j + 4], keep = u4 ? pv[j + 4] : pv[j];
+        w4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float send = u2 ? w4[j] : w4[j + 2], keep = u2 ? w4[j + 2] : w4[j];
+        w2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      const float sc = (u1 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, u1 ? w2[0] : w2[1], 1);
+      const int key = k0 + 4 * b8 + g;
       if (key < pos) {
-        ssc[key] = s;
-        lmax = fmaxf(lmax, s);
+        ssc[key] = sc;
+        lmax = fmaxf(lmax, sc);
       }
     }
     const float s_self = warp_sum(q * k);  // the token attends to itself (causal mask keeps keys <= pos)
@@ -127,18 +144,38 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
     const float p_self = expf(s_self - lmax);
     const float inv = 1.0f / (warp_sum(lsum) + p_self);
     __syncwarp();
-    float o0 = p_self * v, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-    int key = 0;
-    for (; key + 4 <= pos; key += 4) {
-      const float4 p4 = *reinterpret_cast<const float4*>(ssc + key);
-      const float* vr = V + (size_t)key * G_E + lane;
-      o0 = fmaf(p4.x, __ldcg(vr), o0);
-      o1 = fmaf(p4.y, __ldcg(vr + G_E), o1);
-      o2 = fmaf(p4.z, __ldcg(vr + 2 * G_E), o2);
-      o3 = fmaf(p4.w, __ldcg(vr + 3 * G_E), o3);
+    float4 oa = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k0 = 0; k0 < pos; k0 += 32) {
+      float4 vv[8];
+      float pr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int key = k0 + 4 * i + g;
+        const bool ok = key < pos;                 // rows >= pos are uninitialised: never touch them
+        vv[i] = ok ? __ldcg(V4 + (size_t)key * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+        pr[i] = ok ? ssc[key] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        oa.x = fmaf(pr[i], vv[i].x, oa.x);
+        oa.y = fmaf(pr[i], vv[i].y, oa.y);
+        oa.z = fmaf(pr[i], vv[i].z, oa.z);
+        oa.w = fmaf(pr[i], vv[i].w, oa.w);
+      }
     }
-    for (; key < pos; ++key) o0 = fmaf(ssc[key], __ldcg(V + (size_t)key * G_E + lane), o0);
-    const float o = ((o0 + o1) + (o2 + o3)) * inv;
+    // sum the 4 key groups (lanes with equal b8), then hand channel `lane` its value
+#pragma unroll
+    for (int o_ = 8; o_ <= 16; o_ <<= 1) {
+      oa.x += __shfl_xor_sync(0xffffffffu, oa.x, o_);
+      oa.y += __shfl_xor_sync(0xffffffffu, oa.y, o_);
+      oa.z += __shfl_xor_sync(0xffffffffu, oa.z, o_);
+      oa.w += __shfl_xor_sync(0xffffffffu, oa.w, o_);
+    }
+    __syncwarp();
+    if (lane < 8) reinterpret_cast<float4*>(sx)[lane] = oa;
+    __syncwarp();
+    const float osum = sx[lane] + p_self * v;
+    const float o = osum * inv;
     __syncwarp();
     sx[lane] = o;
     __syncwarp();

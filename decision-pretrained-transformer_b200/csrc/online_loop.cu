@@ -37,6 +37,7 @@ struct OnlineParams {
   uint64_t env_id0;
   int N, H, d;
   uint32_t magic_d;  // ceil(2^32 / d): floor(x / d) == umulhi(x, magic_d) for the small x used here
+  uint32_t magic_nq; // same for nq = OL_T * d / 4 (float4 per env per full flush)
   float *ctx_s, *ctx_a, *ctx_ns, *ctx_r, *cum_means;
   double* regret;
   dpt_online_inject_t in;
@@ -240,22 +241,32 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
       const double r = (double)ma + (0.0 + p.var * (double)z);          // envs/bandit_env.py:59
       // ------------------------------------------------ controller statistics --------------
       if (KIND == K_EMP || KIND == K_UCB || KIND == K_THOMPSON) {
+        // gather the pulled arm's (sum, count) with selects, update once, scatter back with selects:
+        // no divergence although the lanes of a warp pull different arms
+        double sa = 0.0;
+        int ca = 0;
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j)
+          if (j == a) sa = st.sum[j], ca = st.cnt[j];
+        sa += r;
+        ca += 1;
+        const double n = (double)ca;
+        double n0, n1 = 0.0;
+        if (KIND == K_THOMPSON) {   // update_posterior_all :196-203, over the common denominator var + n*prior_var
+          const double inv = 1.0 / (sigma2 + n * p.p2);
+          n0 = (sigma2 * p.p1 + p.p2 * sa) * inv;          // = w*prior_mean + (1-w)*sum/n,  w = var/(var + n*prior_var)
+          n1 = sqrt(sigma2 * p.p2 * inv);                  // = sqrt(1 / (1/prior_var + n/var))
+        } else {
+          n0 = sa / n;                                      // b / max(1, counts)
+          if (KIND == K_UCB) n1 = p.p0 / fmax(1.0, sqrt(n));  // const / max(1, sqrt(counts)) :366
+        }
 #pragma unroll
         for (int j = 0; j < DMAX; ++j) {
-          if (j == a) {
-            st.sum[j] += r;
-            st.cnt[j] += 1;
-            const double n = (double)st.cnt[j];
-            if (KIND == K_THOMPSON) {                                   // update_posterior_all :196-203
-              const double arm_mean = st.sum[j] / n;
-              const double pw = sigma2 / (sigma2 + n * p.p2);
-              st.aux0[j] = pw * p.p1 + (1.0 - pw) * arm_mean;
-              st.aux1[j] = sqrt(1.0 / (1.0 / p.p2 + n / sigma2));
-            } else {
-              st.aux0[j] = st.sum[j] / n;                               // b / max(1, counts)
-              if (KIND == K_UCB) st.aux1[j] = p.p0 / fmax(1.0, sqrt(n));  // const / max(1, sqrt(counts)) :366
-            }
-          }
+          const bool hit = (j == a);
+          st.sum[j] = hit ? sa : st.sum[j];
+          st.cnt[j] = hit ? ca : st.cnt[j];
+          st.aux0[j] = hit ? n0 : st.aux0[j];
+          if (KIND != K_EMP) st.aux1[j] = hit ? n1 : st.aux1[j];
         }
       } else if (KIND == K_LINUCB) {
         const int ld = p.lin_d;
@@ -295,14 +306,24 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
       if (p.vec) {
         const int nq = (T * d) >> 2;   // float4 per env in this flush
         const int total = nl * nq;
+        const uint32_t magic_nq = (T == OL_T) ? p.magic_nq : (uint32_t)((0x100000000ull + (uint32_t)nq - 1) / (uint32_t)nq);
         for (int i = lane; i < total; i += 32) {
-          const int e = i / nq, q = i - e * nq;
+          const int e = (int)__umulhi((uint32_t)i, magic_nq), q = i - e * nq;
+          // elements 4q..4q+3 of this env's run span at most two steps t0, t0+1 (d >= 4) -- or more for small d
           float v[4];
+          if (d >= 4) {
+            const int t0 = (int)__umulhi((uint32_t)(4 * q), p.magic_d);
+            const int r0 = 4 * q - t0 * d;
+            const int a0 = tile.acts[e][t0], a1 = tile.acts[e][min(t0 + 1, OL_T - 1)];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int el = 4 * q + c;
-            const int t = (d == 1) ? el : (int)__umulhi((uint32_t)el, p.magic_d);
-            v[c] = (tile.acts[e][t] == el - t * d) ? 1.f : 0.f;
+            for (int c = 0; c < 4; ++c) v[c] = (r0 + c < d) ? (a0 == r0 + c ? 1.f : 0.f) : (a1 == r0 + c - d ? 1.f : 0.f);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int el = 4 * q + c;
+              const int t = (d == 1) ? el : (int)__umulhi((uint32_t)el, p.magic_d);
+              v[c] = (tile.acts[e][t] == el - t * d) ? 1.f : 0.f;
+            }
           }
           st_stream(reinterpret_cast<float4*>(p.ctx_a + ((size_t)(env0w + e) * H + h0) * d) + q,
                     make_float4(v[0], v[1], v[2], v[3]));
@@ -413,6 +434,10 @@ extern "C" int dpt_online_loop(int ctrl_kind, double p0, double p1, double p2, c
   p.env_id0 = env_id0;
   p.N = N, p.H = H, p.d = d;
   p.magic_d = (uint32_t)((0x100000000ull + (uint64_t)d - 1) / (uint64_t)d);
+  {
+    const uint64_t nq = (uint64_t)OL_T * d / 4;
+    p.magic_nq = nq > 1 ? (uint32_t)((0x100000000ull + nq - 1) / nq) : 0u;
+  }
   p.ctx_s = ctx_states, p.ctx_a = ctx_actions, p.ctx_ns = ctx_next_states, p.ctx_r = ctx_rewards;
   p.cum_means = cum_means, p.regret = regret_sums;
   if (inject) p.in = *inject;
