@@ -67,6 +67,25 @@ class OptPolicy(Controller):
         return dict(kind="opt")
 
 
+class GreedyOptPolicy(Controller):
+    """ctrls/ctrl_bandit.py:41-54: the context action with the largest observed reward."""
+
+    def __init__(self, env):
+        super().__init__()
+        self.env = env
+
+    def reset(self):
+        return
+
+    def act(self, x):
+        rewards = torch.as_tensor(np.asarray(self.batch["context_rewards"].cpu() if torch.is_tensor(self.batch["context_rewards"])
+                                             else self.batch["context_rewards"])).flatten()
+        acts = self.batch["context_actions"]
+        acts = acts.cpu().numpy() if torch.is_tensor(acts) else np.asarray(acts)
+        self.a = acts[0][int(torch.argmax(rewards))]
+        return self.a
+
+
 class EmpMeanPolicy(Controller):
     """ctrls/ctrl_bandit.py:57-118."""
 

@@ -461,6 +461,49 @@ def deploy_online_vec(means, var, H, ctrl, noise, include_meta=True):
                            "context_next_states": ctx_ns, "context_rewards": ctx_r}
 
 
+def deploy_online_vec_darkroom(goals, dim, Heps, H, horizon, logits_fn, noise, perm_indices=None, sample=True):
+    """evals/eval_darkroom.py:20-84 driving DarkroomEnvVec.deploy (envs/darkroom_env.py:151-175) and
+    DarkroomTransformerController.act (ctrls/ctrl_darkroom.py:35-66).  ``logits_fn(query [N,2], cs, ca,
+    cns, cr) -> [N,5]``.  Returns per-episode returns [N, Heps] and the last context."""
+    assert H % horizon == 0
+    ctx_rollouts = H // horizon
+    N = len(goals)
+    goals = np.asarray(goals)
+    perms = None if perm_indices is None else [DARKROOM_PERMS[int(p)] for p in perm_indices]
+    cs = np.zeros((N, ctx_rollouts, horizon, 2))
+    ca = np.zeros((N, ctx_rollouts, horizon, 5))
+    cns = np.zeros((N, ctx_rollouts, horizon, 2))
+    cr = np.zeros((N, ctx_rollouts, horizon, 1))
+    cum = []
+    for ep in range(Heps):
+        k = min(ep, ctx_rollouts)
+        ctx = (cs[:, :k].reshape(N, -1, 2), ca[:, :k].reshape(N, -1, 5), cns[:, :k].reshape(N, -1, 2), cr[:, :k].reshape(N, -1, 1))
+        state = np.zeros((N, 2), dtype=np.int64)                                   # reset, darkroom_env.py:32-35
+        S, A, NS, R = (np.zeros((N, horizon, 2)), np.zeros((N, horizon, 5)), np.zeros((N, horizon, 2)), np.zeros((N, horizon)))
+        for t in range(horizon):
+            logits = np.asarray(logits_fn(state.astype(np.float64), *ctx), dtype=np.float64)
+            if sample:
+                e = np.exp(logits - logits.max(-1, keepdims=True))                # scipy softmax, temp = 1
+                probs = e / e.sum(-1, keepdims=True)
+                a = np.array([int(choice_cdf(p).searchsorted(noise.uniform01("ctrl_u"), side="right")) for p in probs])
+            else:
+                a = logits.argmax(-1)
+            for e_ in range(N):
+                ns, r = darkroom_transit(state[e_], int(a[e_]), goals[e_], dim, None if perms is None else perms[e_])
+                S[e_, t], NS[e_, t], R[e_, t] = state[e_], ns, r
+                A[e_, t, a[e_]] = 1.0
+                state[e_] = ns
+        cum.append(R.sum(-1))
+        if ep < ctx_rollouts:
+            cs[:, ep], ca[:, ep], cns[:, ep], cr[:, ep, :, 0] = S, A, NS, R
+        else:
+            cs = np.concatenate([cs[:, 1:], S[:, None]], 1)
+            ca = np.concatenate([ca[:, 1:], A[:, None]], 1)
+            cns = np.concatenate([cns[:, 1:], NS[:, None]], 1)
+            cr = np.concatenate([cr[:, 1:], R[:, None, :, None]], 1)
+    return np.stack(cum, axis=1), (cs, ca, cns, cr)
+
+
 def regret_stats(opt_means, alg_means):
     """evals/eval_bandit.py:169-178: inputs [N,H]; returns per-step mean, sem and cumulative mean, sem."""
     diff = np.asarray(opt_means) - np.asarray(alg_means)

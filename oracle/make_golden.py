@@ -275,6 +275,55 @@ def transformer(ref, name, seed, H, n_layer, n_embd, d, N, var):
     print("ok", name)
 
 
+def darkroom_online(ref, name, seed, dim, horizon, H, Heps, n_layer, goals=None, perm_indices=None):
+    import torch
+    torch.manual_seed(seed)
+    cfg = {"horizon": H, "state_dim": 2, "action_dim": 5, "n_layer": n_layer, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True}
+    model = ref.net.Transformer(cfg).to(ref.net.device).eval()
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if "wte" in k:
+                continue
+            if "ln_" in k and k.endswith("weight"):
+                p.add_(0.2 * torch.randn_like(p))
+            elif k.endswith("bias"):
+                p.add_(0.1 * torch.randn_like(p))
+            elif "transformer.h" in k and k.endswith("weight"):
+                p.mul_(5.0)
+            elif "embed_transition.weight" in k:
+                p.mul_(0.3)       # states go up to dim-1: keep activations O(1)
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items() if "wte" not in k and ".attn.bias" not in k
+          and "masked_bias" not in k}
+    if perm_indices is None:
+        envs = [ref.darkroom_env.DarkroomEnv(dim, g, horizon) for g in goals]
+    else:
+        envs = [ref.darkroom_env.DarkroomEnvPermuted(dim, int(pi), horizon) for pi in perm_indices]
+        goals = [[dim - 1, dim - 1]] * len(perm_indices)
+    N = len(envs)
+    np.random.seed(seed)
+    ctrl = ref.ctrl_darkroom.DarkroomTransformerController(model, batch_size=N, sample=True)
+    rc = ref.eval_darkroom.deploy_online_vec(ref.darkroom_env.DarkroomEnvVec(envs), ctrl, Heps, H, horizon)
+
+    def logits_fn(q, cs, ca, cns, cr):
+        batch = {"query_states": torch.tensor(q).float(), "zeros": torch.zeros(N, 10),
+                 "context_states": torch.tensor(cs).float(), "context_actions": torch.tensor(ca).float(),
+                 "context_next_states": torch.tensor(cns).float(), "context_rewards": torch.tensor(cr).float()}
+        with torch.no_grad():
+            lt = model(batch).numpy()
+        o = O.transformer_forward(sd, q, cs, ca, cns, cr, n_layer, test=True)
+        assert np.abs(lt - o).max() < 3e-5 * max(1.0, np.abs(lt).max()), np.abs(lt - o).max()
+        return lt
+    np.random.seed(seed)
+    noise = O.GlobalNoise()
+    oc, _ = O.deploy_online_vec_darkroom(goals, dim, Heps, H, horizon, logits_fn, noise, perm_indices)
+    _eq(rc, oc, (name, "returns"))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), dim=dim, horizon=horizon, H=H, Heps=Heps, n_layer=n_layer, seed=seed,
+                        goals=np.asarray(goals), perm_indices=np.asarray(perm_indices if perm_indices is not None else []),
+                        ctrl_u=noise.arrays()["ctrl_u"].reshape(Heps * horizon, N), ref_returns=rc,
+                        **{"sd/" + k: v for k, v in sd.items()})
+    print("ok", name)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
@@ -292,7 +341,16 @@ def main():
     linear(ref, "linear_bandit", seed=4, N=24, dim=10, lin_d=2, H=30, var=0.3)
     transformer(ref, "transformer_l2", seed=0, H=12, n_layer=2, n_embd=32, d=5, N=8, var=0.3)
     transformer(ref, "transformer_l4", seed=1, H=40, n_layer=4, n_embd=32, d=5, N=4, var=0.3)
+    darkroom_online(ref, "darkroom_online", seed=2, dim=6, horizon=8, H=16, Heps=5, n_layer=2,
+                    goals=[(0, 0), (5, 5), (2, 3), (5, 0), (1, 4), (3, 3), (0, 5)])
+    darkroom_online(ref, "darkroom_online_perm", seed=3, dim=5, horizon=6, H=12, Heps=4, n_layer=3, perm_indices=[0, 7, 57, 119])
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "darkroom_online":
+        ref_ = ref_loader.load()
+        darkroom_online(ref_, "darkroom_online", seed=2, dim=6, horizon=8, H=16, Heps=5, n_layer=2,
+                        goals=[(0, 0), (5, 5), (2, 3), (5, 0), (1, 4), (3, 3), (0, 5)])
+        darkroom_online(ref_, "darkroom_online_perm", seed=3, dim=5, horizon=6, H=12, Heps=4, n_layer=3, perm_indices=[0, 7, 57, 119])
+    else:
+        main()

@@ -82,6 +82,8 @@ def load():
         ns.ctrl_bandit = importlib.import_module("ctrls.ctrl_bandit")
         ns.eval_bandit = importlib.import_module("evals.eval_bandit")
         ns.eval_linear_bandit = importlib.import_module("evals.eval_linear_bandit")
+        ns.ctrl_darkroom = importlib.import_module("ctrls.ctrl_darkroom")
+        ns.eval_darkroom = importlib.import_module("evals.eval_darkroom")
         ns.net = importlib.import_module("models.net")
     finally:
         sys.path.remove(REF_ROOT)

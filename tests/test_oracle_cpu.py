@@ -146,3 +146,18 @@ def test_regret_stats_match_scipy():
     diff = opt - alg
     assert np.allclose(m, diff.mean(0)) and np.allclose(s, scipy.stats.sem(diff, axis=0))
     assert np.allclose(cs, scipy.stats.sem(np.cumsum(diff, axis=1), axis=0))
+
+
+@pytest.mark.parametrize("name", ["darkroom_online", "darkroom_online_perm"])
+def test_darkroom_online_golden(name):
+    """evals/eval_darkroom.py deploy_online_vec: oracle loop + oracle float64 forward on the recorded uniforms."""
+    g = golden(name)
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
+    L = int(g["n_layer"])
+    perms = g["perm_indices"] if len(g["perm_indices"]) else None
+
+    def logits_fn(q, cs, ca, cns, cr):
+        return O.transformer_forward(sd, q, cs, ca, cns, cr, L, test=True)
+    ret, _ = O.deploy_online_vec_darkroom(g["goals"], int(g["dim"]), int(g["Heps"]), int(g["H"]), int(g["horizon"]), logits_fn,
+                                          O.ReplayNoise({"ctrl_u": g["ctrl_u"].reshape(-1)}), perms)
+    assert np.array_equal(ret, g["ref_returns"])

@@ -216,3 +216,34 @@ def test_online_loop_config4_size(dpt):
     b = {k: out[k][idx][:, :H - 1] for k in ("context_states", "context_actions", "context_next_states", "context_rewards")}
     b["query_states"] = torch.ones(len(idx), 1, device="cuda")
     _close(_np(out["noise"]["logits"][H - 1][idx]), _np(m(b)), 5e-6)
+
+
+@pytest.mark.parametrize("name", ["darkroom_online", "darkroom_online_perm"])
+def test_darkroom_online_eval_matches_reference(dpt, name):
+    """evals/eval_darkroom.py deploy_online_vec with DarkroomTransformerController
+    (sample=True) reproduces the reference's per-episode returns from the same np.random seed."""
+    from dpt_b200.models.net import Transformer
+    from dpt_b200.ctrls.ctrl_darkroom import DarkroomOptPolicy, DarkroomTransformerController
+    from dpt_b200.envs.darkroom_env import DarkroomEnv, DarkroomEnvPermuted, DarkroomEnvVec
+    from dpt_b200.evals import eval_darkroom
+    g = golden(name)
+    dim, horizon, H, Heps = int(g["dim"]), int(g["horizon"]), int(g["H"]), int(g["Heps"])
+    m = Transformer({"horizon": H, "state_dim": 2, "action_dim": 5, "n_layer": int(g["n_layer"]), "n_embd": 32, "n_head": 1,
+                     "dropout": 0.0, "test": True})
+    m.load_state_dict({k[3:]: torch.tensor(g[k]) for k in g.files if k.startswith("sd/")}, strict=False)
+    if len(g["perm_indices"]):
+        envs = [DarkroomEnvPermuted(dim, int(pi), horizon) for pi in g["perm_indices"]]
+    else:
+        envs = [DarkroomEnv(dim, goal, horizon) for goal in g["goals"]]
+    N = len(envs)
+    np.random.seed(int(g["seed"]))
+    ret = eval_darkroom.deploy_online_vec(DarkroomEnvVec(envs), DarkroomTransformerController(m, batch_size=N, sample=True),
+                                          Heps, H, horizon)
+    assert ret.shape == (N, Heps) and np.array_equal(ret, g["ref_returns"])
+    # the optimal policy reaches the goal and stays (ctrls/ctrl_darkroom.py:10-20)
+    env = envs[0]
+    obs, acts, nobs, rews = env.deploy(DarkroomOptPolicy(env))
+    assert rews.shape == (horizon,) and rews[-1] == 1
+    trajs = [{"goal": e.goal, "perm_index": getattr(e, "perm_index", 0)} for e in envs]
+    allm, mean, sem = eval_darkroom.online(trajs, m, Heps, H, N, dim, horizon, permuted=bool(len(g["perm_indices"])))
+    assert allm.shape == (N, Heps) and mean.shape == (Heps,) and sem.shape == (Heps,)
