@@ -85,7 +85,7 @@ PROTOTYPES = {
                                 c_void_p, POINTER(OnlineInject), POINTER(OnlineDump), c_void_p]),
     "dpt_gpt2_create": (c_int, [POINTER(Gpt2Weights), POINTER(c_void_p), c_void_p]),
     "dpt_gpt2_destroy": (c_int, [c_void_p]),
-    "dpt_gpt2_forward_workspace_bytes": (c_uint64, [c_void_p, c_int, c_int]),
+    "dpt_gpt2_forward_workspace_bytes": (c_uint64, [c_void_p, c_int, c_int, c_int]),
     "dpt_gpt2_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p, c_void_p, c_uint64, c_void_p]),
     "dpt_gpt2_online_kv_bytes": (c_uint64, [c_void_p, c_int, c_int, c_int]),

@@ -20,6 +20,8 @@
 // expf/tanhf/sqrtf (the 1e-5 logit parity bar excludes TF32 and .approx forms).
 // Bound: K/V bytes read per token-forward = n_layer * 2 * t * 32 * 4 (HBM once the in-flight caches
 // exceed L2), ~0.9 FLOP/B -- HBM-bound, not tensor-bound.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -74,12 +76,11 @@ __device__ __forceinline__ float gelu_new(float x) {  // transformers NewGELUAct
 
 // One token through all layers.  x: this lane's channel of the embedded token (+wpe).  kv: this
 // sequence's cache, [L][2][32][Tpad] floats.  sx[32], sh[128], ssc[Tpad]: per-warp shared scratch.
-__device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int pos, float* kv, int Tpad, float* sx,
+template <bool BF16>
+__device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int pos, void* kv_, int Tpad, float* sx,
                                                float* sh, float* ssc, int lane) {
   for (int l = 0; l < m.L; ++l) {
     const LayerW& w = m.layer[l];
-    float* K = kv + (size_t)(l * 2) * G_E * Tpad;
-    float* V = K + (size_t)G_E * Tpad;
     // ---- attention ----
     sx[lane] = layer_norm(x, w.ln1_w, w.ln1_b, lane);
     __syncwarp();
@@ -92,89 +93,202 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
       k = fmaf(hv, __ldg(row + G_E + lane), k);
       v = fmaf(hv, __ldg(row + 2 * G_E + lane), v);
     }
+    float lmax = -INFINITY, s_self, p_self, inv, osum;
+    if constexpr (!BF16) {
+      __syncwarp();
+      float* K = reinterpret_cast<float*>(kv_) + (size_t)(l * 2) * G_E * Tpad;
+      float* V = K + (size_t)G_E * Tpad;
+      K[(size_t)pos * G_E + lane] = k;   // both caches are [t][channel]: appends are coalesced 128 B rows
+      V[(size_t)pos * G_E + lane] = v;
+      q *= 0.17677669529663687f;  // 1/sqrt(head_dim = 32)
+      sx[lane] = q;
+      __syncwarp();
+      // lane = (key group g = lane/8, channel quad c4 = 4*(lane%8)): one LDG.128 instruction covers 4 keys
+      const int g = lane >> 3, b8 = lane & 7;
+      const float4 q4 = reinterpret_cast<const float4*>(sx)[b8];
+      const float4* K4 = reinterpret_cast<const float4*>(K) + b8;   // row stride = 8 float4
+      const float4* V4 = reinterpret_cast<const float4*>(V) + b8;
+      __syncwarp();
+      for (int k0 = 0; k0 < pos; k0 += 32) {  // cached keys 0..pos-1, 32 per iteration: 8 row loads in flight per lane
+        float4 kk[8];
+  #pragma unroll
+        for (int i = 0; i < 8; ++i) kk[i] = __ldcg(K4 + (size_t)(k0 + 4 * i + g) * 8);   // in bounds (Tpad % 32 == 0)
+        float pv[8];
+  #pragma unroll
+        for (int i = 0; i < 8; ++i) pv[i] = fmaf(q4.x, kk[i].x, fmaf(q4.y, kk[i].y, fmaf(q4.z, kk[i].z, q4.w * kk[i].w)));
+        // butterfly transpose-reduce over the 8 lanes of a key group: lane b8 ends with the full dot of chunk i = b8
+        float w4[4], w2[2];
+        const bool u4 = b8 & 4, u2 = b8 & 2, u1 = b8 & 1;
+  #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float send = u4 ? pv[j] : pv[j + 4], keep = u4 ? pv[j + 4] : pv[j];
+          w4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+  #pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float send = u2 ? w4[j] : w4[j + 2], keep = u2 ? w4[j + 2] : w4[j];
+          w2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        const float sc = (u1 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, u1 ? w2[0] : w2[1], 1);
+        const int key = k0 + 4 * b8 + g;
+        if (key < pos) {
+          ssc[key] = sc;
+          lmax = fmaxf(lmax, sc);
+        }
+      }
+      s_self = warp_sum(q * k);  // the token attends to itself (causal mask keeps keys <= pos)
+      lmax = fmaxf(warp_max(lmax), s_self);
+      __syncwarp();
+      float lsum = 0.f;
+      for (int key = lane; key < pos; key += 32) {
+        const float pr = expf(ssc[key] - lmax);
+        ssc[key] = pr;
+        lsum += pr;
+      }
+      p_self = expf(s_self - lmax);
+      inv = 1.0f / (warp_sum(lsum) + p_self);
+      __syncwarp();
+      float4 oa = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k0 = 0; k0 < pos; k0 += 32) {
+        float4 vv[8];
+        float pr[8];
+  #pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int key = k0 + 4 * i + g;
+          const bool ok = key < pos;                 // rows >= pos are uninitialised: never touch them
+          vv[i] = ok ? __ldcg(V4 + (size_t)key * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+          pr[i] = ok ? ssc[key] : 0.f;
+        }
+  #pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          oa.x = fmaf(pr[i], vv[i].x, oa.x);
+          oa.y = fmaf(pr[i], vv[i].y, oa.y);
+          oa.z = fmaf(pr[i], vv[i].z, oa.z);
+          oa.w = fmaf(pr[i], vv[i].w, oa.w);
+        }
+      }
+      // sum the 4 key groups (lanes with equal b8), then hand channel `lane` its value
+  #pragma unroll
+      for (int o_ = 8; o_ <= 16; o_ <<= 1) {
+        oa.x += __shfl_xor_sync(0xffffffffu, oa.x, o_);
+        oa.y += __shfl_xor_sync(0xffffffffu, oa.y, o_);
+        oa.z += __shfl_xor_sync(0xffffffffu, oa.z, o_);
+        oa.w += __shfl_xor_sync(0xffffffffu, oa.w, o_);
+      }
+      __syncwarp();
+      if (lane < 8) reinterpret_cast<float4*>(sx)[lane] = oa;
+      __syncwarp();
+      osum = sx[lane] + p_self * v;
+    } else {
     __syncwarp();
-    K[(size_t)pos * G_E + lane] = k;   // both caches are [t][channel]: appends are coalesced 128 B rows
-    V[(size_t)pos * G_E + lane] = v;
-    q *= 0.17677669529663687f;  // 1/sqrt(head_dim = 32)
-    sx[lane] = q;
-    __syncwarp();
-    // lane = (key group g = lane/8, channel quad c4 = 4*(lane%8)): one LDG.128 instruction covers 4 keys
-    const int g = lane >> 3, b8 = lane & 7;
-    const float4 q4 = reinterpret_cast<const float4*>(sx)[b8];
-    const float4* K4 = reinterpret_cast<const float4*>(K) + b8;   // row stride = 8 float4
-    const float4* V4 = reinterpret_cast<const float4*>(V) + b8;
-    __syncwarp();
-    float lmax = -INFINITY;
-    for (int k0 = 0; k0 < pos; k0 += 32) {  // cached keys 0..pos-1, 32 per iteration: 8 row loads in flight per lane
-      float4 kk[8];
+      // bf16 cache: rows are 64 B; lane = (key group g = lane/4, channel oct b4 = lane%4); one LDG.128
+      // instruction covers 8 keys x 32 channels; 8 are in flight per lane (64 keys per iteration)
+      __nv_bfloat16* K = reinterpret_cast<__nv_bfloat16*>(kv_) + (size_t)(l * 2) * G_E * Tpad;
+      __nv_bfloat16* V = K + (size_t)G_E * Tpad;
+      K[(size_t)pos * G_E + lane] = __float2bfloat16_rn(k);
+      V[(size_t)pos * G_E + lane] = __float2bfloat16_rn(v);
+      q *= 0.17677669529663687f;
+      sx[lane] = q;
+      __syncwarp();
+      const int g = lane >> 2, b4 = lane & 3;
+      float qv[8];
+      {
+        const float4 qa = reinterpret_cast<const float4*>(sx)[2 * b4], qb = reinterpret_cast<const float4*>(sx)[2 * b4 + 1];
+        qv[0] = qa.x, qv[1] = qa.y, qv[2] = qa.z, qv[3] = qa.w, qv[4] = qb.x, qv[5] = qb.y, qv[6] = qb.z, qv[7] = qb.w;
+      }
+      const uint4* K8 = reinterpret_cast<const uint4*>(K) + b4;   // row stride = 4 uint4
+      const uint4* V8 = reinterpret_cast<const uint4*>(V) + b4;
+      __syncwarp();
+      for (int k0 = 0; k0 < pos; k0 += 64) {
+        uint4 kk[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) kk[i] = __ldcg(K4 + (size_t)(k0 + 4 * i + g) * 8);   // in bounds (Tpad % 32 == 0)
-      float pv[8];
+        for (int i = 0; i < 8; ++i) kk[i] = __ldcg(K8 + (size_t)(k0 + 8 * i + g) * 4);   // in bounds (Tpad % 64 == 0)
+        float pv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) pv[i] = fmaf(q4.x, kk[i].x, fmaf(q4.y, kk[i].y, fmaf(q4.z, kk[i].z, q4.w * kk[i].w)));
-      // butterfly transpose-reduce over the 8 lanes of a key group: lane b8 ends with the full dot of chunk i = b8
-      float w4[4], w2[2];
-      const bool u4 = b8 & 4, u2 = b8 & 2, u1 = b8 & 1;
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t w0 = kk[i].x, w1 = kk[i].y, w2 = kk[i].z, w3 = kk[i].w;
+          float a = qv[0] * __uint_as_float(w0 << 16);
+          a = fmaf(qv[1], __uint_as_float(w0 & 0xffff0000u), a);
+          a = fmaf(qv[2], __uint_as_float(w1 << 16), a);
+          a = fmaf(qv[3], __uint_as_float(w1 & 0xffff0000u), a);
+          a = fmaf(qv[4], __uint_as_float(w2 << 16), a);
+          a = fmaf(qv[5], __uint_as_float(w2 & 0xffff0000u), a);
+          a = fmaf(qv[6], __uint_as_float(w3 << 16), a);
+          pv[i] = fmaf(qv[7], __uint_as_float(w3 & 0xffff0000u), a);
+        }
+        // reduce over the 4 lanes of a key group: 8 partials -> lane b4 keeps chunks i = 2*b4, 2*b4+1
+        const bool u2 = b4 & 2, u1 = b4 & 1;
+        float w4[4], w2_[2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float send = u4 ? pv[j] : pv[j + 4], keep = u4 ? pv[j + 4] : pv[j];
-        w4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        for (int j = 0; j < 4; ++j) {
+          const float send = u2 ? pv[j] : pv[j + 4], keep = u2 ? pv[j + 4] : pv[j];
+          w4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float send = u1 ? w4[j] : w4[j + 2], keep = u1 ? w4[j + 2] : w4[j];
+          w2_[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+        // lane (u2,u1) holds chunks i = 4*u2 + 2*u1 + {0,1}
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int key = k0 + 8 * ((u2 ? 4 : 0) + (u1 ? 2 : 0) + j) + g;
+          if (key < pos) {
+            ssc[key] = w2_[j];
+            lmax = fmaxf(lmax, w2_[j]);
+          }
+        }
+      }
+      s_self = warp_sum(q * k);
+      lmax = fmaxf(warp_max(lmax), s_self);
+      __syncwarp();
+      float lsum = 0.f;
+      for (int key = lane; key < pos; key += 32) {
+        const float pr = expf(ssc[key] - lmax);
+        ssc[key] = pr;
+        lsum += pr;
+      }
+      p_self = expf(s_self - lmax);
+      inv = 1.0f / (warp_sum(lsum) + p_self);
+      __syncwarp();
+      float oa[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) oa[j] = 0.f;
+      for (int k0 = 0; k0 < pos; k0 += 64) {
+        uint4 vv[8];
+        float pr[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int key = k0 + 8 * i + g;
+          const bool ok = key < pos;
+          vv[i] = ok ? __ldcg(V8 + (size_t)key * 4) : make_uint4(0, 0, 0, 0);
+          pr[i] = ok ? ssc[key] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          oa[0] = fmaf(pr[i], __uint_as_float(vv[i].x << 16), oa[0]);
+          oa[1] = fmaf(pr[i], __uint_as_float(vv[i].x & 0xffff0000u), oa[1]);
+          oa[2] = fmaf(pr[i], __uint_as_float(vv[i].y << 16), oa[2]);
+          oa[3] = fmaf(pr[i], __uint_as_float(vv[i].y & 0xffff0000u), oa[3]);
+          oa[4] = fmaf(pr[i], __uint_as_float(vv[i].z << 16), oa[4]);
+          oa[5] = fmaf(pr[i], __uint_as_float(vv[i].z & 0xffff0000u), oa[5]);
+          oa[6] = fmaf(pr[i], __uint_as_float(vv[i].w << 16), oa[6]);
+          oa[7] = fmaf(pr[i], __uint_as_float(vv[i].w & 0xffff0000u), oa[7]);
+        }
       }
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const float send = u2 ? w4[j] : w4[j + 2], keep = u2 ? w4[j + 2] : w4[j];
-        w2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      for (int o_ = 4; o_ <= 16; o_ <<= 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) oa[j] += __shfl_xor_sync(0xffffffffu, oa[j], o_);
       }
-      const float sc = (u1 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, u1 ? w2[0] : w2[1], 1);
-      const int key = k0 + 4 * b8 + g;
-      if (key < pos) {
-        ssc[key] = sc;
-        lmax = fmaxf(lmax, sc);
+      __syncwarp();
+      if (lane < 4) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sx[8 * lane + j] = oa[j];
       }
+      __syncwarp();
+      osum = sx[lane] + p_self * v;
     }
-    const float s_self = warp_sum(q * k);  // the token attends to itself (causal mask keeps keys <= pos)
-    lmax = fmaxf(warp_max(lmax), s_self);
-    __syncwarp();
-    float lsum = 0.f;
-    for (int key = lane; key < pos; key += 32) {
-      const float pr = expf(ssc[key] - lmax);
-      ssc[key] = pr;
-      lsum += pr;
-    }
-    const float p_self = expf(s_self - lmax);
-    const float inv = 1.0f / (warp_sum(lsum) + p_self);
-    __syncwarp();
-    float4 oa = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k0 = 0; k0 < pos; k0 += 32) {
-      float4 vv[8];
-      float pr[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int key = k0 + 4 * i + g;
-        const bool ok = key < pos;                 // rows >= pos are uninitialised: never touch them
-        vv[i] = ok ? __ldcg(V4 + (size_t)key * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
-        pr[i] = ok ? ssc[key] : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        oa.x = fmaf(pr[i], vv[i].x, oa.x);
-        oa.y = fmaf(pr[i], vv[i].y, oa.y);
-        oa.z = fmaf(pr[i], vv[i].z, oa.z);
-        oa.w = fmaf(pr[i], vv[i].w, oa.w);
-      }
-    }
-    // sum the 4 key groups (lanes with equal b8), then hand channel `lane` its value
-#pragma unroll
-    for (int o_ = 8; o_ <= 16; o_ <<= 1) {
-      oa.x += __shfl_xor_sync(0xffffffffu, oa.x, o_);
-      oa.y += __shfl_xor_sync(0xffffffffu, oa.y, o_);
-      oa.z += __shfl_xor_sync(0xffffffffu, oa.z, o_);
-      oa.w += __shfl_xor_sync(0xffffffffu, oa.w, o_);
-    }
-    __syncwarp();
-    if (lane < 8) reinterpret_cast<float4*>(sx)[lane] = oa;
-    __syncwarp();
-    const float osum = sx[lane] + p_self * v;
     const float o = osum * inv;
     __syncwarp();
     sx[lane] = o;
@@ -240,9 +354,10 @@ struct ForwardParams {
   const float *query, *cs, *ca, *cns, *cr;
   int B, T, Ts, test, Tpad;
   float* out;
-  float* kv;
+  void* kv;
 };
 
+template <bool BF16>
 __global__ void __launch_bounds__(G_THREADS) gpt2_forward_kernel(const ForwardParams p) {
   extern __shared__ __align__(16) float g_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -250,7 +365,7 @@ __global__ void __launch_bounds__(G_THREADS) gpt2_forward_kernel(const ForwardPa
   if (b >= p.B) return;
   const Gpt2Dev& m = p.m;
   const WarpScratch ws = warp_scratch(g_smem, warp, p.Tpad);
-  float* kv = p.kv + (size_t)b * m.L * 2 * G_E * p.Tpad;
+  char* kv = reinterpret_cast<char*>(p.kv) + (size_t)b * m.L * 2 * G_E * p.Tpad * (BF16 ? 2 : 4);
   const int dx = m.dx, du = m.du, din = m.din;
   for (int pos = 0; pos <= p.T; ++pos) {
     // token = [state | action | next_state | reward]; position 0 = query state, zeros elsewhere (models/net.py:45-53)
@@ -272,7 +387,7 @@ __global__ void __launch_bounds__(G_THREADS) gpt2_forward_kernel(const ForwardPa
     }
     float x = __ldg(m.embed_b + lane) + __ldg(m.wpe + (size_t)pos * G_E + lane);
     for (int i = 0; i < din; ++i) x = fmaf(__shfl_sync(0xffffffffu, tok, i), __ldg(m.embed_wT + i * G_E + lane), x);
-    x = token_forward(m, x, pos, kv, p.Tpad, ws.sx, ws.sh, ws.ssc, lane);
+    x = token_forward<BF16>(m, x, pos, kv, p.Tpad, ws.sx, ws.sh, ws.ssc, lane);
     if (p.test ? (pos == p.T) : (pos >= 1)) {
       const float lg = head_logits(m, x, ws.sx, lane);
       if (lane < du) {
@@ -296,13 +411,14 @@ struct OnlineGptParams {
   Key key;
   uint64_t env_id0;
   int N, H, Tpad;
-  float* kv;
+  void* kv;
   float *ctx_s, *ctx_a, *ctx_ns, *ctx_r, *cum_means;
   double* regret;
   dpt_gpt2_online_inject_t in;
   dpt_gpt2_online_dump_t out;
 };
 
+template <bool BF16>
 __global__ void __launch_bounds__(G_THREADS) gpt2_online_kernel(const OnlineGptParams p) {
   extern __shared__ __align__(16) float g_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -310,7 +426,7 @@ __global__ void __launch_bounds__(G_THREADS) gpt2_online_kernel(const OnlineGptP
   if (env >= p.N) return;
   const Gpt2Dev& m = p.m;
   const WarpScratch ws = warp_scratch(g_smem, warp, p.Tpad);
-  float* kv = p.kv + (size_t)env * m.L * 2 * G_E * p.Tpad;
+  char* kv = reinterpret_cast<char*>(p.kv) + (size_t)env * m.L * 2 * G_E * p.Tpad * (BF16 ? 2 : 4);
   const int du = m.du, H = p.H, N = p.N;
   const uint64_t gid = p.env_id0 + (uint64_t)env;
   const float mean_l = lane < du ? p.means[(size_t)env * du + lane] : -INFINITY;
@@ -332,7 +448,7 @@ __global__ void __launch_bounds__(G_THREADS) gpt2_online_kernel(const OnlineGptP
   for (int h = 0; h < H; ++h) {
     float x = e_bias + e_state + __ldg(m.wpe + (size_t)h * G_E + lane);
     if (h > 0) x += __ldg(m.embed_wT + (1 + a_prev) * G_E + lane) + e_next + e_rew * r_prev;
-    x = token_forward(m, x, h, kv, p.Tpad, ws.sx, ws.sh, ws.ssc, lane);
+    x = token_forward<BF16>(m, x, h, kv, p.Tpad, ws.sx, ws.sh, ws.ssc, lane);
     const float lg = head_logits(m, x, ws.sx, lane);
     if (p.out.logits && lane < du) p.out.logits[((size_t)h * N + env) * du + lane] = lg;
     int a;
@@ -397,7 +513,7 @@ __global__ void transpose_kernel(const float* src, float* dst, int rows, int col
   if (i < rows * cols) dst[(i % cols) * rows + i / cols] = src[i];
 }
 
-static int tpad_for(int T1) { return (T1 + 31) & ~31; }
+static int tpad_for(int T1, int precision) { return precision ? (T1 + 63) & ~63 : (T1 + 31) & ~31; }
 
 }  // namespace dpt
 
@@ -465,9 +581,9 @@ extern "C" int dpt_gpt2_destroy(dpt_gpt2_t* m) {
   return DPT_OK;
 }
 
-extern "C" uint64_t dpt_gpt2_forward_workspace_bytes(const dpt_gpt2_t* m, int B, int T) {
+extern "C" uint64_t dpt_gpt2_forward_workspace_bytes(const dpt_gpt2_t* m, int B, int T, int precision) {
   if (!m || B <= 0 || T < 0) return 0;
-  return (uint64_t)B * m->dev.L * 2 * G_E * tpad_for(T + 1) * sizeof(float);
+  return (uint64_t)B * m->dev.L * 2 * G_E * tpad_for(T + 1, precision) * (precision ? 2 : 4);
 }
 
 static int launch_smem(const void* kern, size_t smem) {
@@ -486,33 +602,34 @@ extern "C" int dpt_gpt2_forward(dpt_gpt2_t* m, const float* query_states, const 
                                 int T, int T_stride, int test, int precision, float* out, void* workspace,
                                 uint64_t workspace_bytes, void* stream) {
   DPT_CHECK_ARG(m, "dpt_gpt2_forward: null model");
-  if (precision != 0) {
-    set_error("dpt_gpt2_forward: precision %d not built in this round (0 = fp32 only)", precision);
-    return DPT_ERR_UNSUPPORTED;
-  }
+  DPT_CHECK_ARG(precision == 0 || precision == 1, "dpt_gpt2_forward: precision %d (0 = fp32, 1 = bf16 K/V cache)", precision);
   DPT_CHECK_ARG(B >= 0 && T >= 0 && T_stride >= T, "dpt_gpt2_forward: B=%d T=%d T_stride=%d", B, T, T_stride);
   DPT_CHECK_ARG(T + 1 <= m->dev.n_pos, "dpt_gpt2_forward: sequence %d exceeds n_positions %d", T + 1, m->dev.n_pos);
   if (B == 0 || (!test && T == 0)) return DPT_OK;
   DPT_CHECK_ARG(query_states && out && (T == 0 || (ctx_states && ctx_actions && ctx_next_states && ctx_rewards)),
                 "dpt_gpt2_forward: null pointer");
-  DPT_CHECK_ARG(workspace && workspace_bytes >= dpt_gpt2_forward_workspace_bytes(m, B, T),
+  DPT_CHECK_ARG(workspace && workspace_bytes >= dpt_gpt2_forward_workspace_bytes(m, B, T, precision),
                 "dpt_gpt2_forward: workspace too small");
   ForwardParams p{};
   p.m = m->dev;
   p.query = query_states, p.cs = ctx_states, p.ca = ctx_actions, p.cns = ctx_next_states, p.cr = ctx_rewards;
-  p.B = B, p.T = T, p.Ts = T_stride, p.test = test, p.Tpad = tpad_for(T + 1);
-  p.out = out, p.kv = reinterpret_cast<float*>(workspace);
+  p.B = B, p.T = T, p.Ts = T_stride, p.test = test, p.Tpad = tpad_for(T + 1, precision);
+  p.out = out, p.kv = workspace;
   const size_t smem = (size_t)G_WARPS * (G_E + G_FF + p.Tpad) * sizeof(float);
-  int rc = launch_smem((const void*)gpt2_forward_kernel, smem);
+  const void* kern = precision ? (const void*)gpt2_forward_kernel<true> : (const void*)gpt2_forward_kernel<false>;
+  int rc = launch_smem(kern, smem);
   if (rc != DPT_OK) return rc;
-  gpt2_forward_kernel<<<(B + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
+  if (precision)
+    gpt2_forward_kernel<true><<<(B + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
+  else
+    gpt2_forward_kernel<false><<<(B + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
   DPT_LAUNCH_CHECK();
   return DPT_OK;
 }
 
 extern "C" uint64_t dpt_gpt2_online_kv_bytes(const dpt_gpt2_t* m, int N, int H, int precision) {
-  if (!m || N <= 0 || H <= 0 || precision != 0) return 0;
-  return (uint64_t)N * m->dev.L * 2 * G_E * tpad_for(H) * sizeof(float);
+  if (!m || N <= 0 || H <= 0) return 0;
+  return (uint64_t)N * m->dev.L * 2 * G_E * tpad_for(H, precision) * (precision ? 2 : 4);
 }
 
 extern "C" int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, double var, int sample, uint64_t seed,
@@ -521,15 +638,12 @@ extern "C" int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, double va
                                     float* cum_means, double* regret_sums, const dpt_gpt2_online_inject_t* inject,
                                     const dpt_gpt2_online_dump_t* dump, void* stream) {
   DPT_CHECK_ARG(m, "dpt_gpt2_online_loop: null model");
-  if (precision != 0) {
-    set_error("dpt_gpt2_online_loop: precision %d not built in this round (0 = fp32 only)", precision);
-    return DPT_ERR_UNSUPPORTED;
-  }
+  DPT_CHECK_ARG(precision == 0 || precision == 1, "dpt_gpt2_online_loop: precision %d (0 = fp32, 1 = bf16 K/V cache)", precision);
   DPT_CHECK_ARG(m->dev.dx == 1, "dpt_gpt2_online_loop: bandit loop needs state_dim == 1 (got %d)", m->dev.dx);
   DPT_CHECK_ARG(N >= 0 && H >= 0, "dpt_gpt2_online_loop: N=%d H=%d", N, H);
   DPT_CHECK_ARG(H <= m->dev.n_pos, "dpt_gpt2_online_loop: H=%d exceeds n_positions %d", H, m->dev.n_pos);
   if (N == 0 || H == 0) return DPT_OK;
-  DPT_CHECK_ARG(means && kv_cache && kv_bytes >= dpt_gpt2_online_kv_bytes(m, N, H, 0), "dpt_gpt2_online_loop: null means or kv cache too small");
+  DPT_CHECK_ARG(means && kv_cache && kv_bytes >= dpt_gpt2_online_kv_bytes(m, N, H, precision), "dpt_gpt2_online_loop: null means or kv cache too small");
   const bool any = ctx_states || ctx_actions || ctx_next_states || ctx_rewards;
   DPT_CHECK_ARG(!any || (ctx_states && ctx_actions && ctx_next_states && ctx_rewards),
                 "dpt_gpt2_online_loop: context pointers must be all NULL or all non-NULL");
@@ -538,16 +652,20 @@ extern "C" int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, double va
   p.means = means, p.var = var, p.sample = sample;
   p.key = Key{(uint32_t)seed, (uint32_t)(seed >> 32)};
   p.env_id0 = env_id0;
-  p.N = N, p.H = H, p.Tpad = tpad_for(H);
-  p.kv = reinterpret_cast<float*>(kv_cache);
+  p.N = N, p.H = H, p.Tpad = tpad_for(H, precision);
+  p.kv = kv_cache;
   p.ctx_s = ctx_states, p.ctx_a = ctx_actions, p.ctx_ns = ctx_next_states, p.ctx_r = ctx_rewards;
   p.cum_means = cum_means, p.regret = regret_sums;
   if (inject) p.in = *inject;
   if (dump) p.out = *dump;
   const size_t smem = (size_t)G_WARPS * (G_E + G_FF + p.Tpad) * sizeof(float);
-  int rc = launch_smem((const void*)gpt2_online_kernel, smem);
+  const void* kern = precision ? (const void*)gpt2_online_kernel<true> : (const void*)gpt2_online_kernel<false>;
+  int rc = launch_smem(kern, smem);
   if (rc != DPT_OK) return rc;
-  gpt2_online_kernel<<<(N + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
+  if (precision)
+    gpt2_online_kernel<true><<<(N + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
+  else
+    gpt2_online_kernel<false><<<(N + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
   DPT_LAUNCH_CHECK();
   return DPT_OK;
 }

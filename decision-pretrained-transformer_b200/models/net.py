@@ -82,6 +82,7 @@ class Transformer(nn.Module):
         self._handle = None
         self._handle_version = None
         self._workspace = None
+        self.precision = 0      # 0 = fp32 (reference parity 1e-5); 1 = bf16 K/V cache, fp32 arithmetic (2e-2)
 
     # ---- checkpoint compatibility --------------------------------------------------------
     def load_state_dict(self, state_dict, strict=True, **kw):
@@ -167,11 +168,11 @@ class Transformer(nn.Module):
             cs, ca, cns, cr = cs.contiguous(), ca.contiguous(), cns.contiguous(), cr.contiguous()
             stride = T
         out = torch.empty((B, self.action_dim) if self.test else (B, T, self.action_dim), dtype=torch.float32, device=dev)
-        nbytes = lib().dpt_gpt2_forward_workspace_bytes(h, B, T)
+        nbytes = lib().dpt_gpt2_forward_workspace_bytes(h, B, T, self.precision)
         ws = self._scratch(nbytes)
         check(lib().dpt_gpt2_forward(h, q.data_ptr(), cs.data_ptr() if T else None, ca.data_ptr() if T else None,
                                      cns.data_ptr() if T else None, cr.data_ptr() if T else None, B, T, stride,
-                                     1 if self.test else 0, 0, ptr(out), ptr(ws), ws.numel(), stream_ptr()),
+                                     1 if self.test else 0, self.precision, ptr(out), ptr(ws), ws.numel(), stream_ptr()),
               "dpt_gpt2_forward")
         return out
 
@@ -195,7 +196,7 @@ class Transformer(nn.Module):
                        context_actions=torch.empty((N, H, d), dtype=torch.float32, device=dev),
                        context_next_states=torch.empty((N, H, 1), dtype=torch.float32, device=dev),
                        context_rewards=torch.empty((N, H, 1), dtype=torch.float32, device=dev))
-        kv_bytes = lib().dpt_gpt2_online_kv_bytes(h, N, H, 0)
+        kv_bytes = lib().dpt_gpt2_online_kv_bytes(h, N, H, self.precision)
         kv = self._scratch(kv_bytes)
         inj_p, dump_p, keep = None, None, []
         if inject is not None:
@@ -215,7 +216,7 @@ class Transformer(nn.Module):
             for k, t in noise.items():
                 setattr(s2, k, ptr(t))
             dump_p = ctypes.byref(s2)
-        check(lib().dpt_gpt2_online_loop(h, ptr(means), float(var), 1 if sample else 0, seed, env_id0, N, H, 0, ptr(kv),
+        check(lib().dpt_gpt2_online_loop(h, ptr(means), float(var), 1 if sample else 0, seed, env_id0, N, H, self.precision, ptr(kv),
                                          kv.numel(), ptr(out.get("context_states")), ptr(out.get("context_actions")),
                                          ptr(out.get("context_next_states")), ptr(out.get("context_rewards")),
                                          ptr(out["cum_means"]), ptr(out.get("regret_sums")), inj_p, dump_p, stream_ptr()),

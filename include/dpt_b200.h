@@ -202,10 +202,10 @@ int dpt_gpt2_destroy(dpt_gpt2_t* m);
 /* Transformer.forward(x) (models/net.py:41-60): query_states [B,dx], context_* [B,T,.] fp32,
  * context row stride `T_stride` steps (so views context[:, :h] of a [B,H,.] buffer can be passed
  * without a copy, as evals/eval_bandit.py:71-76 does).  test != 0 -> out [B,du] (last position);
- * test == 0 -> out [B,T,du] (positions 1..T).  precision: 0 = fp32 (the only one built in this
- * round; 1 = bf16 tensor-core contractions is reserved and returns DPT_ERR_UNSUPPORTED).
- * workspace: device scratch of dpt_gpt2_forward_workspace_bytes(m, B, T) bytes (per-sequence K/V). */
-uint64_t dpt_gpt2_forward_workspace_bytes(const dpt_gpt2_t* m, int B, int T);
+ * test == 0 -> out [B,T,du] (positions 1..T).  precision: 0 = fp32 everywhere (1e-5 logit bar);
+ * 1 = bf16 K/V cache with fp32 arithmetic (2e-2 bar, half the K/V bytes).
+ * workspace: device scratch of dpt_gpt2_forward_workspace_bytes(m, B, T, precision) bytes (per-sequence K/V). */
+uint64_t dpt_gpt2_forward_workspace_bytes(const dpt_gpt2_t* m, int B, int T, int precision);
 int dpt_gpt2_forward(dpt_gpt2_t* m, const float* query_states, const float* ctx_states, const float* ctx_actions,
                      const float* ctx_next_states, const float* ctx_rewards, int B, int T, int T_stride, int test,
                      int precision, float* out, void* workspace, uint64_t workspace_bytes, void* stream);

@@ -80,15 +80,18 @@ def main():
     if want("gpt2"):
         from dpt_b200.models.net import Transformer
         torch.manual_seed(0)
-        for N, H in [(10000, 500), (2000, 500), (10000, 100)]:
+        for N, H, prec in [(10000, 500, 0), (10000, 500, 1), (2000, 500, 0), (10000, 100, 0), (20000, 500, 1)]:
             m = Transformer({"horizon": H, "state_dim": 1, "action_dim": 5, "n_layer": 4, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True})
+            m.precision = prec
+            esz = 2 if prec else 4
             means, _, _ = kernels.bandit_sample_means(N, 5, 0, 0)
             m.online_loop(means, H, 0.3, True, 0, 0)
             mm, mn = timeit(lambda: m.online_loop(means, H, 0.3, True, 1, 0), max(2, R // 4), warm=1)
-            kv_bytes = 4 * 2 * 32 * 4 * (H * (H - 1) / 2) / H        # K/V bytes read per env-step (fp32, mean over t)
+            kv_bytes = 4 * 2 * 32 * esz * (H * (H - 1) / 2) / H      # K/V bytes read per env-step (mean over t)
             flops = (4 * (24576 * 2) + 832) + 4 * 128 * (H / 2)        # per env-step
-            report("gpt2_online_loop fp32 N=%d H=%d L=4 E=32 sample" % (N, H), N * H, kv_bytes + 36, mm, mn, trajs_per_s=N / (mm * 1e-3),
-                   kv_cache_gb=N * 4 * 2 * 32 * ((H + 31) // 32 * 32) * 4 / 1e9, gflops=N * H * flops / (mm * 1e-3) / 1e9)
+            report("gpt2_online_loop %s N=%d H=%d L=4 E=32 sample" % ("bf16-kv" if prec else "fp32", N, H), N * H, kv_bytes + 36, mm, mn,
+                   trajs_per_s=N / (mm * 1e-3), kv_cache_gb=N * 4 * 2 * 32 * 512 * esz / 1e9, gflops=N * H * flops / (mm * 1e-3) / 1e9)
+            del m
         m = Transformer({"horizon": 100, "state_dim": 2, "action_dim": 5, "n_layer": 4, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True})
         B, T = 4096, 100
         x = {"query_states": torch.rand(B, 2, device="cuda"), "zeros": torch.zeros(B, 10, device="cuda"), "context_states": torch.rand(B, T, 2, device="cuda"),

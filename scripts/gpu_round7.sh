@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_transformer_gpu.py -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
 python scripts/bench_kernels.py --reps 8 --only gpt2 > gpurun_out/kernels_gpt2.jsonl 2> gpurun_out/kernels_gpt2.err; echo "rc=$?"
 python - <<'PY'

@@ -243,7 +243,38 @@ def test_darkroom_online_eval_matches_reference(dpt, name):
     # the optimal policy reaches the goal and stays (ctrls/ctrl_darkroom.py:10-20)
     env = envs[0]
     obs, acts, nobs, rews = env.deploy(DarkroomOptPolicy(env))
-    assert rews.shape == (horizon,) and rews[-1] == 1
+    gx, gy = int(env.goal[0]), int(env.goal[1])
+    assert rews.shape == (horizon,) and rews.sum() == max(0, horizon - max(gx + gy, 1) + 1)
     trajs = [{"goal": e.goal, "perm_index": getattr(e, "perm_index", 0)} for e in envs]
     allm, mean, sem = eval_darkroom.online(trajs, m, Heps, H, N, dim, horizon, permuted=bool(len(g["perm_indices"])))
     assert allm.shape == (N, Heps) and mean.shape == (Heps,) and sem.shape == (Heps,)
+
+
+@pytest.mark.parametrize("name", ["transformer_l2", "transformer_l4"])
+def test_bf16_kv_mode_within_2e2(dpt, name):
+    """precision = 1 (bf16 K/V cache, fp32 arithmetic): logits within 2e-2 relative (north_star bf16 bar)
+    of the reference's fp32 logits; the loop's arms are consistent with the logits it dumped."""
+    g = golden(name)
+    m, sd = _model(dpt, g)
+    m.precision = 1
+    H, L, d = int(g["H"]), int(g["n_layer"]), int(g["d"])
+    for t in (0, 1, 5, H):
+        b = _batch(g, t)
+        m.test = True
+        out = m(b)
+        _close(_np(out), g["logits_t%d" % t], 2e-2)
+        assert t == 0 or not np.array_equal(_np(out), g["logits_t%d" % t])
+    N, var, seed = 16, 0.3, 5
+    means, _, _ = dpt.kernels.bandit_sample_means(N, d, seed, 0)
+    out = m.online_loop(means, H, var, True, seed, 0, dump=True)
+    nz = {k: _np(v).astype(np.float64) for k, v in out["noise"].items()}
+    ca, cr = _np(out["context_actions"]).astype(np.float64), _np(out["context_rewards"]).astype(np.float64)
+    ones = np.ones((N, H, 1))
+    for h in range(H):
+        ref = O.transformer_forward(sd, np.ones((N, 1)), ones[:, :h], ca[:, :h], ones[:, :h], cr[:, :h], L, test=True)
+        _close(nz["logits"][h], ref, 2e-2)
+        lg = nz["logits"][h]
+        e = np.exp(lg - lg.max(-1, keepdims=True))
+        pr = e / e.sum(-1, keepdims=True)
+        a = np.array([int(O.choice_cdf(p).searchsorted(u, side="right")) for p, u in zip(pr, nz["ctrl_u"][h])])
+        assert np.array_equal(a, ca[:, h].argmax(-1))
