@@ -176,8 +176,11 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_fast(const RollinPar
   const int chunks = (H + 63) >> 6;
   const bool inj_actions = (MODE == MODE_INJECT) && p.in.actions != nullptr;
   float st_r = 0.f, st_r2 = 0.f, st_opt = 0.f;
-  for (int task = warp; task < ne * chunks; task += RB_WARPS) {
-    const int e = task / chunks, c = task - e * chunks;
+  int e = 0, c = warp;   // (env, chunk) of this warp's task, advanced without a division
+  while (c >= chunks) c -= chunks, ++e;
+  for (; e < ne; c += RB_WARPS) {
+    while (c >= chunks) c -= chunks, ++e;
+    if (e >= ne) break;
     const int env = env0 + e;
     const int h0 = c * 64 + 2 * lane;
     const size_t row = (size_t)env * H + h0;
@@ -218,11 +221,11 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_fast(const RollinPar
       z1 = p.in.z[row + 1];
     }
     // r = means[a] + var * z   (envs/bandit_env.py:59)
-    if (h0 < H) {
+    {
       const float r0 = fmaf(p.var, z0, s_means[e][a0]);
       const float r1 = fmaf(p.var, z1, s_means[e][a1]);
-      st_stream(reinterpret_cast<float2*>(p.ctx_r + row), make_float2(r0, r1));
-      if (p.stats) {
+      st_stream_if(h0 < H, reinterpret_cast<float2*>(p.ctx_r + row), make_float2(r0, r1));
+      if (p.stats && h0 < H) {
         const int oa = s_opt[e];
         st_r += r0 + r1;
         st_r2 = fmaf(r0, r0, fmaf(r1, r1, st_r2));
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_fast(const RollinPar
       const uint32_t bits = (uint32_t)(((((uint64_t)mhi) << (2 * D)) | mlo) >> off);
       const float4 v = make_float4((bits & 1u) ? 1.f : 0.f, (bits & 2u) ? 1.f : 0.f, (bits & 4u) ? 1.f : 0.f,
                                    (bits & 8u) ? 1.f : 0.f);
-      if (q < n_valid4) st_stream(abase + q, v);
+      st_stream_if(q < n_valid4, abase + q, v);
     }
   }
   if (p.stats) reduce_stats(p.stats, st_r, st_r2, st_opt);

@@ -51,6 +51,18 @@ __device__ __forceinline__ void st_stream(float4* p, float4 v) {
                "f"(v.w)
                : "memory");
 }
+// predicated forms (one instruction, no branch around the store)
+__device__ __forceinline__ void st_stream_if(bool pred, float4* p, float4 v) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+      ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)pred)
+      : "memory");
+}
+__device__ __forceinline__ void st_stream_if(bool pred, float2* p, float2 v) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(p),
+               "f"(v.x), "f"(v.y), "r"((int)pred)
+               : "memory");
+}
 __device__ __forceinline__ void st_stream(float2* p, float2 v) {
   asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
 }

@@ -26,6 +26,7 @@ struct DarkroomParams {
   Key key;
   uint64_t env_id0;
   int N, H, S, envs_per_cta;
+  uint32_t magic_H;  // ceil(2^32 / H) when floor(t / H) == umulhi(t, magic_H) for all CTA-local t, else 0
   float *ctx_s, *ctx_a, *ctx_ns, *ctx_r, *query, *opt;
   dpt_darkroom_inject_t in;
   dpt_darkroom_dump_t out;
@@ -156,7 +157,8 @@ __global__ void __launch_bounds__(DK_THREADS) darkroom_rollin_fast(const Darkroo
     const int t0 = c * 128 + 4 * lane;          // first of this lane's 4 steps (CTA-local)
     uint32_t spk0 = 0, spk1 = 0, npk0 = 0, npk1 = 0, amask = 0, rmask = 0;
     if (t0 < total) {
-      const int el = t0 / H, h0 = t0 - el * H;  // H % 4 == 0: all 4 steps are in env el
+      const int el = p.magic_H ? (int)__umulhi((uint32_t)t0, p.magic_H) : t0 / H;
+      const int h0 = t0 - el * H;  // H % 4 == 0: all 4 steps are in env el
       const int env = env0 + el;
       const EnvInfo e = s_env[el];
       uint4 w = make_uint4(0, 0, 0, 0);
@@ -184,8 +186,7 @@ __global__ void __launch_bounds__(DK_THREADS) darkroom_rollin_fast(const Darkroo
     const size_t cbase = base + (size_t)c * 128;            // first step of the chunk (global flat)
     const int nsteps = min(128, total - c * 128);           // multiple of 4
     // rewards: float4 #lane = this lane's own 4 steps
-    if (4 * lane < nsteps)
-      st_stream(reinterpret_cast<float4*>(p.ctx_r + cbase) + lane,
+    st_stream_if(4 * lane < nsteps, reinterpret_cast<float4*>(p.ctx_r + cbase) + lane,
                 make_float4((float)(rmask & 1), (float)((rmask >> 1) & 1), (float)((rmask >> 2) & 1),
                             (float)((rmask >> 3) & 1)));
     // states / next_states: 2 floats per step -> float4 #f holds steps 2f, 2f+1 = lane f/2, half f%2
@@ -196,14 +197,12 @@ __global__ void __launch_bounds__(DK_THREADS) darkroom_rollin_fast(const Darkroo
       const uint32_t s0 = __shfl_sync(0xffffffffu, spk0, src), s1 = __shfl_sync(0xffffffffu, spk1, src);
       const uint32_t n0 = __shfl_sync(0xffffffffu, npk0, src), n1 = __shfl_sync(0xffffffffu, npk1, src);
       const uint32_t sv = (f & 1) ? s1 : s0, nv = (f & 1) ? n1 : n0;
-      if (2 * f < nsteps) {
-        st_stream(reinterpret_cast<float4*>(p.ctx_s + 2 * cbase) + f,
-                  make_float4((float)(sv & 255), (float)((sv >> 8) & 255), (float)((sv >> 16) & 255),
-                              (float)(sv >> 24)));
-        st_stream(reinterpret_cast<float4*>(p.ctx_ns + 2 * cbase) + f,
-                  make_float4((float)(nv & 255), (float)((nv >> 8) & 255), (float)((nv >> 16) & 255),
-                              (float)(nv >> 24)));
-      }
+      st_stream_if(2 * f < nsteps, reinterpret_cast<float4*>(p.ctx_s + 2 * cbase) + f,
+                   make_float4((float)(sv & 255), (float)((sv >> 8) & 255), (float)((sv >> 16) & 255),
+                               (float)(sv >> 24)));
+      st_stream_if(2 * f < nsteps, reinterpret_cast<float4*>(p.ctx_ns + 2 * cbase) + f,
+                   make_float4((float)(nv & 255), (float)((nv >> 8) & 255), (float)((nv >> 16) & 255),
+                               (float)(nv >> 24)));
     }
     // actions: 5 floats per step, 20 per lane -> float4 #f = lane f/5, bits 4*(f%5)..+3
 #pragma unroll
@@ -211,10 +210,9 @@ __global__ void __launch_bounds__(DK_THREADS) darkroom_rollin_fast(const Darkroo
       const int f = it * 32 + lane;
       const int src = f / 5;
       const uint32_t bits = __shfl_sync(0xffffffffu, amask, src) >> (4 * (f - 5 * src));
-      if (4 * f < 5 * nsteps)
-        st_stream(reinterpret_cast<float4*>(p.ctx_a + 5 * cbase) + f,
-                  make_float4((bits & 1u) ? 1.f : 0.f, (bits & 2u) ? 1.f : 0.f, (bits & 4u) ? 1.f : 0.f,
-                              (bits & 8u) ? 1.f : 0.f));
+      st_stream_if(4 * f < 5 * nsteps, reinterpret_cast<float4*>(p.ctx_a + 5 * cbase) + f,
+                   make_float4((bits & 1u) ? 1.f : 0.f, (bits & 2u) ? 1.f : 0.f, (bits & 4u) ? 1.f : 0.f,
+                               (bits & 8u) ? 1.f : 0.f));
     }
   }
 }
@@ -317,6 +315,7 @@ extern "C" int dpt_darkroom_rollin(const int32_t* goals, const int32_t* perm_ind
   if (e < min_e) e = min_e;
   if (e > DK_MAX_ENVS) e = DK_MAX_ENVS;
   p.envs_per_cta = e;
+  p.magic_H = (H > 1 && (uint64_t)e * H * H < 0xffffffffull) ? (uint32_t)((0x100000000ull + (uint64_t)H - 1) / (uint64_t)H) : 0u;
   const int grid = (N + e - 1) / e;
   const bool fast = H > 0 && (H % 4 == 0) && dim <= 256 && aligned16(ctx_states) && aligned16(ctx_actions) &&
                     aligned16(ctx_next_states) && aligned16(ctx_rewards);

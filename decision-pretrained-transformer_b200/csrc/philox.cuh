@@ -61,8 +61,19 @@ __device__ __forceinline__ float u32_open0(uint32_t w) {
 
 // Box-Muller: two words -> two standard normals (fast intrinsics; the oracle consumes the
 // dumped values, so only the distribution matters here -- checked statistically in tests).
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
-  float r = sqrtf(-2.0f * __logf(u32_open0(a)));
+  // u in [2^-33, 1]: no denormals, -2 ln u = -2 ln2 * lg2 u >= 0
+  float r = fast_sqrt(-1.3862943611198906f * fast_lg2(u32_open0(a)));
   float s, c;
   __sincosf((float)b * 1.4629180792671596e-09f /* 2*pi*2^-32 */, &s, &c);
   z0 = r * c;
