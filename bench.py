@@ -127,6 +127,47 @@ def run_reference(args, rank):
     }))
 
 
+def other_workloads(kernels, torch):
+    """The other BASELINE.json configs on one GPU (informational; CUDA events, 3 warm-up + 5 timed runs each)."""
+    import numpy as np
+
+    def t(fn, reps=5, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    out = {}
+    goals = torch.tensor(np.repeat(np.stack(np.meshgrid(np.arange(10), np.arange(10), indexing="ij"), -1).reshape(-1, 2), 1000, 0),
+                         dtype=torch.int32, device="cuda")
+    ms = t(lambda: kernels.darkroom_rollin(goals, 10, 100, "uniform", 1, 0, None, 1))
+    out["config2_darkroom_rollin_100k_envs_H100"] = {"ms": ms, "env_steps_per_s": 1e7 / (ms * 1e-3), "gbs": 4e8 / (ms * 1e-3) / 1e9}
+    means10, _, _ = kernels.bandit_sample_means(100000, 10, 0, 0)
+    arms = np.random.RandomState(1234).normal(size=(10, 2)) / np.sqrt(2)
+    ms = t(lambda: kernels.online_loop("thompson", means10, 200, 0.3, 1, 0, p0=0.3, p1=0.0, p2=1.0))
+    out["config3_linear_thompson_collect_100k_envs_H200_d10"] = {"ms": ms, "env_steps_per_s": 2e7 / (ms * 1e-3), "trajs_per_s": 1e5 / (ms * 1e-3)}
+    ms = t(lambda: kernels.online_loop("linucb", means10, 200, 0.3, 1, 0, p0=1.0, arms=arms, materialise=False))
+    out["config3_linucb_online_100k_envs_H200_d10"] = {"ms": ms, "env_steps_per_s": 2e7 / (ms * 1e-3), "trajs_per_s": 1e5 / (ms * 1e-3)}
+    import dpt_b200
+    from dpt_b200.models.net import Transformer
+    torch.manual_seed(0)
+    m = Transformer({"horizon": 500, "state_dim": 1, "action_dim": 5, "n_layer": 4, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True})
+    means5, _, _ = kernels.bandit_sample_means(10000, 5, 0, 0)
+    for prec, name in ((0, "fp32"), (1, "bf16_kv")):
+        m.precision = prec
+        ms = t(lambda: m.online_loop(means5, 500, 0.3, True, 1, 0), reps=2, warm=1)
+        esz = 2 if prec else 4
+        out["config4_gpt2_online_eval_10k_envs_H500_" + name] = {
+            "ms": ms, "trajs_per_s": 1e4 / (ms * 1e-3), "env_steps_per_s": 5e6 / (ms * 1e-3),
+            "kv_read_gbs": 1e4 * 4 * 2 * 32 * esz * (500 * 499 / 2) / (ms * 1e-3) / 1e9}
+    return out
+
+
 # ----------------------------------------------------------------------------- our arm --------
 def main():
     ap = argparse.ArgumentParser()
@@ -136,6 +177,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--no-other", action="store_true", help="skip the secondary workloads (configs 2-4)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -264,6 +306,9 @@ def main():
         w_.wait()
     torch.cuda.synchronize()
     totals = (gathered.view(n_slots, world, 3).sum((0, 1)) if world > 1 else stats.sum(0))
+    other = None
+    if rank == 0 and world == 1 and not args.no_other:
+        other = other_workloads(kernels, torch)
     if rank == 0:
         st = totals
         n_tot = world * N * H * (args.steps + args.warmup)
@@ -280,6 +325,8 @@ def main():
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
+        if other is not None:
+            line["other_workloads"] = other
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

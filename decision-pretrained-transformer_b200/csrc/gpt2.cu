@@ -33,8 +33,12 @@ constexpr int G_MAX_L = 8;
 constexpr int G_WARPS = 4;
 constexpr int G_THREADS = G_WARPS * 32;
 
+// Weight matrices [in][out] are repacked at create time into per-lane quads:
+//   P[(in/4)][out/32][lane][in%4]  so that one LDG.128 gives a lane the 4 consecutive-input weights of its
+//   output (out = group*32 + lane), consumed by two FFMA2 (fma.rn.f32x2) against an LDS.128 of the inputs.
 struct LayerW {
-  const float *ln1_w, *ln1_b, *attn_w, *attn_b, *proj_w, *proj_b, *ln2_w, *ln2_b, *fc_w, *fc_b, *fc2_w, *fc2_b;
+  const float *ln1_w, *ln1_b, *attn_b, *proj_b, *ln2_w, *ln2_b, *fc_b, *fc2_b;
+  const float4 *attn_wP, *proj_wP, *fc_wP, *fc2_wP;
 };
 
 struct Gpt2Dev {
@@ -70,6 +74,36 @@ __device__ __forceinline__ float layer_norm(float x, const float* w, const float
   return dv * (1.0f / sqrtf(var + 1e-5f)) * __ldg(w + lane) + __ldg(b + lane);
 }
 
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return d;
+}
+
+// out[g] = bias[g*32 + lane] + sum_i xs[i] * W[i][g*32 + lane]  for g < G, W packed as described at LayerW.
+// Two float2 accumulators per output (4 partial sums) keep the dependent FFMA2 chain at IN/4.
+template <int IN, int G>
+__device__ __forceinline__ void matvec_packed(const float* xs, const float4* wP, const float* bias, int lane, float* out) {
+  float2 acc[G][2];
+#pragma unroll
+  for (int g = 0; g < G; ++g) acc[g][0] = make_float2(__ldg(bias + g * 32 + lane), 0.f), acc[g][1] = make_float2(0.f, 0.f);
+#pragma unroll 4
+  for (int iq = 0; iq < IN / 4; ++iq) {
+    const float4 xv = reinterpret_cast<const float4*>(xs)[iq];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float4 wv = __ldg(wP + (size_t)(iq * G + g) * 32 + lane);
+      acc[g][0] = ffma2(make_float2(xv.x, xv.y), make_float2(wv.x, wv.y), acc[g][0]);
+      acc[g][1] = ffma2(make_float2(xv.z, xv.w), make_float2(wv.z, wv.w), acc[g][1]);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g) out[g] = (acc[g][0].x + acc[g][0].y) + (acc[g][1].x + acc[g][1].y);
+}
+
 __device__ __forceinline__ float gelu_new(float x) {  // transformers NewGELUActivation
   return 0.5f * x * (1.0f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
 }
@@ -84,15 +118,10 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
     // ---- attention ----
     sx[lane] = layer_norm(x, w.ln1_w, w.ln1_b, lane);
     __syncwarp();
-    float q = __ldg(w.attn_b + lane), k = __ldg(w.attn_b + G_E + lane), v = __ldg(w.attn_b + 2 * G_E + lane);
-#pragma unroll 8
-    for (int i = 0; i < G_E; ++i) {
-      const float hv = sx[i];
-      const float* row = w.attn_w + i * 3 * G_E;
-      q = fmaf(hv, __ldg(row + lane), q);
-      k = fmaf(hv, __ldg(row + G_E + lane), k);
-      v = fmaf(hv, __ldg(row + 2 * G_E + lane), v);
-    }
+    float qkv[3];
+    matvec_packed<G_E, 3>(sx, w.attn_wP, w.attn_b, lane, qkv);
+    float q = qkv[0];
+    const float k = qkv[1], v = qkv[2];
     float lmax = -INFINITY, s_self, p_self, inv, osum;
     if constexpr (!BF16) {
       __syncwarp();
@@ -293,30 +322,19 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
     __syncwarp();
     sx[lane] = o;
     __syncwarp();
-    float y = __ldg(w.proj_b + lane);
-#pragma unroll 8
-    for (int i = 0; i < G_E; ++i) y = fmaf(sx[i], __ldg(w.proj_w + i * G_E + lane), y);
+    float y;
+    matvec_packed<G_E, 1>(sx, w.proj_wP, w.proj_b, lane, &y);
     x += y;
     __syncwarp();
     // ---- MLP ----
     sx[lane] = layer_norm(x, w.ln2_w, w.ln2_b, lane);
     __syncwarp();
-    float h0 = __ldg(w.fc_b + lane), h1 = __ldg(w.fc_b + 32 + lane), h2 = __ldg(w.fc_b + 64 + lane),
-          h3 = __ldg(w.fc_b + 96 + lane);
-#pragma unroll 8
-    for (int i = 0; i < G_E; ++i) {
-      const float hv = sx[i];
-      const float* row = w.fc_w + i * G_FF;
-      h0 = fmaf(hv, __ldg(row + lane), h0);
-      h1 = fmaf(hv, __ldg(row + 32 + lane), h1);
-      h2 = fmaf(hv, __ldg(row + 64 + lane), h2);
-      h3 = fmaf(hv, __ldg(row + 96 + lane), h3);
-    }
-    sh[lane] = gelu_new(h0), sh[32 + lane] = gelu_new(h1), sh[64 + lane] = gelu_new(h2), sh[96 + lane] = gelu_new(h3);
+    float hh[4];
+    matvec_packed<G_E, 4>(sx, w.fc_wP, w.fc_b, lane, hh);
+    sh[lane] = gelu_new(hh[0]), sh[32 + lane] = gelu_new(hh[1]), sh[64 + lane] = gelu_new(hh[2]), sh[96 + lane] = gelu_new(hh[3]);
     __syncwarp();
-    float y2 = __ldg(w.fc2_b + lane);
-#pragma unroll 8
-    for (int j = 0; j < G_FF; ++j) y2 = fmaf(sh[j], __ldg(w.fc2_w + j * G_E + lane), y2);
+    float y2;
+    matvec_packed<G_FF, 1>(sh, w.fc2_wP, w.fc2_b, lane, &y2);
     x += y2;
     __syncwarp();
   }
@@ -513,6 +531,15 @@ __global__ void transpose_kernel(const float* src, float* dst, int rows, int col
   if (i < rows * cols) dst[(i % cols) * rows + i / cols] = src[i];
 }
 
+// dst[((iq * G + g) * 32 + lane) * 4 + r] = src[(4 iq + r) * Out + g * 32 + lane],  G = Out / 32
+__global__ void pack_quads_kernel(const float* src, float* dst, int In, int Out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= In * Out) return;
+  const int r = i & 3, lane = (i >> 2) & 31, rest = i >> 7;
+  const int G = Out / 32, g = rest % G, iq = rest / G;
+  dst[i] = src[(size_t)(4 * iq + r) * Out + g * 32 + lane];
+}
+
 static int tpad_for(int T1, int precision) { return precision ? (T1 + 63) & ~63 : (T1 + 31) & ~31; }
 
 }  // namespace dpt
@@ -563,11 +590,16 @@ extern "C" int dpt_gpt2_create(const dpt_gpt2_weights_t* w, dpt_gpt2_t** out, vo
     LayerW& lw = d.layer[l];
     DPT_CHECK_ARG(w->ln1_w[l] && w->attn_w[l] && w->proj_w[l] && w->fc_w[l] && w->fc2_w[l], "dpt_gpt2_create: null layer %d weight", l);
     lw.ln1_w = copy(w->ln1_w[l], G_E), lw.ln1_b = copy(w->ln1_b[l], G_E);
-    lw.attn_w = copy(w->attn_w[l], G_E * 3 * G_E), lw.attn_b = copy(w->attn_b[l], 3 * G_E);
-    lw.proj_w = copy(w->proj_w[l], G_E * G_E), lw.proj_b = copy(w->proj_b[l], G_E);
+    auto pack = [&](const float* src, int In, int Out) {
+      float* d = take((size_t)In * Out);
+      pack_quads_kernel<<<(In * Out + 255) / 256, 256, 0, st>>>(src, d, In, Out);
+      return reinterpret_cast<const float4*>(d);
+    };
+    lw.attn_wP = pack(w->attn_w[l], G_E, 3 * G_E), lw.attn_b = copy(w->attn_b[l], 3 * G_E);
+    lw.proj_wP = pack(w->proj_w[l], G_E, G_E), lw.proj_b = copy(w->proj_b[l], G_E);
     lw.ln2_w = copy(w->ln2_w[l], G_E), lw.ln2_b = copy(w->ln2_b[l], G_E);
-    lw.fc_w = copy(w->fc_w[l], G_E * G_FF), lw.fc_b = copy(w->fc_b[l], G_FF);
-    lw.fc2_w = copy(w->fc2_w[l], G_FF * G_E), lw.fc2_b = copy(w->fc2_b[l], G_E);
+    lw.fc_wP = pack(w->fc_w[l], G_E, G_FF), lw.fc_b = copy(w->fc_b[l], G_FF);
+    lw.fc2_wP = pack(w->fc2_w[l], G_FF, G_E), lw.fc2_b = copy(w->fc2_b[l], G_E);
   }
   DPT_LAUNCH_CHECK();
   *out = m;
