@@ -220,11 +220,16 @@ def main():
     stats = torch.zeros((n_slots, 3), dtype=torch.float64, device=dev)
     gathered = torch.zeros((n_slots, 3 * world), dtype=torch.float64, device=dev)
     pending = []
+    gather_marks = [0]
+
+    GATHER_EVERY = 8   # statistics of 8 consecutive passes travel in one NCCL call (same bytes, fewer rendezvous)
 
     def step(i):
         kernels.bandit_rollin(means, H, VAR, seed + i, env_id0, out=out, stats=stats[i])
-        if world > 1:
-            pending.append(dist.all_gather_into_tensor(gathered[i], stats[i], async_op=True))
+        if world > 1 and ((i + 1) % GATHER_EVERY == 0 or i + 1 == n_slots or i + 1 == args.warmup):
+            lo = max(j for j in gather_marks if j <= i)
+            gather_marks.append(i + 1)
+            pending.append(dist.all_gather_into_tensor(gathered[lo:i + 1].view(-1), stats[lo:i + 1].view(-1), async_op=True))
 
     def barrier():
         if world > 1:
@@ -305,7 +310,10 @@ def main():
     for w_ in pending:
         w_.wait()
     torch.cuda.synchronize()
-    totals = (gathered.view(n_slots, world, 3).sum((0, 1)) if world > 1 else stats.sum(0))
+    if world > 1:   # every call wrote [world, k, 3] into gathered[lo:hi] (as a flat block): summing all of it is order-free
+        totals = gathered.view(-1, 3).sum(0)
+    else:
+        totals = stats.sum(0)
     other = None
     if rank == 0 and world == 1 and not args.no_other:
         other = other_workloads(kernels, torch)

@@ -233,6 +233,11 @@ int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, double var, int samp
                          double* regret_sums, const dpt_gpt2_online_inject_t* inject,
                          const dpt_gpt2_online_dump_t* dump, void* stream);
 
+/* ---------------------------------------------------------------- bring-up / regression ----
+ * D[128,N] = A[128,K] * B[N,K]^T through tcgen05.mma (bf16 operands, fp32 accumulate in tensor memory):
+ * the self-test of the UMMA helpers (descriptors, 128 B swizzle, TMEM loads) used by the dense forward. */
+int dpt_debug_umma_gemm(const float* A, const float* B, float* D, int N, int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
