@@ -162,7 +162,7 @@ class Transformer(nn.Module):
         B, T = ca.shape[0], ca.shape[1]
         # context views [:, :h] of a [B,H,.] buffer are passed with their row stride, without a copy
         stride = ca.stride(0) // max(1, ca.shape[2]) if T > 0 else 0
-        ok = T > 0 and all(t.stride(-1) == 1 and t.stride(1) == t.shape[2] and t.stride(0) == stride * t.shape[2]
+        ok = T > 0 and stride >= T and all(t.stride(-1) == 1 and t.stride(1) == t.shape[2] and t.stride(0) == stride * t.shape[2]
                            for t in (cs, ca, cns, cr.reshape(B, T, 1) if cr.dim() == 2 else cr))
         if not ok:
             cs, ca, cns, cr = cs.contiguous(), ca.contiguous(), cns.contiguous(), cr.contiguous()

@@ -278,3 +278,50 @@ def test_bf16_kv_mode_within_2e2(dpt, name):
         pr = e / e.sum(-1, keepdims=True)
         a = np.array([int(O.choice_cdf(p).searchsorted(u, side="right")) for p, u in zip(pr, nz["ctrl_u"][h])])
         assert np.array_equal(a, ca[:, h].argmax(-1))
+
+
+@pytest.mark.parametrize("dx,du,L", [(2, 5, 4), (1, 5, 3), (1, 10, 2)])
+def test_dense_tensor_core_forward(dpt, dx, du, L):
+    """precision = 1, sequences <= 128 tokens: the tcgen05 dense kernel (bf16 operands, fp32 accumulate in
+    TMEM) against the fp32 path and the float64 oracle at the 2e-2 bar; longer sequences fall back to the
+    bf16-K/V token-sequential kernel."""
+    from dpt_b200.models.net import Transformer
+    torch.manual_seed(dx * 100 + du)
+    cfg = {"horizon": 160, "state_dim": dx, "action_dim": du, "n_layer": L, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True}
+    m = Transformer(cfg)
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if "wte" not in k:
+                p.add_(0.1 * torch.randn_like(p))
+    sd = {k: v.cpu().numpy() for k, v in m.state_dict().items()}
+    rs = np.random.RandomState(1)
+    B, Tmax = 37, 160
+    q = rs.randint(0, 10, (B, dx)).astype(np.float64) if dx == 2 else np.ones((B, dx))
+    cs = rs.randint(0, 10, (B, Tmax, dx)).astype(np.float64) if dx == 2 else np.ones((B, Tmax, dx))
+    cns = rs.randint(0, 10, (B, Tmax, dx)).astype(np.float64) if dx == 2 else np.ones((B, Tmax, dx))
+    ca, cr = np.eye(du)[rs.randint(0, du, (B, Tmax))], rs.normal(0.5, 0.5, (B, Tmax, 1))
+    f = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda")   # noqa: E731
+    full = {"context_states": f(cs), "context_actions": f(ca), "context_next_states": f(cns), "context_rewards": f(cr)}
+    for t in (0, 1, 17, 63, 64, 100, 127, 128, 150):
+        x = {k: v[:, :t] for k, v in full.items()}
+        x["query_states"] = f(q)
+        for test in (True, False):
+            if not test and t == 0:
+                continue
+            m.test = test
+            m.precision = 0
+            ref = m(x)
+            m.precision = 1
+            out = m(x)
+            assert out.shape == ref.shape
+            _close(_np(out), _np(ref), 2e-2)
+            assert not torch.equal(out, ref)
+        if t in (17, 127):
+            o64 = O.transformer_forward(sd, q, cs[:, :t], ca[:, :t], cns[:, :t], cr[:, :t], L, test=False)
+            _close(_np(out), o64, 2e-2)
+    m.precision = 1
+    m.test = True
+    big = {k: v[:1, :100].expand(300, -1, -1) for k, v in full.items()}     # many CTAs, identical sequences
+    big["query_states"] = f(q)[:1].expand(300, -1)
+    o = m(big)
+    assert float((o - o[0]).abs().max()) == 0.0
