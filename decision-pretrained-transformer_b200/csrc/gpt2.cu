@@ -532,7 +532,7 @@ extern "C" int dpt_gpt2_create(const dpt_gpt2_weights_t* w, dpt_gpt2_t** out, vo
   cudaStream_t st = (cudaStream_t)stream;
   const int L = w->n_layer, du = w->action_dim;
   const size_t per_layer = 4 * G_E + G_E * 3 * G_E + 3 * G_E + G_E * G_E + G_E + G_E * G_FF + G_FF + G_FF * G_E + G_E;
-  const size_t total = (size_t)w->n_positions * G_E + (size_t)din * G_E + G_E + (size_t)G_E * du + du + 2 * G_E + L * (per_layer + WIMG_BYTES / 4) + 4 * (16 + 13 * (size_t)L);
+  const size_t total = (size_t)w->n_positions * G_E + (size_t)din * G_E + G_E + (size_t)G_E * du + du + 2 * G_E + L * (2 * per_layer + WIMG_BYTES / 4) + 4 * (16 + 17 * (size_t)L);
   dpt_gpt2* m = new dpt_gpt2();
   DPT_CUDA(cudaMalloc(&m->blob, total * sizeof(float)));
   float* cur = m->blob;
@@ -573,6 +573,8 @@ extern "C" int dpt_gpt2_create(const dpt_gpt2_weights_t* w, dpt_gpt2_t** out, vo
     lw.ln2_w = copy(w->ln2_w[l], G_E), lw.ln2_b = copy(w->ln2_b[l], G_E);
     lw.fc_wP = pack(w->fc_w[l], G_E, G_FF), lw.fc_b = copy(w->fc_b[l], G_FF);
     lw.fc2_wP = pack(w->fc2_w[l], G_FF, G_E), lw.fc2_b = copy(w->fc2_b[l], G_E);
+    lw.attn_w = copy(w->attn_w[l], G_E * 3 * G_E), lw.proj_w = copy(w->proj_w[l], G_E * G_E);
+    lw.fc_w = copy(w->fc_w[l], G_E * G_FF), lw.fc2_w = copy(w->fc2_w[l], G_FF * G_E);
     unsigned char* img = reinterpret_cast<unsigned char*>(take(WIMG_BYTES / 4));   // tcgen05 B-operand image (bf16)
     gpt2_pack_wimg(w->attn_w[l], w->proj_w[l], w->fc_w[l], w->fc2_w[l], img, st);
     lw.wimg = reinterpret_cast<const uint4*>(img);
@@ -616,12 +618,12 @@ extern "C" int dpt_gpt2_forward(dpt_gpt2_t* m, const float* query_states, const 
   if (B == 0 || (!test && T == 0)) return DPT_OK;
   DPT_CHECK_ARG(query_states && out && (T == 0 || (ctx_states && ctx_actions && ctx_next_states && ctx_rewards)),
                 "dpt_gpt2_forward: null pointer");
-  if (precision == 1 && T + 1 <= 128) {   // dense tensor-core path (tcgen05, bf16 operands): no K/V scratch needed
+  if (T + 1 <= 128) {   // dense path, one CTA per sequence, no K/V scratch: tcgen05 (bf16 operands) or CUDA-core fp32
     DenseParams dp{};
     dp.m = m->dev;
     dp.query = query_states, dp.cs = ctx_states, dp.ca = ctx_actions, dp.cns = ctx_next_states, dp.cr = ctx_rewards;
     dp.B = B, dp.T = T, dp.Ts = T_stride, dp.test = test, dp.out = out;
-    return gpt2_dense_launch(dp, (cudaStream_t)stream);
+    return precision == 1 ? gpt2_dense_launch(dp, (cudaStream_t)stream) : gpt2_dense_fp32_launch(dp, (cudaStream_t)stream);
   }
   DPT_CHECK_ARG(workspace && workspace_bytes >= dpt_gpt2_forward_workspace_bytes(m, B, T, precision),
                 "dpt_gpt2_forward: workspace too small");

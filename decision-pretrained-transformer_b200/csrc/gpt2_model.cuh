@@ -17,6 +17,7 @@ constexpr int G_THREADS = G_WARPS * 32;
 struct LayerW {
   const float *ln1_w, *ln1_b, *attn_b, *proj_b, *ln2_w, *ln2_b, *fc_b, *fc2_b;
   const float4 *attn_wP, *proj_wP, *fc_wP, *fc2_wP;
+  const float *attn_w, *proj_w, *fc_w, *fc2_w;   // original [in][out] layouts (dense fp32 kernel)
   const uint4* wimg;  // bf16 B-operand image for the tcgen05 dense forward (see gpt2_dense.cu), 40 KB
 };
 
@@ -47,7 +48,8 @@ struct DenseParams {
   int B, T, Ts, test;
   float* out;
 };
-int gpt2_dense_launch(const DenseParams& p, cudaStream_t st);   // gpt2_dense.cu
+int gpt2_dense_launch(const DenseParams& p, cudaStream_t st);        // gpt2_dense.cu (tcgen05, bf16 operands)
+int gpt2_dense_fp32_launch(const DenseParams& p, cudaStream_t st);   // gpt2_dense_fp32.cu (CUDA cores, fp32)
 void gpt2_pack_wimg(const float* attn_w, const float* proj_w, const float* fc_w, const float* fc2_w, unsigned char* img,
                     cudaStream_t st);
 }  // namespace dpt
