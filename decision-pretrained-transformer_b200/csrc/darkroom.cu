@@ -276,9 +276,78 @@ __global__ void darkroom_opt_kernel(const int32_t* states, const int32_t* goals,
   for (int j = 0; j < 5; ++j) actions[5 * (size_t)env + j] = (j == oa) ? 1.f : 0.f;
 }
 
+// One episode per env from a logits table: thread = env.
+__global__ void darkroom_policy_rollout_kernel(const float* __restrict__ logits, const int32_t* goals,
+                                               const int32_t* perm_index, int dim, int horizon, int sample, Key key,
+                                               uint64_t env_id0, uint32_t episode, int N, float* st, float* ac, float* ns,
+                                               float* rw, float* returns, const double* inject_u, double* dump_u) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= N) return;
+  DarkroomParams p{};
+  p.goals = goals, p.perm_index = perm_index;
+  const EnvInfo e = load_env(p, env);
+  Step s;
+  s.sx = 0, s.sy = 0;                                     // reset (envs/darkroom_env.py:32-35)
+  float ret = 0.f;
+  for (int t = 0; t < horizon; ++t) {
+    const float* lg = logits + ((size_t)env * dim * dim + (size_t)s.sx * dim + s.sy) * 5;
+    float l[5];
+    float lm = -INFINITY;
+    for (int j = 0; j < 5; ++j) l[j] = lg[j], lm = fmaxf(lm, l[j]);
+    int a = 0;
+    if (sample) {   // scipy softmax (float64, temp = 1) + np.random.choice(p): ctrls/ctrl_darkroom.py:49-54
+      double pe[5], tot = 0.0;
+      for (int j = 0; j < 5; ++j) pe[j] = exp((double)l[j] - (double)lm), tot = __dadd_rn(tot, pe[j]);
+      double acc = 0.0, cdf[5];
+      for (int j = 0; j < 5; ++j) {
+        const double pj = __ddiv_rn(pe[j], tot);
+        acc = (j == 0) ? pj : __dadd_rn(acc, pj);
+        cdf[j] = acc;
+      }
+      double u;
+      if (inject_u) {
+        u = inject_u[(size_t)t * N + env];
+      } else {
+        const uint4 w = philox_words(key, env_id0 + (uint64_t)env, episode * 65536u + (uint32_t)t, STREAM_CTRL);
+        u = ((double)(w.x >> 5) * 67108864.0 + (double)(w.y >> 6)) * (1.0 / 9007199254740992.0);
+      }
+      if (dump_u) dump_u[(size_t)t * N + env] = u;
+      for (int j = 0; j < 4; ++j) a += (__ddiv_rn(cdf[j], cdf[4]) <= u);
+    } else {
+      for (int j = 1; j < 5; ++j)
+        if (l[j] > l[a]) a = j;                            // np.argmax: first maximum
+    }
+    s.a = a;
+    transit(s, e, dim);
+    const size_t row = (size_t)env * horizon + t;
+    st[2 * row] = (float)s.sx, st[2 * row + 1] = (float)s.sy;
+    ns[2 * row] = (float)s.nx, ns[2 * row + 1] = (float)s.ny;
+    rw[row] = (float)s.r;
+    for (int j = 0; j < 5; ++j) ac[5 * row + j] = (j == a) ? 1.f : 0.f;
+    ret += (float)s.r;
+    s.sx = s.nx, s.sy = s.ny;
+  }
+  if (returns) returns[env] = ret;
+}
+
 }  // namespace dpt
 
 using namespace dpt;
+
+extern "C" int dpt_darkroom_policy_rollout(const float* logits, const int32_t* goals, const int32_t* perm_index, int dim,
+                                           int horizon, int sample, uint64_t seed, uint64_t env_id0, int64_t episode,
+                                           int N, float* states, float* actions, float* next_states, float* rewards,
+                                           float* returns, const double* inject_u, double* dump_u, void* stream) {
+  DPT_CHECK_ARG(N >= 0 && horizon >= 0 && dim >= 1 && horizon < 65536 && episode >= 0,
+                "dpt_darkroom_policy_rollout: N=%d horizon=%d dim=%d", N, horizon, dim);
+  if (N == 0 || horizon == 0) return DPT_OK;
+  DPT_CHECK_ARG(logits && goals && states && actions && next_states && rewards, "dpt_darkroom_policy_rollout: null pointer");
+  darkroom_policy_rollout_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      logits, goals, perm_index, dim, horizon, sample, Key{(uint32_t)seed, (uint32_t)(seed >> 32)}, env_id0,
+      (uint32_t)episode, N, states, actions, next_states, rewards, returns, inject_u, dump_u);
+  DPT_LAUNCH_CHECK();
+  return DPT_OK;
+}
 
 extern "C" int dpt_darkroom_rollin(const int32_t* goals, const int32_t* perm_index, int dim, int mode, uint64_t seed,
                                    uint64_t env_id0, int N, int H, int n_samples, float* ctx_states,

@@ -343,7 +343,7 @@ __device__ __forceinline__ WarpScratch warp_scratch(float* smem, int warp, int T
 struct ForwardParams {
   Gpt2Dev m;
   const float *query, *cs, *ca, *cns, *cr;
-  int B, T, Ts, test, Tpad;
+  int B, T, Ts, test, Tpad, share;
   float* out;
   void* kv;
 };
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(G_THREADS) gpt2_forward_kernel(const ForwardPa
       if (pos == 0) {
         tok = lane < dx ? p.query[(size_t)b * dx + lane] : 0.f;
       } else {
-        const size_t row = (size_t)b * p.Ts + (pos - 1);
+        const size_t row = (size_t)(b / p.share) * p.Ts + (pos - 1);
         if (lane < dx)
           tok = p.cs[row * dx + lane];
         else if (lane < dx + du)
@@ -609,11 +609,12 @@ static int launch_smem(const void* kern, size_t smem) {
 
 extern "C" int dpt_gpt2_forward(dpt_gpt2_t* m, const float* query_states, const float* ctx_states,
                                 const float* ctx_actions, const float* ctx_next_states, const float* ctx_rewards, int B,
-                                int T, int T_stride, int test, int precision, float* out, void* workspace,
+                                int T, int T_stride, int ctx_share, int test, int precision, float* out, void* workspace,
                                 uint64_t workspace_bytes, void* stream) {
   DPT_CHECK_ARG(m, "dpt_gpt2_forward: null model");
   DPT_CHECK_ARG(precision == 0 || precision == 1, "dpt_gpt2_forward: precision %d (0 = fp32, 1 = bf16 K/V cache)", precision);
   DPT_CHECK_ARG(B >= 0 && T >= 0 && T_stride >= T, "dpt_gpt2_forward: B=%d T=%d T_stride=%d", B, T, T_stride);
+  DPT_CHECK_ARG(ctx_share >= 1, "dpt_gpt2_forward: ctx_share=%d must be >= 1", ctx_share);
   DPT_CHECK_ARG(T + 1 <= m->dev.n_pos, "dpt_gpt2_forward: sequence %d exceeds n_positions %d", T + 1, m->dev.n_pos);
   if (B == 0 || (!test && T == 0)) return DPT_OK;
   DPT_CHECK_ARG(query_states && out && (T == 0 || (ctx_states && ctx_actions && ctx_next_states && ctx_rewards)),
@@ -622,7 +623,7 @@ extern "C" int dpt_gpt2_forward(dpt_gpt2_t* m, const float* query_states, const 
     DenseParams dp{};
     dp.m = m->dev;
     dp.query = query_states, dp.cs = ctx_states, dp.ca = ctx_actions, dp.cns = ctx_next_states, dp.cr = ctx_rewards;
-    dp.B = B, dp.T = T, dp.Ts = T_stride, dp.test = test, dp.out = out;
+    dp.B = B, dp.T = T, dp.Ts = T_stride, dp.test = test, dp.share = ctx_share, dp.out = out;
     return precision == 1 ? gpt2_dense_launch(dp, (cudaStream_t)stream) : gpt2_dense_fp32_launch(dp, (cudaStream_t)stream);
   }
   DPT_CHECK_ARG(workspace && workspace_bytes >= dpt_gpt2_forward_workspace_bytes(m, B, T, precision),
@@ -630,7 +631,7 @@ extern "C" int dpt_gpt2_forward(dpt_gpt2_t* m, const float* query_states, const 
   ForwardParams p{};
   p.m = m->dev;
   p.query = query_states, p.cs = ctx_states, p.ca = ctx_actions, p.cns = ctx_next_states, p.cr = ctx_rewards;
-  p.B = B, p.T = T, p.Ts = T_stride, p.test = test, p.Tpad = tpad_for(T + 1, precision);
+  p.B = B, p.T = T, p.Ts = T_stride, p.test = test, p.Tpad = tpad_for(T + 1, precision), p.share = ctx_share;
   p.out = out, p.kv = workspace;
   const size_t smem = (size_t)G_WARPS * (G_E + G_FF + p.Tpad) * sizeof(float);
   const void* kern = precision ? (const void*)gpt2_forward_kernel<true> : (const void*)gpt2_forward_kernel<false>;

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(DN_THREADS) gpt2_dense_kernel(const DenseParam
       if (tid == 0) {
         for (int i = 0; i < dx; ++i) tok[i] = p.query[(size_t)b * dx + i];
       } else {
-        const size_t row = (size_t)b * p.Ts + (tid - 1);
+        const size_t row = (size_t)(b / p.share) * p.Ts + (tid - 1);
         for (int i = 0; i < dx; ++i) tok[i] = p.cs[row * dx + i];
         for (int i = 0; i < du; ++i) tok[dx + i] = p.ca[row * du + i];
         for (int i = 0; i < dx; ++i) tok[dx + du + i] = p.cns[row * dx + i];

@@ -45,7 +45,7 @@ constexpr int WIMG_BYTES = 40960;
 struct DenseParams {
   Gpt2Dev m;
   const float *query, *cs, *ca, *cns, *cr;
-  int B, T, Ts, test;
+  int B, T, Ts, test, share;   // share: sequences per context row
   float* out;
 };
 int gpt2_dense_launch(const DenseParams& p, cudaStream_t st);        // gpt2_dense.cu (tcgen05, bf16 operands)

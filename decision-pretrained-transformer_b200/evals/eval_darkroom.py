@@ -14,9 +14,60 @@ from ..ctrls.ctrl_darkroom import DarkroomOptPolicy, DarkroomTransformerControll
 from ..envs.darkroom_env import DarkroomEnv, DarkroomEnvPermuted, DarkroomEnvVec
 
 
+def deploy_online_vec_device(vec_env, model, Heps, H, horizon, sample=True, seed=None, env_id0=0, inject_u=None, dump=False):
+    """The same loop with everything on the device and TWO launches per episode.
+
+    Within an episode the context is fixed, so the controller's logits depend only on the query state.
+    Instead of `horizon` sequential forwards per episode, ONE batched dense forward evaluates all
+    dim*dim query states of every env against its context (ctx_share = dim*dim: the states of an env
+    share one context row), and a rollout kernel then plays the episode from that logits table
+    (softmax + categorical draw + grid transition per step).  Results are identical to the step-by-step
+    loop given the same uniforms (``inject_u`` f64 [Heps*horizon, N]).  Returns a dict with
+    ``returns`` [N,Heps] (device) and the final context tensors [, ``u``]."""
+    from .. import rng
+    assert H % horizon == 0
+    ctx_rollouts = H // horizon
+    dev = kernels._dev()
+    n = vec_env.num_envs
+    dim = vec_env.envs[0].dim
+    goals = torch.as_tensor(np.stack([e.goal for e in vec_env.envs]), dtype=torch.int32).to(dev)
+    perms = [getattr(e, "perm_index", None) for e in vec_env.envs]
+    perm = None if perms[0] is None else torch.as_tensor(perms, dtype=torch.int32).to(dev)
+    key = rng.next_key() if seed is None else seed
+    g = torch.arange(dim, device=dev, dtype=torch.float32)
+    grid = torch.stack(torch.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)          # index x*dim + y
+    q = grid.repeat(n, 1).contiguous()
+    names = ("states", "actions", "next_states", "rewards")
+    ctx = {k: torch.zeros((n, 0, w), device=dev) for k, w in zip(names, (2, 5, 2, 1))}
+    inj = None if inject_u is None else torch.as_tensor(np.asarray(inject_u), dtype=torch.float64).to(dev)
+    rets, us = [], []
+    was_test = model.test
+    model.test = True
+    for ep in range(Heps):
+        logits = model.forward({"query_states": q, "context_states": ctx["states"], "context_actions": ctx["actions"],
+                                "context_next_states": ctx["next_states"], "context_rewards": ctx["rewards"]},
+                               ctx_share=dim * dim)
+        ro = kernels.darkroom_policy_rollout(logits.view(n, dim * dim, 5), goals, dim, horizon, sample, key, env_id0, ep, perm,
+                                             None if inj is None else inj[ep * horizon:(ep + 1) * horizon].contiguous(), dump)
+        rets.append(ro["returns"])
+        if dump:
+            us.append(ro["u"])
+        drop = horizon if ep >= ctx_rollouts else 0          # slide the window by one episode (:73-82)
+        ctx = {k: torch.cat((ctx[k][:, drop:], ro[k]), dim=1).contiguous() for k in names}
+    model.test = was_test
+    out = {"returns": torch.stack(rets, dim=1), "context": ctx}
+    if dump:
+        out["u"] = torch.cat(us, dim=0)
+    return out
+
+
 def deploy_online_vec(vec_env, controller, Heps, H, horizon):
     """evals/eval_darkroom.py:20-84.  Returns per-episode returns [num_envs, Heps]."""
     assert H % horizon == 0
+    if (isinstance(vec_env, DarkroomEnvVec) and isinstance(controller, DarkroomTransformerController)
+            and getattr(controller, "fused", True) and controller.temp == 1.0):
+        out = deploy_online_vec_device(vec_env, controller.model, Heps, H, horizon, sample=controller.sample)
+        return out["returns"].cpu().numpy().astype(np.float64)
     ctx_rollouts = H // horizon
     dev = kernels._dev()
     n = vec_env.num_envs

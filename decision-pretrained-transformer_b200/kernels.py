@@ -271,3 +271,25 @@ def online_loop(kind, means, H, var, seed, env_id0=0, p0=0.0, p1=0.0, p2=0.0, ar
     if noise is not None:
         out["noise"] = noise
     return out
+
+
+def darkroom_policy_rollout(logits, goals, dim, horizon, sample, seed, env_id0=0, episode=0, perm_index=None,
+                            inject_u=None, dump=False):
+    """One darkroom episode per env from a logits table [N, dim*dim, 5] (see dpt_darkroom_policy_rollout).
+    Returns dict: context rows of the episode [N,horizon,.] fp32, returns [N] [, u [horizon,N] f64]."""
+    dev = _dev(logits.device)
+    logits = _as(logits, F32, dev)
+    goals = _as(goals, I32, dev)
+    perm = None if perm_index is None else _as(perm_index, I32, dev)
+    N = goals.shape[0]
+    out = {"states": torch.empty((N, horizon, 2), dtype=F32, device=dev), "actions": torch.empty((N, horizon, 5), dtype=F32, device=dev),
+           "next_states": torch.empty((N, horizon, 2), dtype=F32, device=dev), "rewards": torch.empty((N, horizon, 1), dtype=F32, device=dev),
+           "returns": torch.empty((N,), dtype=F32, device=dev)}
+    inj = None if inject_u is None else _as(inject_u, F64, dev)
+    if dump:
+        out["u"] = torch.zeros((horizon, N), dtype=F64, device=dev)
+    check(lib().dpt_darkroom_policy_rollout(ptr(logits), ptr(goals), ptr(perm), dim, horizon, 1 if sample else 0, seed, env_id0,
+                                            episode, N, ptr(out["states"]), ptr(out["actions"]), ptr(out["next_states"]),
+                                            ptr(out["rewards"]), ptr(out["returns"]), ptr(inj), ptr(out.get("u")), stream_ptr()),
+          "dpt_darkroom_policy_rollout")
+    return out

@@ -153,17 +153,20 @@ class Transformer(nn.Module):
 
     # ---- models/net.py:41-60 --------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, x):
+    def forward(self, x, ctx_share=1):
+        """``ctx_share`` > 1: ``query_states`` has ctx_share rows per context row (see dpt_gpt2_forward)."""
         dev = kernels._dev()
         h = self.handle()
         f = lambda t: t.to(device=dev, dtype=torch.float32)   # noqa: E731
         q = f(x["query_states"]).contiguous()
         cs, ca, cns, cr = f(x["context_states"]), f(x["context_actions"]), f(x["context_next_states"]), f(x["context_rewards"])
-        B, T = ca.shape[0], ca.shape[1]
+        B, T = ca.shape[0] * ctx_share, ca.shape[1]
+        Bc = ca.shape[0]
+        assert q.shape[0] == B
         # context views [:, :h] of a [B,H,.] buffer are passed with their row stride, without a copy
         stride = ca.stride(0) // max(1, ca.shape[2]) if T > 0 else 0
         ok = T > 0 and stride >= T and all(t.stride(-1) == 1 and t.stride(1) == t.shape[2] and t.stride(0) == stride * t.shape[2]
-                           for t in (cs, ca, cns, cr.reshape(B, T, 1) if cr.dim() == 2 else cr))
+                           for t in (cs, ca, cns, cr.reshape(Bc, T, 1) if cr.dim() == 2 else cr))
         if not ok:
             cs, ca, cns, cr = cs.contiguous(), ca.contiguous(), cns.contiguous(), cr.contiguous()
             stride = T
@@ -171,7 +174,7 @@ class Transformer(nn.Module):
         nbytes = lib().dpt_gpt2_forward_workspace_bytes(h, B, T, self.precision)
         ws = self._scratch(nbytes)
         check(lib().dpt_gpt2_forward(h, q.data_ptr(), cs.data_ptr() if T else None, ca.data_ptr() if T else None,
-                                     cns.data_ptr() if T else None, cr.data_ptr() if T else None, B, T, stride,
+                                     cns.data_ptr() if T else None, cr.data_ptr() if T else None, B, T, stride, ctx_share,
                                      1 if self.test else 0, self.precision, ptr(out), ptr(ws), ws.numel(), stream_ptr()),
               "dpt_gpt2_forward")
         return out

@@ -120,6 +120,18 @@ int dpt_darkroom_step(const int32_t* states, const float* actions, const int32_t
 int dpt_darkroom_opt_action(const int32_t* states, const int32_t* goals, const int32_t* perm_index, int N,
                             float* actions, void* stream);
 
+/* Policy rollout of one darkroom episode from a per-env logits table (SURVEY.md §8(f) row 1:
+ * DarkroomEnvVec.deploy_eval + DarkroomTransformerController.act, envs/darkroom_env.py:151-175,
+ * ctrls/ctrl_darkroom.py:35-66).  Within an episode the context is fixed, so the controller's logits
+ * depend only on the query state: logits [N, dim*dim, 5] holds them for every state (index x*dim+y).
+ * Each env starts at (0,0) and runs `horizon` steps: softmax (float64) + categorical draw (sample != 0;
+ * uniforms from Philox or inject_u f64 [horizon,N]) or argmax, then the grid transition.  Outputs are the
+ * episode's fp32 context rows [N,horizon,.] and returns [N] (sum of rewards, nullable). */
+int dpt_darkroom_policy_rollout(const float* logits, const int32_t* goals, const int32_t* perm_index, int dim,
+                                int horizon, int sample, uint64_t seed, uint64_t env_id0, int64_t episode, int N,
+                                float* states, float* actions, float* next_states, float* rewards, float* returns,
+                                const double* inject_u, double* dump_u, void* stream);
+
 /* ---------------------------------------------------------------- E5: GPUBanditEnv.step ----
  * envs/gpu_bandit_env.py:53-63 (transit) in one launch: a = argmax(actions), r = means[a] +
  * var * z (type 0, 'uniform') or Bernoulli(means[a]) (type 1).  `step` is the env's step
@@ -203,12 +215,16 @@ int dpt_gpt2_destroy(dpt_gpt2_t* m);
  * context row stride `T_stride` steps (so views context[:, :h] of a [B,H,.] buffer can be passed
  * without a copy, as evals/eval_bandit.py:71-76 does).  test != 0 -> out [B,du] (last position);
  * test == 0 -> out [B,T,du] (positions 1..T).  precision: 0 = fp32 everywhere (1e-5 logit bar);
- * 1 = bf16 K/V cache with fp32 arithmetic (2e-2 bar, half the K/V bytes).
+ * 1 = bf16 (2e-2 bar): sequences of <= 128 tokens run the dense tcgen05 kernel (bf16 operands, fp32
+ * accumulation in tensor memory), longer ones the token-sequential kernel with a bf16 K/V cache.
+ * ctx_share >= 1: consecutive groups of ctx_share sequences share ONE context row (sequence b reads
+ * context row b / ctx_share; query_states and out stay per sequence) -- used to evaluate every
+ * possible query state of an env against its context in one launch (darkroom policy table).
  * workspace: device scratch of dpt_gpt2_forward_workspace_bytes(m, B, T, precision) bytes (per-sequence K/V). */
 uint64_t dpt_gpt2_forward_workspace_bytes(const dpt_gpt2_t* m, int B, int T, int precision);
 int dpt_gpt2_forward(dpt_gpt2_t* m, const float* query_states, const float* ctx_states, const float* ctx_actions,
-                     const float* ctx_next_states, const float* ctx_rewards, int B, int T, int T_stride, int test,
-                     int precision, float* out, void* workspace, uint64_t workspace_bytes, void* stream);
+                     const float* ctx_next_states, const float* ctx_rewards, int B, int T, int T_stride, int ctx_share,
+                     int test, int precision, float* out, void* workspace, uint64_t workspace_bytes, void* stream);
 
 /* Fused bandit online loop with the transformer controller: evals/eval_bandit.py:56-103 +
  * ctrls/ctrl_bandit.py:383-444 (BanditTransformerController, sample != 0 -> softmax + categorical

@@ -34,6 +34,16 @@ elif t in ("gpt2", "gpt2_bf16"):
     means, _, _ = kernels.bandit_sample_means(4000, 5, 0, 0)
     for i in range(reps):
         m.online_loop(means, H, 0.3, True, i, 0)
+elif t in ("dense_bf16", "dense_fp32"):
+    from dpt_b200.models.net import Transformer
+    torch.manual_seed(0)
+    m = Transformer({"horizon": 100, "state_dim": 2, "action_dim": 5, "n_layer": 4, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True})
+    m.precision = 1 if t == "dense_bf16" else 0
+    B, T = 4096, 100
+    x = {"query_states": torch.rand(B, 2, device="cuda"), "context_states": torch.rand(B, T, 2, device="cuda"), "context_actions": torch.rand(B, T, 5, device="cuda"),
+         "context_next_states": torch.rand(B, T, 2, device="cuda"), "context_rewards": torch.rand(B, T, 1, device="cuda")}
+    for i in range(reps):
+        m(x)
 elif t == "bandit":
     means, _, _ = kernels.bandit_sample_means(125000, 5, 0, 0)
     out = kernels.bandit_rollin(means, 500, 0.3, 0, 0)

@@ -237,9 +237,24 @@ def test_darkroom_online_eval_matches_reference(dpt, name):
         envs = [DarkroomEnv(dim, goal, horizon) for goal in g["goals"]]
     N = len(envs)
     np.random.seed(int(g["seed"]))
-    ret = eval_darkroom.deploy_online_vec(DarkroomEnvVec(envs), DarkroomTransformerController(m, batch_size=N, sample=True),
-                                          Heps, H, horizon)
+    slow = DarkroomTransformerController(m, batch_size=N, sample=True)
+    slow.fused = False                                 # the reference's step-by-step loop, same np.random stream
+    ret = eval_darkroom.deploy_online_vec(DarkroomEnvVec(envs), slow, Heps, H, horizon)
     assert ret.shape == (N, Heps) and np.array_equal(ret, g["ref_returns"])
+    # fused device path (one batched dense forward over all dim*dim query states + one rollout kernel per episode)
+    # fed the uniforms the reference consumed: same returns
+    fo = eval_darkroom.deploy_online_vec_device(DarkroomEnvVec(envs), m, Heps, H, horizon, sample=True, seed=1, inject_u=g["ctrl_u"])
+    assert np.array_equal(_np(fo["returns"]).astype(np.float64), g["ref_returns"])
+    # Philox mode: dump the uniforms, replay them through the oracle loop (float64 oracle forward)
+    fo = eval_darkroom.deploy_online_vec_device(DarkroomEnvVec(envs), m, Heps, H, horizon, sample=True, seed=7, dump=True)
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
+    pidx = g["perm_indices"] if len(g["perm_indices"]) else None
+    want, _ = O.deploy_online_vec_darkroom(g["goals"], dim, Heps, H, horizon,
+                                           lambda q, cs, ca, cns, cr: O.transformer_forward(sd, q, cs, ca, cns, cr, int(g["n_layer"]), test=True),
+                                           O.ReplayNoise({"ctrl_u": _np(fo["u"]).reshape(-1)}), pidx)
+    assert np.array_equal(_np(fo["returns"]).astype(np.float64), want)
+    fused = eval_darkroom.deploy_online_vec(DarkroomEnvVec(envs), DarkroomTransformerController(m, batch_size=N, sample=False), Heps, H, horizon)
+    assert fused.shape == (N, Heps)
     # the optimal policy reaches the goal and stays (ctrls/ctrl_darkroom.py:10-20)
     env = envs[0]
     obs, acts, nobs, rews = env.deploy(DarkroomOptPolicy(env))
