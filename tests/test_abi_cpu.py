@@ -56,3 +56,20 @@ def test_product_never_imports_oracle():
         for fn in fns:
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 assert not pat.search(open(os.path.join(dp, fn)).read()), fn
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver runs on the box's host cores) prints the contract's JSON line."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, DPT_REF_ENVS_PER_CORE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([x for x in out.stdout.splitlines() if x.startswith("{")][-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["cores"] >= 1
