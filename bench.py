@@ -220,16 +220,11 @@ def main():
     stats = torch.zeros((n_slots, 3), dtype=torch.float64, device=dev)
     gathered = torch.zeros((n_slots, 3 * world), dtype=torch.float64, device=dev)
     pending = []
-    gather_marks = [0]
-
-    GATHER_EVERY = 8   # statistics of 8 consecutive passes travel in one NCCL call (same bytes, fewer rendezvous)
 
     def step(i):
         kernels.bandit_rollin(means, H, VAR, seed + i, env_id0, out=out, stats=stats[i])
-        if world > 1 and ((i + 1) % GATHER_EVERY == 0 or i + 1 == n_slots or i + 1 == args.warmup):
-            lo = max(j for j in gather_marks if j <= i)
-            gather_marks.append(i + 1)
-            pending.append(dist.all_gather_into_tensor(gathered[lo:i + 1].view(-1), stats[lo:i + 1].view(-1), async_op=True))
+        if world > 1:   # every pass's statistics are gathered; the call is asynchronous (overlaps the next pass)
+            pending.append(dist.all_gather_into_tensor(gathered[i], stats[i], async_op=True))
 
     def barrier():
         if world > 1:

@@ -1,7 +1,5 @@
 mkdir -p gpurun_out
-python scripts/sanitize_smoke.py > gpurun_out/sanitize_plain.log 2>&1 && \
-timeout -s KILL 900 compute-sanitizer --tool memcheck --error-exitcode 3 python scripts/sanitize_smoke.py > gpurun_out/sanitize_memcheck.log 2>&1; echo "memcheck rc=$?"
-tail -6 gpurun_out/sanitize_memcheck.log
+python scripts/sanitize_smoke.py > gpurun_out/sanitize_plain.log 2>&1; echo "smoke rc=$?"
 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus 2 --steps 200 --warmup 10 > gpurun_out/bench_n2.log 2> gpurun_out/bench_n2.err; echo "bench2 rc=$?"
 python - <<'PY'
 import json
