@@ -13,12 +13,12 @@ from .envs import base_env, bandit_env, gpu_bandit_env, darkroom_env   # noqa: F
 from . import ctrls, evals                # noqa: F401
 from .ctrls import ctrl_bandit, ctrl_darkroom   # noqa: F401
 from .evals import eval_bandit, eval_linear_bandit, eval_darkroom   # noqa: F401
-from . import models                      # noqa: F401
+from . import models, dataset             # noqa: F401
 from .models import net                   # noqa: F401
 
 __all__ = ["seed", "kernels", "envs", "collect_data", "install_dropin"]
 
-_DROPIN = ("envs", "ctrls", "evals", "models", "collect_data")
+_DROPIN = ("envs", "ctrls", "evals", "models", "collect_data", "dataset")
 
 
 def install_dropin():

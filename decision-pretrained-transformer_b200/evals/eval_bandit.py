@@ -12,8 +12,8 @@ import numpy as np
 import torch
 
 from .. import kernels, rng
-from ..ctrls.ctrl_bandit import (BanditTransformerController, EmpMeanPolicy, OptPolicy, ThompsonSamplingPolicy,  # noqa: F401
-                                 UCBPolicy)
+from ..ctrls.ctrl_bandit import (BanditTransformerController, EmpMeanPolicy, GreedyOptPolicy, OptPolicy,  # noqa: F401
+                                 PessMeanPolicy, ThompsonSamplingPolicy, UCBPolicy)
 from ..envs.bandit_env import BanditEnv, BanditEnvVec
 
 
@@ -107,3 +107,54 @@ def online(eval_trajs, model, n_eval, horizon, var, bandit_type="uniform"):
         assert cm.shape[0] == n_eval
         all_means[name] = cm
     return all_means, regret_stats(all_means)
+
+
+def offline(eval_trajs, model, n_eval, horizon, var, bandit_type="uniform"):
+    """evals/eval_bandit.py:214-301 without the bar plot: every controller sees the first ``horizon``
+    context rows of each eval trajectory and plays ONE noise-free pull (deploy_eval); returns the dict
+    of per-env rewards {'opt','lnr','emp','thmp','lcb'} (``lnr`` only when a model is given).  Per-arm
+    statistics come from dpt_arm_stats, the transformer decision from dpt_gpt2_forward."""
+    num_envs = len(eval_trajs)
+    tmp_env = BanditEnv(eval_trajs[0]["means"], horizon, var=var)
+    context_states = np.zeros((num_envs, horizon, tmp_env.dx))
+    context_actions = np.zeros((num_envs, horizon, tmp_env.du))
+    context_next_states = np.zeros((num_envs, horizon, tmp_env.dx))
+    context_rewards = np.zeros((num_envs, horizon, 1))
+    envs = []
+    for i_eval in range(n_eval):
+        traj = eval_trajs[i_eval]
+        envs.append(BanditEnv(traj["means"], horizon, var=var))
+        context_states[i_eval] = traj["context_states"][:horizon]
+        context_actions[i_eval] = traj["context_actions"][:horizon]
+        context_next_states[i_eval] = traj["context_next_states"][:horizon]
+        context_rewards[i_eval] = np.asarray(traj["context_rewards"])[:horizon, None]
+    vec_env = BanditEnvVec(envs)
+    batch = {"context_states": context_states, "context_actions": context_actions,
+             "context_next_states": context_next_states, "context_rewards": context_rewards}
+    policies = {"opt": OptPolicy(envs, batch_size=num_envs),
+                "emp": EmpMeanPolicy(envs[0], online=False, batch_size=num_envs)}
+    if model is not None:
+        policies["lnr"] = BanditTransformerController(model, sample=False, batch_size=num_envs)
+    policies["lcb"] = PessMeanPolicy(envs[0], const=.8, batch_size=len(envs))
+    policies["thmp"] = ThompsonSamplingPolicy(envs[0], std=var, sample=False, prior_mean=0.5, prior_var=1 / 12.0,
+                                              warm_start=False, batch_size=num_envs)
+    for name in ("opt", "emp", "thmp", "lcb", "lnr"):            # set_batch order of the reference (:270-274)
+        if name in policies:
+            policies[name].set_batch_numpy_vec(batch)
+    baselines = {}
+    for name in ("opt", "emp", "lnr", "lcb", "thmp"):            # deploy order of the reference (:276-280)
+        if name in policies:
+            baselines[name] = np.array(vec_env.deploy_eval(policies[name])[3])
+    return baselines
+
+
+def offline_graph(eval_trajs, model, n_eval, horizon, var, bandit_type="uniform"):
+    """evals/eval_bandit.py:304-335 without plotting: suboptimality against dataset size.  Returns
+    (horizons [50], {name: regret-of-the-mean per horizon})."""
+    horizons = np.linspace(1, horizon, 50, dtype=int)
+    all_means = []
+    for h in horizons:
+        b = offline(eval_trajs, model, n_eval=n_eval, horizon=int(h), var=var, bandit_type=bandit_type)
+        all_means.append({k: np.mean(v, axis=0) for k, v in b.items()})
+    regrets = {k: np.array([m["opt"] - m[k] for m in all_means]) for k in all_means[0] if k != "opt"}
+    return horizons, regrets

@@ -324,6 +324,36 @@ def darkroom_online(ref, name, seed, dim, horizon, H, Heps, n_layer, goals=None,
     print("ok", name)
 
 
+def offline_eval(ref, name, seed, N, d, H, var, n_layer):
+    """evals/eval_bandit.py:214-301 (offline) on trajectories from the reference's own collection."""
+    import torch
+    torch.manual_seed(seed)
+    cfg = {"horizon": H, "state_dim": 1, "action_dim": d, "n_layer": n_layer, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True}
+    model = ref.net.Transformer(cfg).to(ref.net.device).eval()
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if "wte" not in k:
+                p.add_(0.15 * torch.randn_like(p))
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items() if "wte" not in k and ".attn.bias" not in k
+          and "masked_bias" not in k}
+    np.random.seed(seed)
+    trajs = ref.collect_data.generate_bandit_histories(N, d, H, var, n_hists=1, n_samples=1, cov=0.0, type="uniform")
+    for t in trajs:   # fp32-exact tasks so both sides see identical means
+        t["means"] = t["means"].astype(np.float32).astype(np.float64)
+    out = {}
+    for h in (H, H // 2, 1):
+        np.random.seed(seed + h)
+        b = ref.eval_bandit.offline(trajs, model, N, h, var, "uniform")
+        for k, v in b.items():
+            out["h%d_%s" % (h, k)] = np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), d=d, H=H, var=var, seed=seed, n_layer=n_layer,
+                        means=np.stack([t["means"] for t in trajs]),
+                        context_actions=np.stack([t["context_actions"] for t in trajs]).argmax(-1).astype(np.int8),
+                        context_rewards=np.stack([t["context_rewards"] for t in trajs]),
+                        **out, **{"sd/" + k: v for k, v in sd.items()})
+    print("ok", name)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
@@ -344,10 +374,13 @@ def main():
     darkroom_online(ref, "darkroom_online", seed=2, dim=6, horizon=8, H=16, Heps=5, n_layer=2,
                     goals=[(0, 0), (5, 5), (2, 3), (5, 0), (1, 4), (3, 3), (0, 5)])
     darkroom_online(ref, "darkroom_online_perm", seed=3, dim=5, horizon=6, H=12, Heps=4, n_layer=3, perm_indices=[0, 7, 57, 119])
+    offline_eval(ref, "offline_bandit", seed=6, N=40, d=5, H=20, var=0.3, n_layer=2)
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "darkroom_online":
+    if len(sys.argv) > 1 and sys.argv[1] == "offline":
+        offline_eval(ref_loader.load(), "offline_bandit", seed=6, N=40, d=5, H=20, var=0.3, n_layer=2)
+    elif len(sys.argv) > 1 and sys.argv[1] == "darkroom_online":
         ref_ = ref_loader.load()
         darkroom_online(ref_, "darkroom_online", seed=2, dim=6, horizon=8, H=16, Heps=5, n_layer=2,
                         goals=[(0, 0), (5, 5), (2, 3), (5, 0), (1, 4), (3, 3), (0, 5)])

@@ -49,7 +49,16 @@ def _shims():
     skt.resize = None
     sk.transform = skt
     mods["skimage"], mods["skimage.transform"] = sk, skt
-    mpl, plt = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
+    class _Null:   # matplotlib is plotting only (evals/*.py): every attribute / call is a no-op
+        def __getattr__(self, name):
+            return self
+
+        def __call__(self, *a, **k):
+            return self
+
+        def __iter__(self):
+            return iter((self, self))
+    mpl, plt = types.ModuleType("matplotlib"), _Null()
     mpl.pyplot = plt
     mods["matplotlib"], mods["matplotlib.pyplot"] = mpl, plt
     return mods
@@ -85,6 +94,7 @@ def load():
         ns.ctrl_darkroom = importlib.import_module("ctrls.ctrl_darkroom")
         ns.eval_darkroom = importlib.import_module("evals.eval_darkroom")
         ns.net = importlib.import_module("models.net")
+        ns.dataset = importlib.import_module("dataset")
     finally:
         sys.path.remove(REF_ROOT)
         for k in list(sys.modules):

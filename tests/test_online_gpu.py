@@ -228,3 +228,28 @@ def test_deploy_online_vec_dropin(dpt):
     lin.set_batch_numpy_vec({"context_actions": ca[:, :7], "context_rewards": cr[:, :7, None]})
     want = O.LinUCBCtrl(arms, 1.0).act(ca[:, :7], cr[:, :7, None], None, 7)
     assert np.array_equal(lin.act_numpy_vec(None), want)
+
+
+def test_offline_eval_matches_reference(dpt):
+    """evals/eval_bandit.py offline() -- every controller sees a fixed context and plays one
+    noise-free pull; rewards per env equal the reference's (Thompson sample=False consumes np.random identically)."""
+    from dpt_b200.evals import eval_bandit
+    from dpt_b200.models.net import Transformer
+    g = golden("offline_bandit")
+    d, H, var = int(g["d"]), int(g["H"]), float(g["var"])
+    m = Transformer({"horizon": H, "state_dim": 1, "action_dim": d, "n_layer": int(g["n_layer"]), "n_embd": 32, "n_head": 1,
+                     "dropout": 0.0, "test": True})
+    m.load_state_dict({k[3:]: torch.tensor(g[k]) for k in g.files if k.startswith("sd/")}, strict=False)
+    N = g["means"].shape[0]
+    trajs = [{"means": g["means"][i], "context_states": np.ones((H, 1)), "context_actions": np.eye(d)[g["context_actions"][i]],
+              "context_next_states": np.ones((H, 1)), "context_rewards": g["context_rewards"][i]} for i in range(N)]
+    for h in (H, H // 2, 1):
+        np.random.seed(int(g["seed"]) + h)
+        b = eval_bandit.offline(trajs, m, N, h, var, "uniform")
+        assert set(b) == {"opt", "lnr", "emp", "thmp", "lcb"}
+        for k, v in b.items():
+            assert v.shape == (N,)
+            assert np.allclose(v, g["h%d_%s" % (h, k)], rtol=0, atol=1e-6), (h, k)
+    hs, reg = eval_bandit.offline_graph(trajs, None, N, 6, var)
+    assert len(hs) == 50 and set(reg) == {"emp", "thmp", "lcb"} and all(len(v) == 50 for v in reg.values())
+    assert all(np.all(v > -1e-9) for v in reg.values())

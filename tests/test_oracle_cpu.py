@@ -161,3 +161,52 @@ def test_darkroom_online_golden(name):
     ret, _ = O.deploy_online_vec_darkroom(g["goals"], int(g["dim"]), int(g["Heps"]), int(g["H"]), int(g["horizon"]), logits_fn,
                                           O.ReplayNoise({"ctrl_u": g["ctrl_u"].reshape(-1)}), perms)
     assert np.array_equal(ret, g["ref_returns"])
+
+
+def test_dataset_dropin(tmp_path):
+    """dataset.py:11-91 hand-off format: same items as the reference's Dataset (compared live when the
+    reference is mounted, i.e. in the dev container), and the device-batch constructor agrees with it."""
+    import pickle
+    import torch
+    import dpt_b200
+    from dpt_b200.dataset import Dataset
+    from oracle import ref_loader
+    rs = np.random.RandomState(0)
+    H, d = 12, 5
+    trajs = [{"query_state": np.array([1]), "optimal_action": np.eye(d)[rs.randint(d)], "context_states": np.ones((H, 1), dtype=np.int64),
+              "context_actions": np.eye(d)[rs.randint(0, d, H)], "context_next_states": np.ones((H, 1), dtype=np.int64),
+              "context_rewards": rs.normal(size=H), "means": rs.rand(d)} for _ in range(7)]
+    path = tmp_path / "trajs.pkl"
+    pickle.dump(trajs, open(path, "wb"))
+    cfg = {"shuffle": True, "horizon": H, "store_gpu": False, "state_dim": 1, "action_dim": d}
+    ds = Dataset(str(path), cfg)
+    assert len(ds) == 7
+    torch.manual_seed(3)
+    item = ds[2]
+    assert set(item) == {"context_states", "context_actions", "context_next_states", "context_rewards", "query_states", "optimal_actions", "zeros"}
+    assert item["context_rewards"].shape == (H, 1) and item["context_actions"].shape == (H, d) and item["zeros"].shape == (1 + d + 1,)
+    assert all(v.dtype == torch.float32 for v in item.values())
+    torch.manual_seed(3)
+    perm = torch.randperm(H)
+    assert torch.equal(item["context_rewards"][:, 0], torch.tensor(trajs[2]["context_rewards"]).float()[perm])
+    assert torch.equal(item["context_actions"], torch.tensor(trajs[2]["context_actions"]).float()[perm])
+    # from_batch (what collect_bandit returns, here on the CPU) == from_trajs
+    batch = {"context_states": torch.ones(7, H, 1), "context_next_states": torch.ones(7, H, 1),
+             "context_actions": torch.tensor(np.stack([t["context_actions"] for t in trajs])).float(),
+             "context_rewards": torch.tensor(np.stack([t["context_rewards"] for t in trajs])).float()[:, :, None],
+             "optimal_actions": torch.tensor(np.stack([t["optimal_action"] for t in trajs])).float()}
+    cfg2 = dict(cfg, shuffle=False)
+    a, b = Dataset.from_batch(batch, cfg2), Dataset.from_trajs(trajs, cfg2)
+    for i in range(7):
+        for k in a[i]:
+            assert torch.equal(a[i][k], b[i][k]), k
+    if ref_loader.available():
+        ref = ref_loader.load()
+        rds = ref.dataset.Dataset(str(path), cfg)
+        for i in range(7):
+            torch.manual_seed(i)
+            x = rds[i]
+            torch.manual_seed(i)
+            y = ds[i]
+            for k in x:
+                assert torch.equal(x[k].cpu(), y[k]), k
