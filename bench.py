@@ -185,7 +185,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
-    assert args.warmup >= 3, "timing rules: W >= 3 warm-up steps"
+    args.warmup = max(args.warmup, 3)   # timing rule: at least 3 warm-up steps (the JSON line reports the value used)
+    args.steps = max(args.steps, 1)
 
     # CPU baseline first (rank 0, N=1 only), before the GPU is busy: bounded sample on all host cores
     cpu_baseline = None

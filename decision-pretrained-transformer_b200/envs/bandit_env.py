@@ -112,6 +112,10 @@ class BanditEnvVec(BaseEnv):
                                      dtype=torch.float32).to(self.device)
         self._key = rng.next_key() if key is None else key
         self._draws = 0        # monotone step counter: part of the Philox counter
+        # The reference's transit draws np.random.normal(0, var) per env even when var == 0 (envs/bandit_env.py:59).
+        # Set True to burn the same N gaussians per step, so that controllers which draw from np.random
+        # (Thompson sample=False, LinUCB first arm ...) see the reference's global-stream positions.
+        self.np_random_compat = False
         self._done = [True] * self._num_envs
 
     @property
@@ -142,6 +146,8 @@ class BanditEnvVec(BaseEnv):
             if env.current_step >= env.H:
                 raise ValueError("Episode has already ended")
         r = self._transit_device(torch.as_tensor(np.asarray(actions))).cpu().numpy().astype(np.float64)
+        if self.np_random_compat:
+            np.random.standard_normal(self._num_envs)
         next_obs, dones = [], []
         for env in self._envs:
             env.current_step += 1

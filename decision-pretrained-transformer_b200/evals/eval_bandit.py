@@ -109,7 +109,7 @@ def online(eval_trajs, model, n_eval, horizon, var, bandit_type="uniform"):
     return all_means, regret_stats(all_means)
 
 
-def offline(eval_trajs, model, n_eval, horizon, var, bandit_type="uniform"):
+def offline(eval_trajs, model, n_eval, horizon, var, bandit_type="uniform", np_random_compat=False):
     """evals/eval_bandit.py:214-301 without the bar plot: every controller sees the first ``horizon``
     context rows of each eval trajectory and plays ONE noise-free pull (deploy_eval); returns the dict
     of per-env rewards {'opt','lnr','emp','thmp','lcb'} (``lnr`` only when a model is given).  Per-arm
@@ -129,6 +129,7 @@ def offline(eval_trajs, model, n_eval, horizon, var, bandit_type="uniform"):
         context_next_states[i_eval] = traj["context_next_states"][:horizon]
         context_rewards[i_eval] = np.asarray(traj["context_rewards"])[:horizon, None]
     vec_env = BanditEnvVec(envs)
+    vec_env.np_random_compat = np_random_compat     # keep np.random aligned with the reference's env draws
     batch = {"context_states": context_states, "context_actions": context_actions,
              "context_next_states": context_next_states, "context_rewards": context_rewards}
     policies = {"opt": OptPolicy(envs, batch_size=num_envs),

@@ -245,7 +245,7 @@ def test_offline_eval_matches_reference(dpt):
               "context_next_states": np.ones((H, 1)), "context_rewards": g["context_rewards"][i]} for i in range(N)]
     for h in (H, H // 2, 1):
         np.random.seed(int(g["seed"]) + h)
-        b = eval_bandit.offline(trajs, m, N, h, var, "uniform")
+        b = eval_bandit.offline(trajs, m, N, h, var, "uniform", np_random_compat=True)
         assert set(b) == {"opt", "lnr", "emp", "thmp", "lcb"}
         for k, v in b.items():
             assert v.shape == (N,)
@@ -253,3 +253,23 @@ def test_offline_eval_matches_reference(dpt):
     hs, reg = eval_bandit.offline_graph(trajs, None, N, 6, var)
     assert len(hs) == 50 and set(reg) == {"emp", "thmp", "lcb"} and all(len(v) == 50 for v in reg.values())
     assert all(np.all(v > -1e-9) for v in reg.values())
+
+
+@pytest.mark.parametrize("N,d,H", [(1, 2, 1), (31, 32, 7), (33, 1, 5), (65, 3, 64), (2, 5, 129)])
+def test_online_loop_edge_shapes(dpt, N, d, H):
+    """Ragged sizes: one env, one step, one arm, 32 arms, N and H around the 32-wide tiles."""
+    rs = np.random.RandomState(N * 100 + d)
+    means = torch.tensor(rs.rand(N, d), dtype=torch.float32)
+    m64 = means.double().numpy()
+    for kind, par, ctrl in (("emp", dict(p0=1.0), O.EmpMeanCtrl(d, online=True)), ("ucb", dict(p0=1.0), O.UCBCtrl(d, 1.0)),
+                            ("thompson", dict(p0=0.3, p1=0.5, p2=1 / 12.0), O.ThompsonCtrl(d, std=0.3, sample=True, prior_mean=.5, prior_var=1 / 12.0))):
+        out = dpt.kernels.online_loop(kind, means, H, 0.3, 5, 0, dump=True, **par)
+        arrays = {"reward_z": _np(out["noise"]["reward_z"]).astype(np.float64)}
+        if kind == "thompson":
+            arrays["thompson_z"] = _np(out["noise"]["ctrl_z"]).astype(np.float64)
+        cum, meta = O.deploy_online_vec(m64, 0.3, H, ctrl, O.ReplayNoise(arrays))
+        assert np.array_equal(_np(out["context_actions"]).astype(np.float64), meta["context_actions"]), kind
+        _close(_np(out["context_rewards"]), meta["context_rewards"])
+        reg = m64.max(1)[None] - cum
+        _close(_np(out["regret_sums"])[:, 2], np.cumsum(reg, axis=0).sum(1), 1e-5)
+    assert dpt.kernels.online_loop("opt", means[:0], H, 0.3, 5, 0)["cum_means"].shape == (H, 0)
