@@ -193,12 +193,13 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_bench
         pool = cpu_bench.BanditRollinPool()
-        epc = int(os.environ.get("DPT_CPU_ENVS_PER_CORE", 300))
+        epc = int(os.environ.get("DPT_CPU_ENVS_PER_CORE", 3000))
         steps, wall = pool.run(epc, DIM, H, VAR)
         pool.close()
         cpu_baseline = {"value": steps / wall, "unit": UNIT, "cores": pool.cores, "kind": "port",
                         "sample": "%d cores x %d envs x H=%d, oracle port of collect_data.generate_bandit_histories "
-                                  "(%.1f s wall)" % (pool.cores, epc, H, wall)}
+                                  "(%.2f s wall, %.2f s mean per worker)" % (pool.cores, epc, H, wall,
+                                                                             sum(pool.last_worker_seconds) / pool.cores)}
 
     import torch
     import torch.distributed as dist

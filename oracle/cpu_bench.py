@@ -40,6 +40,7 @@ class BanditRollinPool:
         t0 = time.perf_counter()
         res = self.pool.map(_bandit_worker, [(seed0 + i, envs_per_core, dim, H, var) for i in range(self.cores)])
         wall = time.perf_counter() - t0
+        self.last_worker_seconds = [r[1] for r in res]
         return sum(r[0] for r in res), wall
 
     def close(self):
