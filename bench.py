@@ -104,7 +104,7 @@ def run_reference(args, rank):
         return
     from oracle import cpu_bench
     pool = cpu_bench.BanditRollinPool()
-    envs_per_core = int(os.environ.get("DPT_REF_ENVS_PER_CORE", 24))
+    envs_per_core = int(os.environ.get("DPT_REF_ENVS_PER_CORE", 100))
     for _ in range(args.warmup):
         pool.run(envs_per_core, DIM, H, VAR)
     tot_steps, t0 = 0, time.perf_counter()

@@ -47,8 +47,19 @@ __device__ __forceinline__ void ln_row(const float* x, const float* w, const flo
   for (int c = 0; c < G_E; ++c) y[c] = (x[c] - mean) * rs * __ldg(w + c) + __ldg(b + c);
 }
 
+// bf16-operand path (2e-2 bar): hardware approximations are far below the operand rounding (2^-9)
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float exp_fast(float x) {   // e^x = 2^(x log2 e)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
 __device__ __forceinline__ float gelu_new_d(float x) {
-  return 0.5f * x * (1.0f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
+  return 0.5f * x * (1.0f + tanh_fast(0.7978845608028654f * (x + 0.044715f * x * x * x)));
 }
 
 // write a 32-wide fp32 row as bf16 into chunks 0..3 of row m of a K64 tile
@@ -183,7 +194,7 @@ __global__ void __launch_bounds__(DN_THREADS) gpt2_dense_kernel(const DenseParam
       umma::tmem_ld32(umma::tmem_addr(tb, warp, 128 + c0), y);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float pr = (c0 + i <= tid) ? expf(y[i] - mx) : 0.f;
+        const float pr = (c0 + i <= tid) ? exp_fast(y[i] - mx) : 0.f;
         // the normaliser uses the bf16-rounded probabilities that the tensor core will see
         y[i] = __bfloat162float(__float2bfloat16_rn(pr));
         sum += y[i];
