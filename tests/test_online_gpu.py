@@ -273,3 +273,28 @@ def test_online_loop_edge_shapes(dpt, N, d, H):
         reg = m64.max(1)[None] - cum
         _close(_np(out["regret_sums"])[:, 2], np.cumsum(reg, axis=0).sum(1), 1e-5)
     assert dpt.kernels.online_loop("opt", means[:0], H, 0.3, 5, 0)["cum_means"].shape == (H, 0)
+
+
+@pytest.mark.parametrize("kind", ["emp", "ucb", "thompson"])
+def test_regret_curves_statistical_parity(dpt, kind):
+    """SURVEY §4 tier 4: regret curves from INDEPENDENT noise (Philox on the device vs numpy in the oracle)
+    agree within the statistical tolerance: |mean_gpu - mean_oracle| <= 5 combined standard errors per step."""
+    from dpt_b200.dist import regret_stats_from_sums
+    d, H, var = 5, 40, 0.3
+    N_gpu, N_or = 40000, 1500
+    means, _, _ = dpt.kernels.bandit_sample_means(N_gpu, d, 21, 0)
+    par = {"emp": dict(p0=1.0), "ucb": dict(p0=1.0), "thompson": dict(p0=var, p1=0.5, p2=1 / 12.0)}[kind]
+    out = dpt.kernels.online_loop(kind, means, H, var, 21, 0, materialise=False, **par)
+    gpu = regret_stats_from_sums(_np(out["regret_sums"]), N_gpu)
+    rs = np.random.RandomState(5)
+    m_or = rs.uniform(0, 1, (N_or, d))
+    np.random.seed(17)
+    ctrl = {"emp": O.EmpMeanCtrl(d, online=True), "ucb": O.UCBCtrl(d, 1.0),
+            "thompson": O.ThompsonCtrl(d, std=var, sample=True, prior_mean=.5, prior_var=1 / 12.0)}[kind]
+    cum, _ = O.deploy_online_vec(m_or, var, H, ctrl, O.GlobalNoise(record=False))
+    m, s, cm, cs = O.regret_stats(np.repeat(m_or.max(1)[:, None], H, 1), cum.T)
+    tol = 5 * np.sqrt(gpu["sem"] ** 2 + s ** 2) + 1e-3
+    assert np.all(np.abs(gpu["mean"] - m) <= tol), np.abs(gpu["mean"] - m).max()
+    tolc = 5 * np.sqrt(gpu["regret_sem"] ** 2 + cs ** 2) + 1e-3
+    assert np.all(np.abs(gpu["regret_mean"] - cm) <= tolc)
+    assert gpu["regret_mean"][-1] > 0.5 and gpu["mean"][-1] < gpu["mean"][d]      # it learns: late regret below early regret
