@@ -301,7 +301,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t[0])
     e2e = {"value": world * N * H * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": N * DIM * 4,
-           "d2h_bytes_per_step": N * H * BYTES_PER_STEP, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+           # actions + rewards cross PCIe; the constant state columns are filled on the host
+           "d2h_bytes_per_step": N * H * 4 * (DIM + 1), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
            "api": "dpt_bandit_rollin_host (pinned host buffers, chunked H2D/kernel/D2H pipeline)"}
 
     for w_ in pending:

@@ -1,5 +1,9 @@
 // Host-buffer entry points (the e2e path): the same kernels driven from HOST arrays, with the
 // host<->device copies pipelined against the kernel in env chunks (double-buffered scratch).
+#include <algorithm>
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 
 namespace dpt {
@@ -51,6 +55,18 @@ extern "C" int dpt_bandit_rollin_host(const float* means_host, float var, uint64
     DPT_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
     DPT_CUDA(cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming));
   }
+  // The bandit state is the constant [1] (envs/bandit_env.py:38), so context_states / context_next_states
+  // are filled on the host by a few threads while the GPU pipeline runs, instead of crossing PCIe (25 % of
+  // the bytes of a collection).
+  const size_t total_rows = (size_t)N * H;
+  const int n_fill = (int)std::min<size_t>(4, std::max<size_t>(1, total_rows >> 20));
+  std::vector<std::thread> fillers;
+  for (int t = 0; t < n_fill; ++t)
+    fillers.emplace_back([=] {
+      const size_t lo = total_rows * t / n_fill, hi = total_rows * (t + 1) / n_fill;
+      std::fill(ctx_states_host + lo, ctx_states_host + hi, 1.0f);
+      std::fill(ctx_next_states_host + lo, ctx_next_states_host + hi, 1.0f);
+    });
   int rc = DPT_OK;
   int k = 0;
   for (int e0 = 0; e0 < N && rc == DPT_OK; e0 += C, ++k) {
@@ -65,12 +81,11 @@ extern "C" int dpt_bandit_rollin_host(const float* means_host, float var, uint64
     cudaEventRecord(done[b], cs);
     cudaStreamWaitEvent(copy, done[b], 0);
     const size_t row = (size_t)e0 * H, nrow = (size_t)n * H;
-    cudaMemcpyAsync(ctx_states_host + row, buf + L.s, sizeof(float) * nrow, cudaMemcpyDeviceToHost, copy);
     cudaMemcpyAsync(ctx_actions_host + row * d, buf + L.a, sizeof(float) * nrow * d, cudaMemcpyDeviceToHost, copy);
-    cudaMemcpyAsync(ctx_next_states_host + row, buf + L.ns, sizeof(float) * nrow, cudaMemcpyDeviceToHost, copy);
     cudaMemcpyAsync(ctx_rewards_host + row, buf + L.r, sizeof(float) * nrow, cudaMemcpyDeviceToHost, copy);
     cudaEventRecord(freed[b], copy);
   }
+  for (auto& th : fillers) th.join();
   cudaError_t e1 = cudaStreamSynchronize(copy);
   cudaError_t e2 = cudaStreamSynchronize(cs);
   for (int i = 0; i < 2; ++i) cudaEventDestroy(done[i]), cudaEventDestroy(freed[i]);

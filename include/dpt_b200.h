@@ -84,7 +84,8 @@ int dpt_bandit_rollin(const float* means, float var, uint64_t seed, uint64_t env
 /* Host-buffer form of the same call (the e2e path): means_host [N,d] in, the four context
  * arrays out, all HOST pointers (pinned for full speed).  Uses `scratch` (device, at least
  * dpt_bandit_rollin_host_scratch_bytes(...) bytes) for double-buffered chunks so the D2H copies
- * overlap the kernel.  Synchronises `stream` before returning. */
+ * overlap the kernel; the constant state columns (bandit state == [1]) are written by host threads
+ * instead of crossing PCIe.  Synchronises `stream` before returning. */
 uint64_t dpt_bandit_rollin_host_scratch_bytes(int N, int H, int d);
 int dpt_bandit_rollin_host(const float* means_host, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
                            float* ctx_states_host, float* ctx_actions_host, float* ctx_next_states_host,
