@@ -222,11 +222,25 @@ def main():
     stats = torch.zeros((n_slots, 3), dtype=torch.float64, device=dev)
     gathered = torch.zeros((n_slots, 3 * world), dtype=torch.float64, device=dev)
     pending = []
+    peer, gather_how = None, "none"
+    if world > 1:
+        from dpt_b200 import dist as ddist
+        try:      # all-gather fused into the kernel: the last CTA stores the totals into every rank's buffer over NVLink
+            if os.environ.get("DPT_BENCH_GATHER", "p2p") != "p2p":
+                raise RuntimeError("NCCL gather requested")
+            peer = ddist.PeerGather(n_slots)
+            gather_how = "fused in-kernel all-gather of return stats over NVLink peer memory (CUDA IPC), no collective launch"
+        except Exception as e:   # noqa: BLE001
+            peer = None
+            gather_how = "NCCL all-gather of return stats every step (async) [p2p unavailable: %s]" % str(e)[:80]
 
     def step(i):
-        kernels.bandit_rollin(means, H, VAR, seed + i, env_id0, out=out, stats=stats[i])
-        if world > 1:   # every pass's statistics are gathered; the call is asynchronous (overlaps the next pass)
-            pending.append(dist.all_gather_into_tensor(gathered[i], stats[i], async_op=True))
+        if peer is not None:
+            kernels.bandit_rollin(means, H, VAR, seed + i, env_id0, out=out, stats=stats[i], peer=peer, peer_slot=i)
+        else:
+            kernels.bandit_rollin(means, H, VAR, seed + i, env_id0, out=out, stats=stats[i])
+            if world > 1:   # every pass's statistics are gathered; the call is asynchronous (overlaps the next pass)
+                pending.append(dist.all_gather_into_tensor(gathered[i], stats[i], async_op=True))
 
     def barrier():
         if world > 1:
@@ -308,7 +322,11 @@ def main():
     for w_ in pending:
         w_.wait()
     torch.cuda.synchronize()
-    if world > 1:   # every call wrote [world, k, 3] into gathered[lo:hi] (as a flat block): summing all of it is order-free
+    if peer is not None:
+        barrier()
+        totals = torch.tensor(peer.read().sum((0, 1)))
+        peer.close()
+    elif world > 1:
         totals = gathered.view(-1, 3).sum(0)
     else:
         totals = stats.sum(0)
@@ -324,7 +342,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(world), "envs_per_gpu": N, "H": H, "dim": DIM, "var": VAR,
                        "noise": "philox4x32-10", "l2": "outputs larger than L2, no flush",
-                       "parallelism": "env-sharded x%d%s" % (world, ", NCCL all-gather of return stats every step (async, overlapped with the next step)" if world > 1 else "")},
+                       "parallelism": "env-sharded x%d%s" % (world, ", " + gather_how if world > 1 else "")},
             "roofline": roofline, "e2e": e2e, "gpu_launches": args.steps,
             "clocks": sampler.summary() if sampler else None,
             "return_stats": {"mean_reward": float(st[0]) / n_tot, "frac_optimal_arm": float(st[2]) / n_tot},

@@ -14,6 +14,8 @@
 //      d=5) are re-tiled across the warp with shuffles of a 2d-bit one-hot mask so that every
 //      store is a full, 16 B-aligned float4 of a contiguous 64*d*4-byte run.
 // HBM traffic is write-only: 4*(2+d+1) B per env-step (32 B for d=5), inputs are < 0.1 B/step.
+#include <string.h>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -34,6 +36,12 @@ struct RollinParams {
   int N, H, d, envs_per_cta;
   float *ctx_s, *ctx_a, *ctx_ns, *ctx_r;
   double* stats;  // nullable: += (sum r, sum r^2, #pulls of the optimal arm) over all env-steps
+  // fused all-gather over NVLink peer memory (nullable): when the LAST CTA of the launch has seen every
+  // CTA's contribution, it stores this rank's three totals into slot `peer_slot` of every rank's gather
+  // buffer (peer pointers are CUDA-IPC mappings; plain system-scope stores, no collective launch)
+  double* peer_dst[DPT_MAX_PEERS];
+  int n_peers;
+  unsigned int* done_counter;
   dpt_bandit_inject_t in;
   dpt_bandit_dump_t out;
 };
@@ -122,8 +130,10 @@ __device__ __forceinline__ void rollin_setup_env(const RollinParams& p, int env,
 // CTA-level reduction of the return statistics: warp shuffles, then one double atomic per CTA and
 // statistic (the only cross-env operation of the whole path; shards on other GPUs add theirs via
 // the NCCL gather on the host side).
-__device__ __forceinline__ void reduce_stats(double* stats, float sr, float sr2, float nopt) {
+__device__ __forceinline__ void reduce_stats(const RollinParams& p, float sr, float sr2, float nopt) {
+  double* stats = p.stats;
   __shared__ float s_part[3][RB_WARPS];
+  __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -137,6 +147,19 @@ __device__ __forceinline__ void reduce_stats(double* stats, float sr, float sr2,
     double acc = 0.0;
     for (int w = 0; w < RB_WARPS; ++w) acc += (double)s_part[threadIdx.x][w];
     atomicAdd(stats + threadIdx.x, acc);
+    __threadfence();
+  }
+  if (p.n_peers > 0) {   // uniform over the grid
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(p.done_counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x < 3) {
+      __threadfence();
+      const double total = *reinterpret_cast<volatile double*>(stats + threadIdx.x);
+      for (int r = 0; r < p.n_peers; ++r)
+        asm volatile("st.global.release.sys.f64 [%0], %1;" ::"l"(p.peer_dst[r] + threadIdx.x), "d"(total) : "memory");
+      if (threadIdx.x == 0) *p.done_counter = 0u;   // ready for the next launch
+    }
   }
 }
 
@@ -250,7 +273,7 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_fast(const RollinPar
       st_stream_if(q < n_valid4, abase + q, v);
     }
   }
-  if (p.stats) reduce_stats(p.stats, st_r, st_r2, st_opt);
+  if (p.stats) reduce_stats(p, st_r, st_r2, st_opt);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -324,7 +347,7 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_generic(const Rollin
       if (i < nvalid) st_stream(abase + i, (i - s * D) == as ? 1.f : 0.f);
     }
   }
-  if (p.stats) reduce_stats(p.stats, st_r, st_r2, st_opt);
+  if (p.stats) reduce_stats(p, st_r, st_r2, st_opt);
 }
 
 template <int MODE>
@@ -366,10 +389,10 @@ int rollin_envs_per_cta(int N) {
 
 using namespace dpt;
 
-extern "C" int dpt_bandit_rollin(const float* means, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
-                                 float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
-                                 double* return_stats, const dpt_bandit_inject_t* inject,
-                                 const dpt_bandit_dump_t* dump, void* stream) {
+static int bandit_rollin_impl(const float* means, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
+                              float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
+                              double* return_stats, const dpt_bandit_inject_t* inject, const dpt_bandit_dump_t* dump,
+                              double* const* peer_dst, int n_peers, unsigned int* done_counter, void* stream) {
   DPT_CHECK_ARG(N >= 0 && H >= 0, "dpt_bandit_rollin: N=%d H=%d must be >= 0", N, H);
   DPT_CHECK_ARG(d >= 1 && d <= RB_MAX_D, "dpt_bandit_rollin: d=%d outside [1,%d]", d, RB_MAX_D);
   if (N == 0 || H == 0) return DPT_OK;
@@ -383,6 +406,13 @@ extern "C" int dpt_bandit_rollin(const float* means, float var, uint64_t seed, u
   p.N = N, p.H = H, p.d = d;
   p.ctx_s = ctx_states, p.ctx_a = ctx_actions, p.ctx_ns = ctx_next_states, p.ctx_r = ctx_rewards;
   p.stats = return_stats;
+  if (n_peers > 0) {
+    DPT_CHECK_ARG(n_peers <= DPT_MAX_PEERS && peer_dst && done_counter && return_stats,
+                  "dpt_bandit_rollin_p2p: needs return_stats, a done counter and 1..%d peer pointers", DPT_MAX_PEERS);
+    for (int r = 0; r < n_peers; ++r) p.peer_dst[r] = peer_dst[r];
+    p.n_peers = n_peers;
+    p.done_counter = done_counter;
+  }
   p.envs_per_cta = rollin_envs_per_cta(N);
   int mode = MODE_PHILOX;
   if (inject) {
@@ -407,5 +437,57 @@ extern "C" int dpt_bandit_rollin(const float* means, float var, uint64_t seed, u
   else
     launch_mode<MODE_INJECT>(p, fast, grid, st);
   DPT_LAUNCH_CHECK();
+  return DPT_OK;
+}
+
+extern "C" int dpt_bandit_rollin(const float* means, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
+                                 float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
+                                 double* return_stats, const dpt_bandit_inject_t* inject,
+                                 const dpt_bandit_dump_t* dump, void* stream) {
+  return bandit_rollin_impl(means, var, seed, env_id0, N, H, d, ctx_states, ctx_actions, ctx_next_states, ctx_rewards,
+                            return_stats, inject, dump, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int dpt_bandit_rollin_p2p(const float* means, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
+                                     float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
+                                     double* return_stats, double* const* peer_dst, int n_peers,
+                                     unsigned int* done_counter, void* stream) {
+  DPT_CHECK_ARG(N > 0 && H > 0, "dpt_bandit_rollin_p2p: empty shard (N=%d, H=%d) cannot signal its peers", N, H);
+  return bandit_rollin_impl(means, var, seed, env_id0, N, H, d, ctx_states, ctx_actions, ctx_next_states, ctx_rewards,
+                            return_stats, nullptr, nullptr, peer_dst, n_peers, done_counter, stream);
+}
+
+// ---- peer-memory plumbing: buffers that other ranks' kernels can store into over NVLink ----
+extern "C" int dpt_peer_buffer_create(uint64_t bytes, void** dev_ptr, unsigned char handle[64]) {
+  DPT_CHECK_ARG(bytes > 0 && dev_ptr && handle, "dpt_peer_buffer_create: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  void* ptr = nullptr;
+  DPT_CUDA(cudaMalloc(&ptr, bytes));
+  DPT_CUDA(cudaMemset(ptr, 0, bytes));
+  cudaIpcMemHandle_t h;
+  DPT_CUDA(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle, &h, 64);
+  *dev_ptr = ptr;
+  return DPT_OK;
+}
+extern "C" int dpt_peer_buffer_open(const unsigned char handle[64], void** dev_ptr) {
+  DPT_CHECK_ARG(handle && dev_ptr, "dpt_peer_buffer_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  DPT_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return DPT_OK;
+}
+extern "C" int dpt_peer_buffer_close(void* dev_ptr) {
+  if (dev_ptr) DPT_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return DPT_OK;
+}
+extern "C" int dpt_peer_buffer_destroy(void* dev_ptr) {
+  if (dev_ptr) DPT_CUDA(cudaFree(dev_ptr));
+  return DPT_OK;
+}
+extern "C" int dpt_peer_buffer_read(const void* dev_ptr, void* host_dst, uint64_t bytes, void* stream) {
+  DPT_CHECK_ARG(dev_ptr && host_dst, "dpt_peer_buffer_read: null pointer");
+  DPT_CUDA(cudaMemcpyAsync(host_dst, dev_ptr, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  DPT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return DPT_OK;
 }

@@ -69,8 +69,63 @@ def regret_stats_from_sums(sums, n_envs):
     return {"mean": m, "sem": se, "regret_mean": cm, "regret_sem": cse}
 
 
+class PeerGather:
+    """Per-rank gather buffers [slots, world, width] float64, mutually mapped over CUDA IPC.
+
+    Rank r's kernels store their statistics for slot s straight into element [s, r, :] of EVERY rank's
+    buffer over NVLink (dpt_bandit_rollin_p2p): an all-gather with no collective launch.  Readers must
+    order themselves after all ranks' launches (stream synchronise + barrier), then ``read()``."""
+
+    def __init__(self, slots, width=3):
+        import ctypes
+        from ._lib import check, lib
+        self.rank, self.world = world()
+        self.slots, self.width = slots, width
+        self.data_bytes = slots * self.world * width * 8
+        self.ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        check(lib().dpt_peer_buffer_create(self.data_bytes + 256, ctypes.byref(self.ptr), handle), "dpt_peer_buffer_create")
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, bytes(handle))
+        self.peer_ptrs, self._opened = [], []
+        for r in range(self.world):
+            if r == self.rank:
+                self.peer_ptrs.append(self.ptr.value)
+            else:
+                h = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+                pp = ctypes.c_void_p()
+                check(lib().dpt_peer_buffer_open(h, ctypes.byref(pp)), "dpt_peer_buffer_open")
+                self.peer_ptrs.append(pp.value)
+                self._opened.append(pp)
+        self.counter_ptr = self.ptr.value + self.data_bytes          # uint32 done-counter of this rank's launches
+        self._ctypes = ctypes
+
+    def dst_array(self, slot):
+        """Host array of device pointers: element [slot, my rank, 0] of every rank's buffer."""
+        ct = self._ctypes
+        off = ((slot * self.world + self.rank) * self.width) * 8
+        return (ct.c_void_p * self.world)(*[p + off for p in self.peer_ptrs])
+
+    def read(self):
+        """This rank's buffer as a numpy array [slots, world, width] (synchronises the current stream)."""
+        from ._lib import check, lib, stream_ptr
+        out = np.empty((self.slots, self.world, self.width), dtype=np.float64)
+        check(lib().dpt_peer_buffer_read(self.ptr, out.ctypes.data, self.data_bytes, stream_ptr()), "dpt_peer_buffer_read")
+        return out
+
+    def close(self):
+        from ._lib import lib
+        for pp in self._opened:
+            lib().dpt_peer_buffer_close(pp)
+        self._opened = []
+        if self.ptr:
+            lib().dpt_peer_buffer_destroy(self.ptr)
+            self.ptr = None
+
+
 # ------------------------------------------------------------------ sharded entry points -------
-def collect_bandit_sharded(n_envs_total, dim, horizon, var, seed, device=None):
+def collect_bandit_sharded(n_envs_total, dim, horizon, var, seed, device=None, peer=None, peer_slot=0):
     """BASELINE config 5: bandit collection over all ranks.  Returns (local batch dict, global
     statistics dict).  The local batch holds this rank's env slice only."""
     from . import kernels
@@ -78,9 +133,16 @@ def collect_bandit_sharded(n_envs_total, dim, horizon, var, seed, device=None):
     lo, hi = shard_range(n_envs_total, rank, ws)
     means, opt_idx, opt_a = kernels.bandit_sample_means(hi - lo, dim, seed, lo, device)
     stats = torch.zeros(3, dtype=torch.float64, device=means.device)
-    batch = kernels.bandit_rollin(means, horizon, float(var), seed, lo, stats=stats)
+    if peer is not None:   # fused all-gather over NVLink peer memory, no collective launch
+        batch = kernels.bandit_rollin(means, horizon, float(var), seed, lo, stats=stats, peer=peer, peer_slot=peer_slot)
+        torch.cuda.synchronize()
+        if ws > 1:
+            dist.barrier()
+        gathered = peer.read()[peer_slot]
+    else:
+        batch = kernels.bandit_rollin(means, horizon, float(var), seed, lo, stats=stats)
+        gathered = all_gather_stats(stats).cpu().numpy()
     batch.update(means=means, opt_a_index=opt_idx, optimal_actions=opt_a, env_range=(lo, hi))
-    gathered = all_gather_stats(stats).cpu().numpy()
     steps = [(shard_range(n_envs_total, r, ws)[1] - shard_range(n_envs_total, r, ws)[0]) * horizon for r in range(ws)]
     return batch, merge_return_stats(gathered, steps)
 

@@ -54,12 +54,14 @@ def bandit_opt_action(means):
 
 
 # ------------------------------------------------------------------ rollin_bandit --------------
-def bandit_rollin(means, H, var, seed, env_id0=0, inject=None, dump=False, out=None, stats=None):
+def bandit_rollin(means, H, var, seed, env_id0=0, inject=None, dump=False, out=None, stats=None, peer=None, peer_slot=0):
     """Fused rollin_bandit for all envs (collect_data.py:23-53).  ``means`` [N,d] fp32 device tensor.
 
     inject: dict with 'z' [N,H] and either 'actions' [N,H] or ('cov_idx' [N], 'dir_probs' [N,d] f64,
     'rand_idx' [N], 'u' [N,H] f64).  dump=True additionally returns the noise that was used.
     stats: optional f64 [3] device tensor, += (sum r, sum r^2, #optimal-arm pulls).
+    peer: optional dist.PeerGather -- the launch then also stores this rank's three totals into slot
+    ``peer_slot`` of every rank's gather buffer over NVLink (``stats`` must be zero before the launch).
     Returns dict: context_states [N,H,1], context_actions [N,H,d], context_next_states [N,H,1],
     context_rewards [N,H,1] (fp32, device) [+ 'noise' dict]."""
     dev = _dev(means.device if torch.is_tensor(means) and means.is_cuda else None)
@@ -91,6 +93,13 @@ def bandit_rollin(means, H, var, seed, env_id0=0, inject=None, dump=False, out=N
         for k, t in noise.items():
             setattr(s2, k, ptr(t))
         dump_p = ctypes.byref(s2)
+    if peer is not None:
+        assert inject is None and not dump and stats is not None
+        check(lib().dpt_bandit_rollin_p2p(ptr(means), var, seed, env_id0, N, H, d, ptr(out["context_states"]),
+                                          ptr(out["context_actions"]), ptr(out["context_next_states"]),
+                                          ptr(out["context_rewards"]), ptr(stats), peer.dst_array(peer_slot), peer.world,
+                                          peer.counter_ptr, stream_ptr()), "dpt_bandit_rollin_p2p")
+        return out
     check(lib().dpt_bandit_rollin(ptr(means), var, seed, env_id0, N, H, d, ptr(out["context_states"]),
                                   ptr(out["context_actions"]), ptr(out["context_next_states"]),
                                   ptr(out["context_rewards"]), ptr(stats), inj_p, dump_p, stream_ptr()), "dpt_bandit_rollin")

@@ -36,6 +36,7 @@ extern "C" {
 #define DPT_ERR_UNSUPPORTED (-3)
 
 #define DPT_ABI_VERSION 1
+#define DPT_MAX_PEERS 16
 
 int dpt_version(void);
 const char* dpt_last_error(void);
@@ -80,6 +81,24 @@ int dpt_bandit_rollin(const float* means, float var, uint64_t seed, uint64_t env
                       float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
                       double* return_stats, const dpt_bandit_inject_t* inject, const dpt_bandit_dump_t* dump,
                       void* stream);
+
+/* Multi-GPU form: the same launch, plus a fused all-gather of the three return statistics over NVLink peer
+ * memory.  return_stats must be zero before the launch (it holds this launch's totals only).  When the last
+ * CTA has seen every CTA's contribution it stores the three totals to peer_dst[r][0..2] for r < n_peers
+ * (peer_dst: HOST array of device pointers, normally slot `rank` of every rank's gather buffer, opened with
+ * dpt_peer_buffer_open; one of them may be this rank's own buffer).  done_counter: device uint32, zero
+ * before the first launch, reset by the kernel.  No collective launch, no host synchronisation; readers
+ * must order themselves after all ranks' launches (stream sync + barrier). */
+int dpt_bandit_rollin_p2p(const float* means, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
+                          float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
+                          double* return_stats, double* const* peer_dst, int n_peers, unsigned int* done_counter,
+                          void* stream);
+/* Buffers other ranks' kernels may write: cudaMalloc + CUDA IPC handle (64 bytes) / open in a peer process. */
+int dpt_peer_buffer_create(uint64_t bytes, void** dev_ptr, unsigned char handle[64]);
+int dpt_peer_buffer_open(const unsigned char handle[64], void** dev_ptr);
+int dpt_peer_buffer_close(void* dev_ptr);
+int dpt_peer_buffer_destroy(void* dev_ptr);
+int dpt_peer_buffer_read(const void* dev_ptr, void* host_dst, uint64_t bytes, void* stream);  /* D2H + stream sync */
 
 /* Host-buffer form of the same call (the e2e path): means_host [N,d] in, the four context
  * arrays out, all HOST pointers (pinned for full speed).  Uses `scratch` (device, at least

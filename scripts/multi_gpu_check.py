@@ -32,6 +32,14 @@ def main():
     lo, hi = batch["env_range"]
     mine = torch.cat([digest(batch[k]) for k in ("context_actions", "context_rewards", "context_states")])
     allh = D.all_gather_stats(mine)
+    # the same collection with the all-gather fused into the kernel (NVLink peer stores, no NCCL call)
+    pg = D.PeerGather(slots=2)
+    batch2, stats2 = D.collect_bandit_sharded(N, d, H, var, seed, peer=pg, peer_slot=1)
+    p2p_ok = all(abs(stats2[k] - stats[k]) < 1e-12 for k in stats) and all(torch.equal(batch2[k], batch[k]) for k in ("context_actions", "context_rewards"))
+    flag = torch.tensor([1.0 if p2p_ok else 0.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    p2p_ok = bool(flag.item() == 1.0)
+    pg.close()
     out, curves = D.online_eval_sharded("thompson", N, d, H, var, seed, p0=var, p1=0.5, p2=1 / 12.0)
     cm = digest(out["cum_means"])
     allc = D.all_gather_stats(cm)
@@ -50,8 +58,9 @@ def main():
         ok &= abs(ref["mean_reward"] - stats["mean_reward"]) < 1e-9 and abs(ref["frac_optimal_arm"] - stats["frac_optimal_arm"]) < 1e-12
         rc = D.regret_stats_from_sums(fo["regret_sums"].cpu().numpy(), N)
         ok &= bool(np.allclose(rc["regret_mean"], curves["regret_mean"], rtol=1e-9)) and bool(np.allclose(rc["sem"], curves["sem"], rtol=1e-6))
-        print("multi_gpu_check world=%d: %s (mean reward %.5f, final cumulative regret %.3f +- %.3f)" % (
-            ws, "OK" if ok else "MISMATCH", stats["mean_reward"], curves["regret_mean"][-1], curves["regret_sem"][-1]))
+        ok &= p2p_ok
+        print("multi_gpu_check world=%d: %s [p2p gather %s] (mean reward %.5f, final cumulative regret %.3f +- %.3f)" % (
+            ws, "OK" if ok else "MISMATCH", "OK" if p2p_ok else "MISMATCH", stats["mean_reward"], curves["regret_mean"][-1], curves["regret_sem"][-1]))
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
