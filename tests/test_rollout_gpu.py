@@ -355,3 +355,29 @@ def test_collect_data_dropin_api(dpt):
     obs, acts, nobs, rews = vec.deploy(OptCtrl())
     assert obs.shape == (2, 4, 2) and acts.shape == (2, 4, 5) and rews.shape == (2, 4)
     assert np.array_equal(nobs[:, -1], [[2, 2], [0, 1]]) and rews[1].tolist() == [1, 1, 1, 1]
+
+
+def test_bandit_rollin_fused_peer_gather_single_rank(dpt):
+    """dpt_bandit_rollin_p2p with world = 1: the last CTA publishes the launch's three totals into this rank's
+    own CUDA-IPC gather buffer; outputs equal the plain launch, the done-counter resets between launches."""
+    from dpt_b200 import dist as D
+    N, d, H, var, seed = 20000, 5, 100, 0.3, 8
+    means, _, _ = dpt.kernels.bandit_sample_means(N, d, seed, 0)
+    ref_stats = torch.zeros(3, dtype=torch.float64, device="cuda")
+    ref = dpt.kernels.bandit_rollin(means, H, var, seed, 0, stats=ref_stats)
+    pg = D.PeerGather(slots=3)
+    try:
+        for slot in (0, 2, 1):                                  # three launches: the counter must re-arm itself
+            st = torch.zeros(3, dtype=torch.float64, device="cuda")
+            out = dpt.kernels.bandit_rollin(means, H, var, seed, 0, stats=st, peer=pg, peer_slot=slot)
+            for k in ref:
+                assert torch.equal(ref[k], out[k])
+            assert torch.equal(st, ref_stats)
+        got = pg.read()
+        assert got.shape == (3, 1, 3)
+        for slot in range(3):
+            assert np.array_equal(got[slot, 0], _np(ref_stats))
+        batch, stats = D.collect_bandit_sharded(N, d, H, var, seed, peer=pg, peer_slot=0)
+        assert abs(stats["mean_reward"] - float(ref_stats[0]) / (N * H)) < 1e-12 and stats["env_steps"] == N * H
+    finally:
+        pg.close()
