@@ -25,6 +25,22 @@ int sm_count() {
   return cached;
 }
 
+int pick_envs_per_cta(int N, int slots, int min_e, int max_e) {
+  if (min_e < 1) min_e = 1;
+  if (max_e < min_e) max_e = min_e;
+  if (slots < 1) slots = 1;
+  int best = -1;
+  double best_eff = -1.0;
+  for (int e = max_e; e >= min_e; --e) {
+    const long grid = ((long)N + e - 1) / e;
+    const long waves = (grid + slots - 1) / slots;
+    if (waves < 3 && e > min_e) continue;           // too coarse: keep shrinking e
+    const double eff = (double)grid / (double)(waves * slots);
+    if (eff > best_eff + 1e-9) best_eff = eff, best = e;
+  }
+  return best < 0 ? min_e : best;
+}
+
 }  // namespace dpt
 
 extern "C" int dpt_version(void) { return DPT_ABI_VERSION; }

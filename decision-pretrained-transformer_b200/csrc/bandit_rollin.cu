@@ -351,12 +351,21 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_generic(const Rollin
 }
 
 template <int MODE>
-static void launch_mode(const RollinParams& p, bool fast, int grid, cudaStream_t st) {
+static void launch_mode(RollinParams p, bool fast, cudaStream_t st) {
+  // envs per CTA: up to 32, few enough that the grid covers the machine >= 3 times, and chosen so that the
+  // last wave is nearly full (the kernel's real occupancy decides what a wave is)
+  auto go = [&](auto kern) {
+    static int per_sm = 0;
+    if (per_sm == 0) per_sm = resident_ctas(kern);
+    p.envs_per_cta = pick_envs_per_cta(p.N, sm_count() * per_sm, 1, RB_MAX_ENVS);
+    const int grid = (p.N + p.envs_per_cta - 1) / p.envs_per_cta;
+    kern<<<grid, RB_THREADS, 0, st>>>(p);
+  };
   if (fast) {
     switch (p.d) {
-#define DPT_CASE(DD)                                              \
-  case DD:                                                        \
-    bandit_rollin_fast<DD, MODE><<<grid, RB_THREADS, 0, st>>>(p); \
+#define DPT_CASE(DD)                        \
+  case DD:                                  \
+    go(bandit_rollin_fast<DD, MODE>);       \
     return;
       DPT_CASE(2)
       DPT_CASE(3)
@@ -371,18 +380,15 @@ static void launch_mode(const RollinParams& p, bool fast, int grid, cudaStream_t
         break;
     }
   }
-  bandit_rollin_generic<MODE><<<grid, RB_THREADS, 0, st>>>(p);
+  go(bandit_rollin_generic<MODE>);
 }
 
-// envs per CTA: as many as 32, but few enough that the grid covers the machine several times
-// (8 resident CTAs/SM) and ends close to a whole number of waves.
-int rollin_envs_per_cta(int N) {
-  const int slots = sm_count() * 8;
-  int waves = 4;
-  int e = (N + slots * waves - 1) / (slots * waves);
-  if (e > RB_MAX_ENVS) e = RB_MAX_ENVS;
-  if (e < 1) e = 1;
-  return e;
+// resident CTAs per SM of a kernel (occupancy API), cached per kernel pointer
+template <typename K>
+static int resident_ctas(K kern) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, RB_THREADS, 0) != cudaSuccess || n < 1) n = 4;
+  return n;
 }
 
 }  // namespace dpt
@@ -413,7 +419,6 @@ static int bandit_rollin_impl(const float* means, float var, uint64_t seed, uint
     p.n_peers = n_peers;
     p.done_counter = done_counter;
   }
-  p.envs_per_cta = rollin_envs_per_cta(N);
   int mode = MODE_PHILOX;
   if (inject) {
     DPT_CHECK_ARG(!dump, "dpt_bandit_rollin: inject and dump are mutually exclusive");
@@ -428,14 +433,13 @@ static int bandit_rollin_impl(const float* means, float var, uint64_t seed, uint
   }
   const bool fast = (H % 4 == 0) && 2 * d <= 32 && aligned16(ctx_states) && aligned16(ctx_actions) &&
                     aligned16(ctx_next_states) && aligned16(ctx_rewards);
-  const int grid = (N + p.envs_per_cta - 1) / p.envs_per_cta;
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == MODE_PHILOX)
-    launch_mode<MODE_PHILOX>(p, fast, grid, st);
+    launch_mode<MODE_PHILOX>(p, fast, st);
   else if (mode == MODE_PHILOX_DUMP)
-    launch_mode<MODE_PHILOX_DUMP>(p, fast, grid, st);
+    launch_mode<MODE_PHILOX_DUMP>(p, fast, st);
   else
-    launch_mode<MODE_INJECT>(p, fast, grid, st);
+    launch_mode<MODE_INJECT>(p, fast, st);
   DPT_LAUNCH_CHECK();
   return DPT_OK;
 }

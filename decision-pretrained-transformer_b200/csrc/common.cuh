@@ -15,6 +15,9 @@ namespace dpt {
 
 void set_error(const char* fmt, ...);
 int sm_count();
+// Envs per CTA such that the grid (ceil(N / e) CTAs, `slots` resident at a time) ends close to a whole number
+// of waves: among e in [min_e, max_e] with at least 3 waves, the one with the fullest last wave (ties: larger e).
+int pick_envs_per_cta(int N, int slots, int min_e, int max_e);
 
 #define DPT_CHECK_ARG(cond, ...)                \
   do {                                          \

@@ -377,17 +377,20 @@ extern "C" int dpt_darkroom_rollin(const int32_t* goals, const int32_t* perm_ind
     p.in = *inject, p.has_in = true;
   }
   if (dump) p.out = *dump, p.has_out = true;
-  // several waves of 8 CTAs/SM, at least ~2k steps per CTA
-  const int slots = sm_count() * 8 * 4;
-  int e = (N + slots - 1) / slots;
-  const int min_e = H > 0 ? (2048 + H - 1) / H : 1;
-  if (e < min_e) e = min_e;
-  if (e > DK_MAX_ENVS) e = DK_MAX_ENVS;
+  // >= 3 waves with a nearly full last wave, at least ~2k steps per CTA
+  const bool fast = H > 0 && (H % 4 == 0) && dim <= 256 && aligned16(ctx_states) && aligned16(ctx_actions) &&
+                    aligned16(ctx_next_states) && aligned16(ctx_rewards);
+  static int per_sm_fast = 0, per_sm_gen = 0;
+  if (per_sm_fast == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fast, darkroom_rollin_fast, DK_THREADS, 0) != cudaSuccess || per_sm_fast < 1) per_sm_fast = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_gen, darkroom_rollin_generic, DK_THREADS, 0) != cudaSuccess || per_sm_gen < 1) per_sm_gen = 4;
+  }
+  int min_e = H > 0 ? (2048 + H - 1) / H : 1;
+  if (min_e > DK_MAX_ENVS) min_e = DK_MAX_ENVS;
+  const int e = pick_envs_per_cta(N, sm_count() * (fast ? per_sm_fast : per_sm_gen), min_e, DK_MAX_ENVS);
   p.envs_per_cta = e;
   p.magic_H = (H > 1 && (uint64_t)e * H * H < 0xffffffffull) ? (uint32_t)((0x100000000ull + (uint64_t)H - 1) / (uint64_t)H) : 0u;
   const int grid = (N + e - 1) / e;
-  const bool fast = H > 0 && (H % 4 == 0) && dim <= 256 && aligned16(ctx_states) && aligned16(ctx_actions) &&
-                    aligned16(ctx_next_states) && aligned16(ctx_rewards);
   if (fast)
     darkroom_rollin_fast<<<grid, DK_THREADS, 0, (cudaStream_t)stream>>>(p);
   else
