@@ -1,4 +1,4 @@
-// Dense Transformer.forward(x) in fp32 on the CUDA cores (precision = 0, sequences of <= 128 tokens).
+// Dense Transformer.forward(x) in fp32 on the CUDA cores (precision = 0, sequences of <= 512 tokens).
 //
 // Same decomposition as the tensor-core kernel (gpt2_dense.cu) -- one CTA per sequence, thread t owns token
 // row t, residual stream in fp32 registers -- but every contraction is fp32 FFMA2 (fma.rn.f32x2) so the
@@ -12,15 +12,13 @@
 
 namespace dpt {
 
-constexpr int DF_THREADS = 128;
-// shared memory (floats)
+// shared memory (floats); the CTA has THREADS = 128 / 256 / 512 threads = token rows
 constexpr int DF_WQKV = 0;                     // [32][96]
 constexpr int DF_WPROJ = DF_WQKV + 32 * 96;    // [32][32]
 constexpr int DF_WFC = DF_WPROJ + 32 * 32;     // [32][128]
 constexpr int DF_WFC2 = DF_WFC + 32 * 128;     // [128][32]
-constexpr int DF_K = DF_WFC2 + 128 * 32;       // [128][32]
-constexpr int DF_V = DF_K + 128 * 32;          // [128][32]
-constexpr int DF_FLOATS = DF_V + 128 * 32;     // 20480 floats = 80 KB
+constexpr int DF_K = DF_WFC2 + 128 * 32;       // [THREADS][32], then V [THREADS][32]
+constexpr int df_floats(int threads) { return DF_K + 2 * threads * 32; }   // 80 KB / 112 KB / 176 KB
 
 __device__ __forceinline__ float2 ffma2_(float2 a, float2 b, float2 c) {
   float2 d;
@@ -64,7 +62,9 @@ __device__ __forceinline__ float gelu_new_f(float x) {
   return 0.5f * x * (1.0f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
 }
 
+template <int DF_THREADS>
 __global__ void __launch_bounds__(DF_THREADS) gpt2_dense_fp32_kernel(const DenseParams p) {
+  constexpr int DF_V = DF_K + DF_THREADS * 32;
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x;
   const int b = blockIdx.x;
@@ -211,15 +211,18 @@ __global__ void __launch_bounds__(DF_THREADS) gpt2_dense_fp32_kernel(const Dense
   }
 }
 
+template <int THREADS>
+static cudaError_t launch_df(const DenseParams& p, cudaStream_t st) {
+  const int smem = df_floats(THREADS) * (int)sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(gpt2_dense_fp32_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  gpt2_dense_fp32_kernel<THREADS><<<p.B, THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
 int gpt2_dense_fp32_launch(const DenseParams& p, cudaStream_t st) {
-  const int smem = DF_FLOATS * (int)sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(gpt2_dense_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) {
-    set_error("gpt2_dense_fp32: cannot reserve %d B of shared memory: %s", smem, cudaGetErrorString(e));
-    return DPT_ERR_CUDA;
-  }
-  gpt2_dense_fp32_kernel<<<p.B, DF_THREADS, smem, st>>>(p);
-  e = cudaGetLastError();
+  const int S = p.T + 1;
+  cudaError_t e = S <= 128 ? launch_df<128>(p, st) : S <= 256 ? launch_df<256>(p, st) : launch_df<512>(p, st);
   if (e != cudaSuccess) {
     set_error("gpt2_dense_fp32 launch failed: %s", cudaGetErrorString(e));
     return DPT_ERR_CUDA;

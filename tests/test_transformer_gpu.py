@@ -298,8 +298,8 @@ def test_bf16_kv_mode_within_2e2(dpt, name):
 @pytest.mark.parametrize("dx,du,L", [(2, 5, 4), (1, 5, 3), (1, 10, 2)])
 def test_dense_tensor_core_forward(dpt, dx, du, L):
     """precision = 1, sequences <= 128 tokens: the tcgen05 dense kernel (bf16 operands, fp32 accumulate in
-    TMEM) against the fp32 path and the float64 oracle at the 2e-2 bar; longer sequences fall back to the
-    bf16-K/V token-sequential kernel."""
+    TMEM) against the fp32 path and the float64 oracle at the 2e-2 bar; 129..512 tokens run the fp32 dense
+    kernel (256 / 512 threads per sequence) in both precisions."""
     from dpt_b200.models.net import Transformer
     torch.manual_seed(dx * 100 + du)
     cfg = {"horizon": 160, "state_dim": dx, "action_dim": du, "n_layer": L, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True}
@@ -330,7 +330,7 @@ def test_dense_tensor_core_forward(dpt, dx, du, L):
             out = m(x)
             assert out.shape == ref.shape
             _close(_np(out), _np(ref), 2e-2)
-            assert not torch.equal(out, ref)
+            assert torch.equal(out, ref) == (t + 1 > 128)      # <= 128 tokens: tcgen05 bf16; longer: the fp32 dense kernel
         if t in (17, 127):
             o64 = O.transformer_forward(sd, q, cs[:, :t], ca[:, :t], cns[:, :t], cr[:, :t], L, test=False)
             _close(_np(out), o64, 2e-2)
@@ -340,3 +340,36 @@ def test_dense_tensor_core_forward(dpt, dx, du, L):
     big["query_states"] = f(q)[:1].expand(300, -1)
     o = m(big)
     assert float((o - o[0]).abs().max()) == 0.0
+
+
+def test_forward_long_sequences(dpt):
+    """Dense fp32 kernel with 256 / 512 token rows, and the token-sequential kernel (> 512 tokens: fp32 and bf16
+    K/V cache) against the float64 oracle."""
+    from dpt_b200.models.net import Transformer
+    torch.manual_seed(3)
+    H, d, L = 560, 5, 2
+    m = Transformer({"horizon": H, "state_dim": 1, "action_dim": d, "n_layer": L, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True})
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if "wte" not in k:
+                p.add_(0.05 * torch.randn_like(p))
+    sd = {k: v.cpu().numpy() for k, v in m.state_dict().items()}
+    rs = np.random.RandomState(2)
+    B = 5
+    ca, cr = np.eye(d)[rs.randint(0, d, (B, H))], rs.normal(0.5, 0.5, (B, H, 1))
+    ones = np.ones((B, H, 1))
+    f = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda")   # noqa: E731
+    for t in (200, 255, 256, 400, 511, 512, 540):
+        x = {"query_states": torch.ones(B, 1, device="cuda"), "context_states": f(ones[:, :t]), "context_actions": f(ca[:, :t]),
+             "context_next_states": f(ones[:, :t]), "context_rewards": f(cr[:, :t])}
+        ref = O.transformer_forward(sd, np.ones((B, 1)), ones[:, :t], ca[:, :t], ones[:, :t], cr[:, :t], L, test=True)
+        m.precision = 0
+        _close(_np(m(x)), ref, 1e-5)
+        m.precision = 1
+        _close(_np(m(x)), ref, 2e-2)
+    m.precision = 0
+    m.test = False
+    t = 300
+    x = {"query_states": torch.ones(B, 1, device="cuda"), "context_states": f(ones[:, :t]), "context_actions": f(ca[:, :t]),
+         "context_next_states": f(ones[:, :t]), "context_rewards": f(cr[:, :t])}
+    _close(_np(m(x)), O.transformer_forward(sd, np.ones((B, 1)), ones[:, :t], ca[:, :t], ones[:, :t], cr[:, :t], L, test=False), 1e-5)
