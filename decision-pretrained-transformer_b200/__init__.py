@@ -12,7 +12,7 @@ from . import envs, collect_data          # noqa: F401
 from .envs import base_env, bandit_env, gpu_bandit_env, darkroom_env   # noqa: F401
 from . import ctrls, evals                # noqa: F401
 from .ctrls import ctrl_bandit, ctrl_darkroom   # noqa: F401
-from .evals import eval_bandit, eval_linear_bandit, eval_darkroom   # noqa: F401
+from .evals import eval_bandit, eval_linear_bandit, eval_darkroom, eval_interactive_bandit   # noqa: F401
 from . import models, dataset             # noqa: F401
 from .models import net                   # noqa: F401
 

@@ -71,3 +71,22 @@ class GPUBanditEnv(BaseEnv):
         res = self.deploy(ctrl)
         self.var = tmp
         return res
+
+    # ---- interactive rollouts (train_interactive.py:97-134, rollout half) ----------------------------
+    def rollout(self, model, K=None, sample=True):
+        """The K-step interactive rollout of the reference's on-policy trainers in ONE fused launch: at each
+        step the transformer sees the context so far (K/V-cached), an action is drawn from its logits, the env
+        steps, the row is appended.  Returns the four context tensors [n_envs,K,.] (device, fp32), the logits
+        the model produced at every step [K,n_envs,du] and ``target = opt_a_index`` (:134).  Training itself
+        (backward through the last forward) is out of scope: a trainer re-runs ``model(batch)`` on
+        ``context[:, :K-1]`` with its own autograd-enabled model to get ``last_logits`` with gradients."""
+        if self.type != "uniform":
+            raise NotImplementedError("fused rollout: uniform bandits only")
+        K = self.H if K is None else K
+        with torch.cuda.device(self._device):
+            out = model.online_loop(self.means, K, float(self.var), sample, self._key ^ 0x2545F4914F6CDD1D, self._env_id0,
+                                    materialise=True, regret=False, dump=True)
+        self._draws += K
+        return {"context_states": out["context_states"], "context_actions": out["context_actions"],
+                "context_next_states": out["context_next_states"], "context_rewards": out["context_rewards"],
+                "logits": out["noise"]["logits"], "target": self.opt_a_index}

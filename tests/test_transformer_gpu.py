@@ -373,3 +373,29 @@ def test_forward_long_sequences(dpt):
     x = {"query_states": torch.ones(B, 1, device="cuda"), "context_states": f(ones[:, :t]), "context_actions": f(ca[:, :t]),
          "context_next_states": f(ones[:, :t]), "context_rewards": f(cr[:, :t])}
     _close(_np(m(x)), O.transformer_forward(sd, np.ones((B, 1)), ones[:, :t], ca[:, :t], ones[:, :t], cr[:, :t], L, test=False), 1e-5)
+
+
+def test_interactive_bandit_rows(dpt):
+    """SURVEY §8(f) row 4 (rollout half of train_interactive.py:97-134) and evals/eval_interactive_bandit.py
+    run_online_eval: fused K-step interactive rollout on GPUBanditEnv; the logits it reports at step t are
+    the dense forward's logits on context[:, :t]."""
+    from dpt_b200.envs.gpu_bandit_env import GPUBanditEnv
+    from dpt_b200.evals import eval_interactive_bandit
+    g = golden("transformer_l2")
+    m, _ = _model(dpt, g)
+    env = GPUBanditEnv(5, 300, 12, var=0.3, seed=4)
+    ro = env.rollout(m, K=12, sample=True)
+    assert ro["context_actions"].shape == (300, 12, 5) and ro["logits"].shape == (12, 300, 5) and ro["target"].shape == (300,)
+    assert torch.equal(ro["target"], env.means.argmax(1))
+    for t in (0, 5, 11):
+        b = {k: ro[k][:, :t] for k in ("context_states", "context_actions", "context_next_states", "context_rewards")}
+        b["query_states"] = env.reset()
+        _close(_np(ro["logits"][t]), _np(m(b)), 5e-6)
+    resid = (ro["context_rewards"][:, :, 0] - (env.means[:, None, :] * ro["context_actions"]).sum(-1)) / 0.3
+    assert abs(float(resid.mean())) < 0.1 and abs(float(resid.std()) - 1) < 0.1
+    rs = np.random.RandomState(0)
+    trajs = [{"means": rs.uniform(0, 1, 5)} for _ in range(64)]
+    res = eval_interactive_bandit.run_online_eval(trajs, m, 64, 12, 0.3, "uniform", sample_model=True)
+    assert set(res) == {"means", "sems", "regret_means", "regret_sems", "all_means", "all_means_diff"}
+    assert set(res["means"]) == {"opt", "Interactive", "Emp", "UCB1.0", "Thomp"}
+    assert res["regret_means"]["Thomp"].shape == (12,) and np.all(res["regret_means"]["opt"] == 0)
