@@ -17,6 +17,10 @@ if t == "darkroom":
     goals = torch.randint(0, 10, (100000, 2), dtype=torch.int32, device="cuda")
     for i in range(reps):
         kernels.darkroom_rollin(goals, 10, 100, "uniform", i, 0, None, 1)
+elif t == "online1m_opt":
+    means, _, _ = kernels.bandit_sample_means(1000000, 5, 0, 0)
+    for i in range(reps):
+        kernels.online_loop("opt", means, 100, 0.3, i, 0)
 elif t.startswith("online_"):
     kind = t.split("_")[1]
     par = {"opt": {}, "emp": dict(p0=1.0), "ucb": dict(p0=1.0), "thompson": dict(p0=0.3, p1=0.5, p2=1 / 12.0),
