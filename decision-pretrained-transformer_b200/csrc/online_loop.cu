@@ -26,7 +26,7 @@ constexpr int OL_THREADS = OL_WARPS * 32;
 constexpr int OL_T = 32;       // steps buffered per flush
 constexpr int OL_MAX_LD = 8;   // max lin_d
 
-enum { K_OPT = 0, K_EMP = 1, K_UCB = 2, K_THOMPSON = 3, K_LINUCB = 4 };
+enum { K_OPT = 0, K_EMP = 1, K_UCB = 2, K_THOMPSON = 3, K_LINUCB = 4, K_LINUCB2 = 5 /* internal: lin_d == 2, state in registers */ };
 
 struct OnlineParams {
   double p0, p1, p2, var;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
   const uint64_t gid = p.env_id0 + (uint64_t)env;
   const bool materialise = p.ctx_a != nullptr;
 
-  if (KIND == K_LINUCB) {
+  if (KIND == K_LINUCB || KIND == K_LINUCB2) {
     for (int i = tid; i < d * p.lin_d; i += OL_THREADS) s_arms[i] = p.arms[i];
   }
   float m[DMAX];
@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
   }
   // LinUCB: S = I + sum x x^T, bvec = sum x r  (ctrls/ctrl_bandit.py:510-513)
   double S[KIND == K_LINUCB ? OL_MAX_LD * OL_MAX_LD : 1], bv[KIND == K_LINUCB ? OL_MAX_LD : 1];
+  double s00 = 1.0, s01 = 0.0, s11 = 1.0, b0 = 0.0, b1 = 0.0;   // K_LINUCB2: Sigma = I + sum x x^T (symmetric), b = sum x r
   if (KIND == K_LINUCB) {
     for (int i = 0; i < p.lin_d; ++i) {
       bv[i] = 0.0;
@@ -190,6 +191,17 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
             if (v > best) best = v, a = j;
           }
         }
+      } else if (KIND == K_LINUCB2 && h > 0) {   // lin_d == 2: closed-form inverse, everything in registers
+        const double idet = 1.0 / (s00 * s11 - s01 * s01);
+        const double i00 = s11 * idet, i01 = -s01 * idet, i11 = s00 * idet;
+        const double t0 = i00 * b0 + i01 * b1, t1 = i01 * b0 + i11 * b1;          // theta = cov_inv @ A^T r  :513
+        double best = -INFINITY;
+        for (int j = 0; j < d; ++j) {
+          const double x0 = s_arms[2 * j], x1 = s_arms[2 * j + 1];
+          const double q = x0 * (i00 * x0 + i01 * x1) + x1 * (i01 * x0 + i11 * x1);
+          const double v = (t0 * x0 + t1 * x1) + p.p0 * sqrt(q);                  // :519
+          if (v > best) best = v, a = j;                                           // strict >: first maximum :520
+        }
       } else {  // LinUCB
         if (h == 0) {                                                   // :496-500 uniform random first arm
           if (p.in.first_arm)
@@ -197,7 +209,7 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
           else
             a = (int)bounded(philox_words(p.key, gid, 0u, STREAM_CTRL).x, (uint32_t)d);
           if (p.out.first_arm && live) p.out.first_arm[env] = a;
-        } else {
+        } else if (KIND == K_LINUCB) {
           const int ld = p.lin_d;
           double Si[OL_MAX_LD * OL_MAX_LD], theta[OL_MAX_LD];
           if (ld == 2) {
@@ -268,6 +280,10 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
           st.aux0[j] = hit ? n0 : st.aux0[j];
           if (KIND != K_EMP) st.aux1[j] = hit ? n1 : st.aux1[j];
         }
+      } else if (KIND == K_LINUCB2) {
+        const double x0 = s_arms[2 * a], x1 = s_arms[2 * a + 1];
+        b0 += x0 * r, b1 += x1 * r;
+        s00 += x0 * x0, s01 += x0 * x1, s11 += x1 * x1;
       } else if (KIND == K_LINUCB) {
         const int ld = p.lin_d;
         const double* x = s_arms + a * ld;
@@ -383,7 +399,7 @@ __global__ void __launch_bounds__(256) arm_stats_kernel(const float* __restrict_
 template <int DMAX, int KIND>
 static cudaError_t launch_online(const OnlineParams& p, cudaStream_t st) {
   const size_t smem = sizeof(WarpTile) * OL_WARPS + sizeof(float) * OL_THREADS * DMAX +
-                      sizeof(double) * (KIND == K_LINUCB ? p.d * p.lin_d : 0) + 16;
+                      sizeof(double) * ((KIND == K_LINUCB || KIND == K_LINUCB2) ? p.d * p.lin_d : 0) + 16;
   auto kern = online_loop_kernel<DMAX, KIND>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -401,7 +417,8 @@ static cudaError_t launch_online_kind(int kind, const OnlineParams& p, cudaStrea
     case K_EMP: return launch_online<DMAX, K_EMP>(p, st);
     case K_UCB: return launch_online<DMAX, K_UCB>(p, st);
     case K_THOMPSON: return launch_online<DMAX, K_THOMPSON>(p, st);
-    default: return launch_online<DMAX, K_LINUCB>(p, st);
+    default:
+      return p.lin_d == 2 ? launch_online<DMAX, K_LINUCB2>(p, st) : launch_online<DMAX, K_LINUCB>(p, st);
   }
 }
 
