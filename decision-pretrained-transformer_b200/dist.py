@@ -83,23 +83,43 @@ class PeerGather:
         self.slots, self.width = slots, width
         self.data_bytes = slots * self.world * width * 8
         self.ptr = ctypes.c_void_p()
-        handle = (ctypes.c_ubyte * 64)()
-        check(lib().dpt_peer_buffer_create(self.data_bytes + 256, ctypes.byref(self.ptr), handle), "dpt_peer_buffer_create")
-        handles = [None] * self.world
-        if self.world > 1:
-            dist.all_gather_object(handles, bytes(handle))
         self.peer_ptrs, self._opened = [], []
+        self._ctypes = ctypes
+        handle = (ctypes.c_ubyte * 64)()
+        # every step is followed by an exchange of success flags, so that all ranks agree on failure
+        # (a rank that raised on its own would leave the others blocked in the next collective)
+        err = None
+        try:
+            check(lib().dpt_peer_buffer_create(self.data_bytes + 256, ctypes.byref(self.ptr), handle), "dpt_peer_buffer_create")
+        except Exception as e:   # noqa: BLE001
+            err = str(e)
+        handles = [bytes(handle) if err is None else None]
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle) if err is None else None)
+        if any(h is None for h in handles):
+            self.close()
+            raise RuntimeError("peer buffer allocation failed on some rank: %s" % err)
         for r in range(self.world):
             if r == self.rank:
                 self.peer_ptrs.append(self.ptr.value)
-            else:
+                continue
+            try:
                 h = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
                 pp = ctypes.c_void_p()
                 check(lib().dpt_peer_buffer_open(h, ctypes.byref(pp)), "dpt_peer_buffer_open")
                 self.peer_ptrs.append(pp.value)
                 self._opened.append(pp)
+            except Exception as e:   # noqa: BLE001
+                err = str(e)
+                break
+        if self.world > 1:
+            oks = [None] * self.world
+            dist.all_gather_object(oks, err is None)
+            if not all(oks):
+                self.close()
+                raise RuntimeError("CUDA IPC peer mapping failed on some rank: %s" % err)
         self.counter_ptr = self.ptr.value + self.data_bytes          # uint32 done-counter of this rank's launches
-        self._ctypes = ctypes
 
     def dst_array(self, slot):
         """Host array of device pointers: element [slot, my rank, 0] of every rank's buffer."""
@@ -119,9 +139,9 @@ class PeerGather:
         for pp in self._opened:
             lib().dpt_peer_buffer_close(pp)
         self._opened = []
-        if self.ptr:
+        if self.ptr is not None and self.ptr.value:
             lib().dpt_peer_buffer_destroy(self.ptr)
-            self.ptr = None
+        self.ptr = None
 
 
 # ------------------------------------------------------------------ sharded entry points -------
