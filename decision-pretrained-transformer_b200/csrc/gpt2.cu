@@ -629,12 +629,13 @@ extern "C" int dpt_gpt2_forward(dpt_gpt2_t* m, const float* query_states, const 
   DPT_CHECK_ARG(query_states && out && (T == 0 || (ctx_states && ctx_actions && ctx_next_states && ctx_rewards)),
                 "dpt_gpt2_forward: null pointer");
   if (T + 1 <= 512) {   // dense path, one CTA per sequence, no K/V scratch:
-    // <= 128 tokens with precision 1: tcgen05 (bf16 operands); otherwise CUDA-core fp32 (also meets the 2e-2 bar)
+    // precision 1: tcgen05 (bf16 operands; 1 tile of 128 tokens or 2..4 tiles); precision 0: CUDA-core fp32
     DenseParams dp{};
     dp.m = m->dev;
     dp.query = query_states, dp.cs = ctx_states, dp.ca = ctx_actions, dp.cns = ctx_next_states, dp.cr = ctx_rewards;
     dp.B = B, dp.T = T, dp.Ts = T_stride, dp.test = test, dp.share = ctx_share, dp.out = out;
-    return (precision == 1 && T + 1 <= 128) ? gpt2_dense_launch(dp, (cudaStream_t)stream) : gpt2_dense_fp32_launch(dp, (cudaStream_t)stream);
+    if (precision == 1) return T + 1 <= 128 ? gpt2_dense_launch(dp, (cudaStream_t)stream) : gpt2_dense_long_launch(dp, (cudaStream_t)stream);
+    return gpt2_dense_fp32_launch(dp, (cudaStream_t)stream);
   }
   DPT_CHECK_ARG(workspace && workspace_bytes >= dpt_gpt2_forward_workspace_bytes(m, B, T, precision),
                 "dpt_gpt2_forward: workspace too small");

@@ -49,6 +49,7 @@ struct DenseParams {
   float* out;
 };
 int gpt2_dense_launch(const DenseParams& p, cudaStream_t st);        // gpt2_dense.cu (tcgen05, bf16 operands)
+int gpt2_dense_long_launch(const DenseParams& p, cudaStream_t st);   // gpt2_dense.cu (tcgen05, 129..512 tokens)
 int gpt2_dense_fp32_launch(const DenseParams& p, cudaStream_t st);   // gpt2_dense_fp32.cu (CUDA cores, fp32)
 void gpt2_pack_wimg(const float* attn_w, const float* proj_w, const float* fc_w, const float* fc2_w, unsigned char* img,
                     cudaStream_t st);

@@ -235,9 +235,10 @@ int dpt_gpt2_destroy(dpt_gpt2_t* m);
  * context row stride `T_stride` steps (so views context[:, :h] of a [B,H,.] buffer can be passed
  * without a copy, as evals/eval_bandit.py:71-76 does).  test != 0 -> out [B,du] (last position);
  * test == 0 -> out [B,T,du] (positions 1..T).  precision: 0 = fp32 everywhere (1e-5 logit bar);
- * 1 = bf16 (2e-2 bar): sequences of <= 128 tokens run the dense tcgen05 kernel (bf16 operands, fp32
- * accumulation in tensor memory).  Sequences of <= 512 tokens otherwise run the dense fp32 CUDA-core kernel
- * (no workspace needed); longer ones the token-sequential kernel with an fp32 / bf16 K/V cache in `workspace`.
+ * 1 = bf16 (2e-2 bar): sequences of <= 512 tokens run the dense tcgen05 kernels (bf16 operands, fp32
+ * accumulation in tensor memory; one 128-token tile, or 2..4 tiles attended flash-style).  With precision 0
+ * sequences of <= 512 tokens run the dense fp32 CUDA-core kernel (neither needs a workspace); longer ones
+ * the token-sequential kernel with an fp32 / bf16 K/V cache in `workspace`.
  * ctx_share >= 1: consecutive groups of ctx_share sequences share ONE context row (sequence b reads
  * context row b / ctx_share; query_states and out stay per sequence) -- used to evaluate every
  * possible query state of an env against its context in one launch (darkroom policy table).

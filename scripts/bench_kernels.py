@@ -98,6 +98,19 @@ def main():
              "context_actions": torch.rand(B, T, 5, device="cuda"), "context_next_states": torch.rand(B, T, 2, device="cuda"), "context_rewards": torch.rand(B, T, 1, device="cuda")}
         mm, mn = timeit(lambda: m(x), max(2, R // 4), warm=1)
         report("gpt2_forward fp32 B=%d T=%d (darkroom token layout, test=True)" % (B, T), B * (T + 1), 40, mm, mn, tokens_per_s=B * (T + 1) / (mm * 1e-3))
+        m.precision = 1
+        mm, mn = timeit(lambda: m(x), max(2, R // 4), warm=1)
+        report("gpt2_forward tcgen05 B=%d T=%d (darkroom token layout, test=True)" % (B, T), B * (T + 1), 40, mm, mn, tokens_per_s=B * (T + 1) / (mm * 1e-3))
+        del m
+        # the bandit model's own context length: 500 tokens, training-style batch (all rows' logits)
+        m = Transformer({"horizon": 500, "state_dim": 1, "action_dim": 5, "n_layer": 4, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": False})
+        B, T = 1024, 500
+        x = {"query_states": torch.ones(B, 1, device="cuda"), "context_states": torch.ones(B, T, 1, device="cuda"),
+             "context_actions": torch.rand(B, T, 5, device="cuda"), "context_next_states": torch.ones(B, T, 1, device="cuda"), "context_rewards": torch.rand(B, T, 1, device="cuda")}
+        for prec in (0, 1):
+            m.precision = prec
+            mm, mn = timeit(lambda: m(x), max(2, R // 4), warm=1)
+            report("gpt2_forward %s B=%d T=%d (bandit token layout, all rows)" % ("tcgen05" if prec else "fp32", B, T), B * (T + 1), 32, mm, mn, tokens_per_s=B * (T + 1) / (mm * 1e-3))
     if want("gpu_bandit_step"):
         N, d = 100000, 5
         means, _, opt_a = kernels.bandit_sample_means(N, d, 0, 0)

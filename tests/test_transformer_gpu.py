@@ -297,9 +297,9 @@ def test_bf16_kv_mode_within_2e2(dpt, name):
 
 @pytest.mark.parametrize("dx,du,L", [(2, 5, 4), (1, 5, 3), (1, 10, 2)])
 def test_dense_tensor_core_forward(dpt, dx, du, L):
-    """precision = 1, sequences <= 128 tokens: the tcgen05 dense kernel (bf16 operands, fp32 accumulate in
-    TMEM) against the fp32 path and the float64 oracle at the 2e-2 bar; 129..512 tokens run the fp32 dense
-    kernel (256 / 512 threads per sequence) in both precisions."""
+    """precision = 1: the tcgen05 dense kernels (bf16 operands, fp32 accumulate in TMEM; <= 128 tokens one
+    tile, 129..512 tokens the flash-style multi-tile kernel) against the fp32 path and the float64 oracle at
+    the 2e-2 bar."""
     from dpt_b200.models.net import Transformer
     torch.manual_seed(dx * 100 + du)
     cfg = {"horizon": 160, "state_dim": dx, "action_dim": du, "n_layer": L, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True}
@@ -330,8 +330,8 @@ def test_dense_tensor_core_forward(dpt, dx, du, L):
             out = m(x)
             assert out.shape == ref.shape
             _close(_np(out), _np(ref), 2e-2)
-            assert torch.equal(out, ref) == (t + 1 > 128)      # <= 128 tokens: tcgen05 bf16; longer: the fp32 dense kernel
-        if t in (17, 127):
+            assert not torch.equal(out, ref)                   # precision 1 is the bf16 tensor-core path
+        if t in (17, 127, 128, 150):
             o64 = O.transformer_forward(sd, q, cs[:, :t], ca[:, :t], cns[:, :t], cr[:, :t], L, test=False)
             _close(_np(out), o64, 2e-2)
     m.precision = 1
@@ -367,12 +367,16 @@ def test_forward_long_sequences(dpt):
         _close(_np(m(x)), ref, 1e-5)
         m.precision = 1
         _close(_np(m(x)), ref, 2e-2)
-    m.precision = 0
     m.test = False
-    t = 300
-    x = {"query_states": torch.ones(B, 1, device="cuda"), "context_states": f(ones[:, :t]), "context_actions": f(ca[:, :t]),
-         "context_next_states": f(ones[:, :t]), "context_rewards": f(cr[:, :t])}
-    _close(_np(m(x)), O.transformer_forward(sd, np.ones((B, 1)), ones[:, :t], ca[:, :t], ones[:, :t], cr[:, :t], L, test=False), 1e-5)
+    for t in (300, 383, 384, 511):      # every row's logits: 3- and 4-tile tensor-core kernels, 512-thread fp32 kernel
+        x = {"query_states": torch.ones(B, 1, device="cuda"), "context_states": f(ones[:, :t]), "context_actions": f(ca[:, :t]),
+             "context_next_states": f(ones[:, :t]), "context_rewards": f(cr[:, :t])}
+        ref = O.transformer_forward(sd, np.ones((B, 1)), ones[:, :t], ca[:, :t], ones[:, :t], cr[:, :t], L, test=False)
+        m.precision = 0
+        _close(_np(m(x)), ref, 1e-5)
+        m.precision = 1
+        _close(_np(m(x)), ref, 2e-2)
+    m.precision = 0
 
 
 def test_interactive_bandit_rows(dpt):
