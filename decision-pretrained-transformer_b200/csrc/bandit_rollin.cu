@@ -163,6 +163,20 @@ __device__ __forceinline__ void reduce_stats(const RollinParams& p, float sr, fl
   }
 }
 
+// packed fp32 pair arithmetic (sm_100: FADD2 / FFMA2, one issue slot for two lanes of work)
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<uint64_t&>(r)) : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+  return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<uint64_t&>(r))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)), "l"(reinterpret_cast<uint64_t&>(c)));
+  return r;
+}
+
 __device__ __forceinline__ int argmax_first(const float* m, int D) {
   int best = 0;
   for (int j = 1; j < D; ++j)
@@ -178,7 +192,7 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_fast(const RollinPar
   using thr_t = typename Thr<MODE>::type;
   __shared__ float s_means[RB_MAX_ENVS][D];
   __shared__ thr_t s_thr[RB_MAX_ENVS][D];
-  __shared__ int s_opt[RB_MAX_ENVS];
+  __shared__ uint32_t s_optmask[RB_MAX_ENVS];   // one-hot bits of the optimal arm in both halves of a step pair
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int env0 = blockIdx.x * p.envs_per_cta;
   const int ne = min(p.envs_per_cta, p.N - env0);
@@ -187,7 +201,8 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_fast(const RollinPar
   if (warp == 0) {
     if (lane < ne) {
       rollin_setup_env<MODE, D>(p, env0 + lane, D, s_means[lane], s_thr[lane]);
-      s_opt[lane] = argmax_first(s_means[lane], D);
+      const int oa = argmax_first(s_means[lane], D);
+      s_optmask[lane] = (1u << oa) | (1u << (D + oa));
     }
   } else {  // bandit state is the constant [1] (envs/bandit_env.py:38): dx = 1
     const size_t b = (size_t)env0 * H, e = (size_t)(env0 + ne) * H;
@@ -198,7 +213,8 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_fast(const RollinPar
 
   const int chunks = (H + 63) >> 6;
   const bool inj_actions = (MODE == MODE_INJECT) && p.in.actions != nullptr;
-  float st_r = 0.f, st_r2 = 0.f, st_opt = 0.f;
+  float2 st_r = make_float2(0.f, 0.f), st_r2 = make_float2(0.f, 0.f);   // per pair component, packed f32x2 updates
+  int st_opt = 0;
   int e = 0, c = warp;   // (env, chunk) of this warp's task, advanced without a division
   while (c >= chunks) c -= chunks, ++e;
   for (; e < ne; c += RB_WARPS) {
@@ -249,14 +265,14 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_fast(const RollinPar
       const float r1 = fmaf(p.var, z1, s_means[e][a1]);
       st_stream_if(h0 < H, reinterpret_cast<float2*>(p.ctx_r + row), make_float2(r0, r1));
       if (p.stats && h0 < H) {
-        const int oa = s_opt[e];
-        st_r += r0 + r1;
-        st_r2 = fmaf(r0, r0, fmaf(r1, r1, st_r2));
-        st_opt += (float)((a0 == oa) + (a1 == oa));
+        const float2 rr = make_float2(r0, r1);
+        st_r = add2(st_r, rr);
+        st_r2 = fma2(rr, rr, st_r2);
       }
     }
     // one-hot rows: lane l holds flat elements [2D*l, 2D*(l+1)) of this chunk as a 2D-bit mask
     const uint32_t m = (1u << a0) | (1u << (D + a1));
+    if (p.stats && h0 < H) st_opt += __popc(m & s_optmask[e]);
     float4* abase = reinterpret_cast<float4*>(p.ctx_a + ((size_t)env * H + (size_t)c * 64) * D);
     const int n_valid4 = (min(64, H - c * 64) * D) >> 2;
 #pragma unroll
@@ -273,7 +289,7 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_fast(const RollinPar
       st_stream_if(q < n_valid4, abase + q, v);
     }
   }
-  if (p.stats) reduce_stats(p, st_r, st_r2, st_opt);
+  if (p.stats) reduce_stats(p, st_r.x + st_r.y, st_r2.x + st_r2.y, (float)st_opt);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -57,6 +57,10 @@ def main():
             out = kernels.bandit_rollin(means, H, 0.3, 0, 0)
             m, mn = timeit(lambda: kernels.bandit_rollin(means, H, 0.3, 1, 0, out=out), R)
             report("bandit_rollin N=%d H=%d d=%d" % (N, H, d), N * H, 4 * (3 + d), m, mn)
+            if N == 125000:   # bench.py's step: the same launch also accumulating the return statistics
+                st = torch.zeros(3, dtype=torch.float64, device="cuda")
+                m, mn = timeit(lambda: kernels.bandit_rollin(means, H, 0.3, 1, 0, out=out, stats=st), R)
+                report("bandit_rollin N=%d H=%d d=%d + return statistics" % (N, H, d), N * H, 4 * (3 + d), m, mn)
             del out
     if want("darkroom"):
         for N, H in [(100000, 100), (1000000, 100)]:
