@@ -16,12 +16,14 @@
 // A thread's own rows are strided by H*d*4 B, so rows are staged per warp in shared memory (1 B per
 // action, 4 B per reward, 32 envs x 32 steps) and flushed as contiguous, 16 B-aligned float4 runs
 // (32 steps * d * 4 B per env).
+#include <type_traits>
+
 #include "common.cuh"
 #include "philox.cuh"
 
 namespace dpt {
 
-constexpr int OL_WARPS = 4;
+constexpr int OL_WARPS = 2;    // max warps per CTA (small CTAs: 11 x 2 warps fit one SM's shared memory at d <= 5)
 constexpr int OL_THREADS = OL_WARPS * 32;
 constexpr int OL_T = 32;       // steps buffered per flush
 constexpr int OL_MAX_LD = 8;   // max lin_d
@@ -37,18 +39,20 @@ struct OnlineParams {
   uint64_t env_id0;
   int N, H, d;
   uint32_t magic_d;  // ceil(2^32 / d): floor(x / d) == umulhi(x, magic_d) for the small x used here
-  uint32_t magic_nq; // same for nq = OL_T * d / 4 (float4 per env per full flush)
   float *ctx_s, *ctx_a, *ctx_ns, *ctx_r, *cum_means;
-  double* regret;
+  double* regret;    // [regret_reps][H][4] accumulators (replicated to spread same-address atomics)
+  int regret_reps;   // power of two
   dpt_online_inject_t in;
   dpt_online_dump_t out;
   bool vec;  // float4 flush allowed
 };
 
 struct WarpTile {
+  // env-major tiles written by lane = env and read back by lane = step; element (e, t) of the float tiles
+  // lives in column (t + e) & 31, which keeps both access directions bank-conflict free without padding
   unsigned char acts[32][OL_T];
-  float rew[32][OL_T + 1];
-  float creg[32][OL_T + 1];   // cumulative regret of each env after each buffered step
+  float rew[32][OL_T];
+  float creg[32][OL_T];       // cumulative regret of each env after each buffered step
 };
 
 template <int DMAX>
@@ -93,16 +97,24 @@ __device__ __forceinline__ void inv_small(const double* S, double* Si, int ld) {
     for (int j = 0; j < ld; ++j) Si[i * ld + j] = a[i][ld + j];
 }
 
+// dynamic shared memory: [nwarps] WarpTile | [nwarps*32][DMAX] float means | (8 B-aligned) [d][lin_d] double arms
+__host__ __device__ inline size_t ol_arms_offset(int nwarps, int dmax) {
+  return (sizeof(WarpTile) * nwarps + sizeof(float) * 32 * nwarps * dmax + 7) & ~size_t(7);
+}
+
 template <int DMAX, int KIND>
 __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlineParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float4 s_nib[16];   // 4-bit pattern -> four 0/1 floats (one-hot flush)
+  const int nthreads = blockDim.x, nwarps = nthreads >> 5;   // 1 or 2 warps per CTA (host picks the wave fit)
   WarpTile* tiles = reinterpret_cast<WarpTile*>(smem_raw);
-  float* s_means_all = reinterpret_cast<float*>(smem_raw + sizeof(WarpTile) * OL_WARPS);  // [OL_THREADS][DMAX]
-  double* s_arms = reinterpret_cast<double*>(s_means_all + OL_THREADS * DMAX);            // [d][lin_d]
+  float* s_means_all = reinterpret_cast<float*>(smem_raw + sizeof(WarpTile) * nwarps);   // [nthreads][DMAX]
+  double* s_arms = reinterpret_cast<double*>(smem_raw + ol_arms_offset(nwarps, DMAX));   // [d][lin_d]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   WarpTile& tile = tiles[warp];
   float(*s_means)[DMAX] = reinterpret_cast<float(*)[DMAX]>(s_means_all) + warp * 32;
-  const int env0w = (blockIdx.x * OL_WARPS + warp) * 32;  // first env of this warp
+  const int env0w = (blockIdx.x * nwarps + warp) * 32;  // first env of this warp
+  if (tid < 16) s_nib[tid] = make_float4((tid & 1) ? 1.f : 0.f, (tid & 2) ? 1.f : 0.f, (tid & 4) ? 1.f : 0.f, (tid & 8) ? 1.f : 0.f);
   const int env = env0w + lane;
   const bool live = env < p.N;
   const int N = p.N, H = p.H, d = p.d;
@@ -110,7 +122,7 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
   const bool materialise = p.ctx_a != nullptr;
 
   if (KIND == K_LINUCB || KIND == K_LINUCB2) {
-    for (int i = tid; i < d * p.lin_d; i += OL_THREADS) s_arms[i] = p.arms[i];
+    for (int i = tid; i < d * p.lin_d; i += nthreads) s_arms[i] = p.arms[i];
   }
   float m[DMAX];
   float mmax = -INFINITY;
@@ -122,6 +134,7 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
     s_means[lane][j] = m[j];
   }
   __syncthreads();
+
 
   // constant states (bandit dx = 1): this warp's envs are one contiguous run
   if (p.ctx_s) {
@@ -149,12 +162,47 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
     }
   }
   const double sigma2 = p.p0 * p.p0;  // Thompson: std^2 (ctrls/ctrl_bandit.py:126)
-  float z_next = 0.f;
   double creg = 0.0;  // this env's cumulative regret (evals/eval_bandit.py:176)
   const int nb_ctrl = (d + 3) >> 2;
 
+  // Thompson: the d control normals of the step about to run; those of step h + 1 are generated while the
+  // float64 posterior arithmetic of step h is in flight (they do not depend on the controller state)
+  float zc[KIND == K_THOMPSON ? DMAX : 1];
+  auto gen_ctrl = [&](int h, float* out) {
+    if (p.in.ctrl_z) {
+#pragma unroll
+      for (int j = 0; j < DMAX; ++j) out[j] = (live && j < d) ? p.in.ctrl_z[((size_t)h * N + env) * d + j] : 0.f;
+    } else {
+#pragma unroll
+      for (int j0 = 0; j0 < DMAX; j0 += 4) {
+        if (j0 < d) {
+          float zz[4];
+          normals4(philox_words(p.key, gid, (uint32_t)(h * nb_ctrl + (j0 >> 2)), STREAM_CTRL), zz);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (j0 + c < DMAX) out[j0 + c] = zz[c];
+        }
+      }
+    }
+  };
+  if (KIND == K_THOMPSON) gen_ctrl(0, zc);
+
   for (int h0 = 0; h0 < H; h0 += OL_T) {
     const int T = min(OL_T, H - h0);
+    // ---- phase A: reward noise of the whole tile (independent Philox / Box-Muller chains, 4 in flight) ----
+    if (p.in.reward_z) {
+      for (int t = 0; t < T; ++t) tile.rew[lane][(t + lane) & (OL_T - 1)] = live ? p.in.reward_z[(size_t)(h0 + t) * N + env] : 0.f;
+    } else {
+#pragma unroll 4
+      for (int t = 0; t < T; t += 2) {
+        const uint4 w = philox_words(p.key, gid, (uint32_t)((h0 + t) >> 1), STREAM_ENV_REWARD);
+        float z0, z1;
+        box_muller(w.z, w.w, z0, z1);
+        tile.rew[lane][(t + lane) & (OL_T - 1)] = z0;
+        tile.rew[lane][(t + 1 + lane) & (OL_T - 1)] = z1;
+      }
+    }
+    // ---- phase B: the sequential controller / env steps ----
     for (int t = 0; t < T; ++t) {
       const int h = h0 + t;
       int a = 0;
@@ -174,23 +222,20 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
         }
         if ((KIND == K_UCB || p.p0 != 0.0) && first_untried >= 0) a = first_untried;   // :110-113 | :373-375
       } else if (KIND == K_THOMPSON) {
+        float zn[DMAX];
+        if (h + 1 < H) gen_ctrl(h + 1, zn);
         double best = -INFINITY;
-        float zz[4];
 #pragma unroll
         for (int j = 0; j < DMAX; ++j) {
           if (j < d) {
-            float zj;
-            if (p.in.ctrl_z) {
-              zj = live ? p.in.ctrl_z[((size_t)h * N + env) * d + j] : 0.f;
-            } else {
-              if ((j & 3) == 0) normals4(philox_words(p.key, gid, (uint32_t)(h * nb_ctrl + (j >> 2)), STREAM_CTRL), zz);
-              zj = zz[j & 3];
-            }
+            const float zj = zc[j];
             if (p.out.ctrl_z && live) p.out.ctrl_z[((size_t)h * N + env) * d + j] = zj;
             const double v = st.aux0[j] + st.aux1[j] * (double)zj;      // np.random.normal(means, sqrt(variances)) :234
             if (v > best) best = v, a = j;
           }
         }
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j) zc[j] = zn[j];
       } else if (KIND == K_LINUCB2 && h > 0) {   // lin_d == 2: closed-form inverse, everything in registers
         const double idet = 1.0 / (s00 * s11 - s01 * s01);
         const double i00 = s11 * idet, i01 = -s01 * idet, i11 = s00 * idet;
@@ -239,15 +284,7 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
         }
       }
       // ------------------------------------------------ env step ---------------------------
-      float z;
-      if (p.in.reward_z) {
-        z = live ? p.in.reward_z[(size_t)h * N + env] : 0.f;
-      } else if ((h & 1) == 0) {
-        const uint4 w = philox_words(p.key, gid, (uint32_t)(h >> 1), STREAM_ENV_REWARD);
-        box_muller(w.z, w.w, z, z_next);
-      } else {
-        z = z_next;
-      }
+      const float z = tile.rew[lane][(t + lane) & (OL_T - 1)];
       if (p.out.reward_z && live) p.out.reward_z[(size_t)h * N + env] = z;
       const float ma = s_means[lane][a];
       const double r = (double)ma + (0.0 + p.var * (double)z);          // envs/bandit_env.py:59
@@ -295,54 +332,50 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
       // ------------------------------------------------ outputs ----------------------------
       if (live && p.cum_means) st_stream(p.cum_means + (size_t)h * N + env, ma);   // get_arm_value :151-153
       tile.acts[lane][t] = (unsigned char)a;
-      tile.rew[lane][t] = (float)r;
+      tile.rew[lane][(t + lane) & (OL_T - 1)] = (float)r;
       creg += (double)mmax - (double)ma;
-      tile.creg[lane][t] = (float)creg;
+      tile.creg[lane][(t + lane) & (OL_T - 1)] = (float)creg;
     }
     __syncwarp();
     // ------------------------------------------------ flush 32 envs x T steps ----------------
     const int nl = min(32, N - env0w);
-    if (nl > 0 && p.regret && lane < T) {     // per-step sums over this warp's envs (evals/eval_bandit.py:169-178)
+    if (nl > 0 && p.regret) {     // per-step sums over this warp's envs (evals/eval_bandit.py:169-178); lane = step
       double s1 = 0.0, s2 = 0.0, c1 = 0.0, c2 = 0.0;
-      for (int e = 0; e < nl; ++e) {
-        const int ae = tile.acts[e][lane];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < DMAX; ++j) mx = fmaxf(mx, s_means[e][j]);
-        const double reg = (double)mx - (double)s_means[e][ae];
-        const double cr = (double)tile.creg[e][lane];
+      for (int e = 0; e < nl; ++e) {   // warp-uniform trip count: the shuffle below needs all lanes
+        const int ae = lane < T ? tile.acts[e][lane] : 0;
+        const double reg = (double)__shfl_sync(0xffffffffu, mmax, e) - (double)s_means[e][ae];
+        const double cr = (double)tile.creg[e][(lane + e) & (OL_T - 1)];
         s1 += reg, s2 += reg * reg, c1 += cr, c2 += cr * cr;
       }
-      double* dst = p.regret + 4 * (size_t)(h0 + lane);
-      atomicAdd(dst, s1), atomicAdd(dst + 1, s2), atomicAdd(dst + 2, c1), atomicAdd(dst + 3, c2);
+      double* dst = p.regret + 4 * ((size_t)((blockIdx.x * nwarps + warp) & (p.regret_reps - 1)) * H + (size_t)(h0 + lane));
+      if (lane < T) atomicAdd(dst, s1), atomicAdd(dst + 1, s2), atomicAdd(dst + 2, c1), atomicAdd(dst + 3, c2);
     }
     if (nl > 0 && materialise) {
-      for (int e = 0; e < nl; ++e)
-        if (lane < T) st_stream(p.ctx_r + (size_t)(env0w + e) * H + h0 + lane, tile.rew[e][lane]);
+      if (lane < T) {
+        size_t idx = (size_t)env0w * H + h0 + lane;
+        for (int e = 0; e < nl; ++e, idx += H) {
+          st_stream(p.ctx_r + idx, tile.rew[e][(lane + e) & (OL_T - 1)]);
+        }
+      }
       if (p.vec) {
+        // float4 q of an env's run covers flat elements 4q..4q+3 = bits [r0, r0+4) of the one-hot bit string of
+        // steps t0, t0+1 (d >= 4) or t0..t0+3 (d < 4); (t0, r0) depend on the lane only, the 4-bit pattern
+        // indexes a 16-entry float4 table: 2 byte loads + 5 integer ops + 1 table load per 16 B store
+        using mask_t = typename std::conditional<(DMAX <= 16), uint32_t, uint64_t>::type;
         const int nq = (T * d) >> 2;   // float4 per env in this flush
-        const int total = nl * nq;
-        const uint32_t magic_nq = (T == OL_T) ? p.magic_nq : (uint32_t)((0x100000000ull + (uint32_t)nq - 1) / (uint32_t)nq);
-        for (int i = lane; i < total; i += 32) {
-          const int e = (int)__umulhi((uint32_t)i, magic_nq), q = i - e * nq;
-          // elements 4q..4q+3 of this env's run span at most two steps t0, t0+1 (d >= 4) -- or more for small d
-          float v[4];
-          if (d >= 4) {
-            const int t0 = (int)__umulhi((uint32_t)(4 * q), p.magic_d);
-            const int r0 = 4 * q - t0 * d;
-            const int a0 = tile.acts[e][t0], a1 = tile.acts[e][min(t0 + 1, OL_T - 1)];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) v[c] = (r0 + c < d) ? (a0 == r0 + c ? 1.f : 0.f) : (a1 == r0 + c - d ? 1.f : 0.f);
-          } else {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int el = 4 * q + c;
-              const int t = (d == 1) ? el : (int)__umulhi((uint32_t)el, p.magic_d);
-              v[c] = (tile.acts[e][t] == el - t * d) ? 1.f : 0.f;
-            }
+        const int nsteps = (d >= 4) ? 2 : 4;
+        const size_t estride = ((size_t)H * d) >> 2;
+        float4* dst0 = reinterpret_cast<float4*>(p.ctx_a + ((size_t)env0w * H + h0) * d);
+        for (int q = lane; q < nq; q += 32) {
+          const int t0 = (d == 1) ? 4 * q : (int)__umulhi((uint32_t)(4 * q), p.magic_d);
+          const int r0 = 4 * q - t0 * d;
+          const int t1 = min(t0 + 1, OL_T - 1), t2 = min(t0 + 2, OL_T - 1), t3 = min(t0 + 3, OL_T - 1);
+          float4* dst = dst0 + q;
+          for (int e = 0; e < nl; ++e, dst += estride) {
+            mask_t M = ((mask_t)1 << tile.acts[e][t0]) | ((mask_t)1 << (d + tile.acts[e][t1]));
+            if (nsteps == 4) M |= ((mask_t)1 << (2 * d + tile.acts[e][t2])) | ((mask_t)1 << (3 * d + tile.acts[e][t3]));
+            st_stream(dst, s_nib[(uint32_t)(M >> r0) & 15u]);
           }
-          st_stream(reinterpret_cast<float4*>(p.ctx_a + ((size_t)(env0w + e) * H + h0) * d) + q,
-                    make_float4(v[0], v[1], v[2], v[3]));
         }
       } else {
         const int per = T * d;
@@ -396,17 +429,62 @@ __global__ void __launch_bounds__(256) arm_stats_kernel(const float* __restrict_
   }
 }
 
+// The regret scratch comes from the device's default stream-ordered pool; let the pool keep up to 64 MB
+// across synchronisations so that repeated calls do not go back to the driver for it.
+static void keep_pool_memory() {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_dev) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t cur = 0, want = 64ull << 20;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) == cudaSuccess && cur < want)
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &want);
+  }
+  cudaGetLastError();
+  done_dev = dev;
+}
+
+// regret[i] += sum over replicas (fixed order: the result does not depend on which replica a warp used)
+__global__ void __launch_bounds__(256) regret_reduce_kernel(const double* __restrict__ reps, int n_reps, int n, double* __restrict__ regret) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  double acc = 0.0;
+  for (int r = 0; r < n_reps; ++r) acc += reps[(size_t)r * n + i];
+  regret[i] += acc;
+}
+
 template <int DMAX, int KIND>
 static cudaError_t launch_online(const OnlineParams& p, cudaStream_t st) {
-  const size_t smem = sizeof(WarpTile) * OL_WARPS + sizeof(float) * OL_THREADS * DMAX +
-                      sizeof(double) * ((KIND == K_LINUCB || KIND == K_LINUCB2) ? p.d * p.lin_d : 0) + 16;
   auto kern = online_loop_kernel<DMAX, KIND>;
+  const size_t arms = sizeof(double) * ((KIND == K_LINUCB || KIND == K_LINUCB2) ? p.d * p.lin_d : 0);
+  // One thread per env and H sequential steps: a partly filled last wave costs a whole wave.  Pick 2 or 1
+  // warps per CTA so that the grid needs the fewest waves (ties: the larger CTA).
+  const int warps_total = (p.N + 31) / 32;
+  int best_nw = OL_WARPS;
+  long best_waves = -1;
+  for (int nw = OL_WARPS; nw >= 1; nw >>= 1) {
+    const size_t smem = ol_arms_offset(nw, DMAX) + arms;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nw * 32, smem) != cudaSuccess || per_sm < 1) {
+      cudaGetLastError();
+      continue;
+    }
+    const long grid = (warps_total + nw - 1) / nw, cap = (long)per_sm * sm_count();
+    const long waves = (grid + cap - 1) / cap;
+    if (best_waves < 0 || waves < best_waves) best_waves = waves, best_nw = nw;
+  }
+  if (best_waves < 0) return cudaErrorInvalidConfiguration;
+  const size_t smem = ol_arms_offset(best_nw, DMAX) + arms;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  const int grid = (p.N + OL_THREADS - 1) / OL_THREADS;
-  kern<<<grid, OL_THREADS, smem, st>>>(p);
+  kern<<<(warps_total + best_nw - 1) / best_nw, best_nw * 32, smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -451,10 +529,6 @@ extern "C" int dpt_online_loop(int ctrl_kind, double p0, double p1, double p2, c
   p.env_id0 = env_id0;
   p.N = N, p.H = H, p.d = d;
   p.magic_d = (uint32_t)((0x100000000ull + (uint64_t)d - 1) / (uint64_t)d);
-  {
-    const uint64_t nq = (uint64_t)OL_T * d / 4;
-    p.magic_nq = nq > 1 ? (uint32_t)((0x100000000ull + nq - 1) / nq) : 0u;
-  }
   p.ctx_s = ctx_states, p.ctx_a = ctx_actions, p.ctx_ns = ctx_next_states, p.ctx_r = ctx_rewards;
   p.cum_means = cum_means, p.regret = regret_sums;
   if (inject) p.in = *inject;
@@ -462,6 +536,24 @@ extern "C" int dpt_online_loop(int ctrl_kind, double p0, double p1, double p2, c
   p.vec = any && ((size_t)H * d) % 4 == 0 && (OL_T * d) % 4 == 0 && aligned16(ctx_actions);
   cudaError_t e;
   cudaStream_t st = (cudaStream_t)stream;
+  // Every warp adds its 32 envs' partial sums to the same [H,4] block, tile by tile and nearly in lockstep:
+  // spread them over replicated accumulators (stream-ordered scratch, <= 4 MB) and fold the replicas afterwards.
+  double* reps = nullptr;
+  p.regret_reps = 1;
+  if (regret_sums && N > 32 * 8) {
+    int r = 64;
+    while (r > 1 && (size_t)r * H * 32 > (4u << 20)) r >>= 1;
+    if (r > 1) {
+      keep_pool_memory();
+      e = cudaMallocAsync(reinterpret_cast<void**>(&reps), (size_t)r * H * 32, st);
+      if (e == cudaSuccess) e = cudaMemsetAsync(reps, 0, (size_t)r * H * 32, st);
+      if (e != cudaSuccess) {
+        set_error("dpt_online_loop: regret scratch: %s", cudaGetErrorString(e));
+        return DPT_ERR_CUDA;
+      }
+      p.regret = reps, p.regret_reps = r;
+    }
+  }
   if (d <= 5)
     e = launch_online_kind<5>(ctrl_kind, p, st);
   else if (d <= 10)
@@ -470,6 +562,13 @@ extern "C" int dpt_online_loop(int ctrl_kind, double p0, double p1, double p2, c
     e = launch_online_kind<16>(ctrl_kind, p, st);
   else
     e = launch_online_kind<32>(ctrl_kind, p, st);
+  if (reps) {
+    if (e == cudaSuccess) {
+      regret_reduce_kernel<<<(H * 4 + 255) / 256, 256, 0, st>>>(reps, p.regret_reps, H * 4, regret_sums);
+      e = cudaGetLastError();
+    }
+    cudaFreeAsync(reps, st);
+  }
   if (e != cudaSuccess) {
     set_error("dpt_online_loop launch failed: %s", cudaGetErrorString(e));
     return DPT_ERR_CUDA;
