@@ -10,7 +10,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_in
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdpt_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
 
@@ -67,7 +67,7 @@ PROTOTYPES = {
     "dpt_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "dpt_bandit_sample_means": (c_int, [c_uint64, c_uint64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dpt_bandit_opt_action": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "dpt_bandit_rollin": (c_int, [c_void_p, c_float, c_uint64, c_uint64, c_int, c_int, c_int, c_void_p, c_void_p,
+    "dpt_bandit_rollin": (c_int, [c_void_p, c_float, c_int, c_uint64, c_uint64, c_int, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, POINTER(BanditInject), POINTER(BanditDump), c_void_p]),
     "dpt_bandit_rollin_p2p": (c_int, [c_void_p, c_float, c_uint64, c_uint64, c_int, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_void_p, c_void_p]),
@@ -87,7 +87,7 @@ PROTOTYPES = {
     "dpt_gpu_bandit_step": (c_int, [c_void_p, c_void_p, c_float, c_int, c_uint64, c_uint64, c_int64, c_int, c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "dpt_arm_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "dpt_online_loop": (c_int, [c_int, c_double, c_double, c_double, c_void_p, c_void_p, c_int, c_double, c_uint64,
+    "dpt_online_loop": (c_int, [c_int, c_double, c_double, c_double, c_void_p, c_void_p, c_int, c_double, c_int, c_uint64,
                                 c_uint64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, POINTER(OnlineInject), POINTER(OnlineDump), c_void_p]),
     "dpt_debug_umma_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
@@ -100,7 +100,7 @@ PROTOTYPES = {
                                             c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_void_p]),
     "dpt_gpt2_online_kv_bytes": (c_uint64, [c_void_p, c_int, c_int, c_int]),
-    "dpt_gpt2_online_loop": (c_int, [c_void_p, c_void_p, c_double, c_int, c_uint64, c_uint64, c_int, c_int, c_int,
+    "dpt_gpt2_online_loop": (c_int, [c_void_p, c_void_p, c_double, c_int, c_int, c_uint64, c_uint64, c_int, c_int, c_int,
                                      c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      POINTER(Gpt2OnlineInject), POINTER(Gpt2OnlineDump), c_void_p]),
 }

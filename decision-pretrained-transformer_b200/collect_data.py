@@ -13,7 +13,7 @@ from . import kernels, rng
 
 
 # --------------------------------------------------------------------------- device batches ---
-def collect_bandit(n_envs, dim, horizon, var, seed=None, env_id0=0, means=None, device=None):
+def collect_bandit(n_envs, dim, horizon, var, seed=None, env_id0=0, means=None, device=None, reward_type="uniform"):
     """Task draw + rollin_bandit for ``n_envs`` envs, all on the device.  Returns a dict of fp32
     device tensors: means [N,d], opt_a_index [N], optimal_actions [N,d], context_* [N,H,.]."""
     key = rng.next_key() if seed is None else seed
@@ -22,7 +22,7 @@ def collect_bandit(n_envs, dim, horizon, var, seed=None, env_id0=0, means=None, 
     else:
         means = kernels._as(means, torch.float32, kernels._dev(device))
         opt_idx, opt_a = kernels.bandit_opt_action(means)
-    out = kernels.bandit_rollin(means, horizon, float(var), key, env_id0)
+    out = kernels.bandit_rollin(means, horizon, float(var), key, env_id0, reward_type=reward_type)
     out.update(means=means, opt_a_index=opt_idx, optimal_actions=opt_a)
     return out
 
@@ -39,7 +39,7 @@ def rollin_bandit(env, cov, orig=False):
     Returns xs (H,1) int64, us (H,d) f64, xps (H,1) int64, rs (H,) f64."""
     H = env.H_context
     out = kernels.bandit_rollin(torch.as_tensor(np.asarray(env.means)[None, :], dtype=torch.float32), H,
-                                float(env.var), rng.next_key(), 0)
+                                float(env.var), rng.next_key(), 0, reward_type=getattr(env, "type", "uniform"))
     xs = out["context_states"][0].cpu().numpy().astype(np.int64)
     us = out["context_actions"][0].cpu().numpy().astype(np.float64)
     xps = out["context_next_states"][0].cpu().numpy().astype(np.int64)
@@ -81,9 +81,12 @@ def _bandit_trajs(batch, n_samples):
 def generate_bandit_histories_from_envs(envs, n_hists, n_samples, cov, type):
     """collect_data.py:158-182, one launch per history index for all envs."""
     means = np.stack([np.asarray(e.means, dtype=np.float64) for e in envs])
+    rtypes = {getattr(e, "type", "uniform") for e in envs}       # rewards follow env.type (env.transit, :45); the
+    if len(rtypes) != 1 or len({float(e.var) for e in envs}) != 1:   # `type` argument is unused, like the reference's
+        raise NotImplementedError("generate_bandit_histories_from_envs: all envs must share var and type")
     per_hist = []
     for _ in range(n_hists):
-        b = collect_bandit(len(envs), means.shape[1], envs[0].H_context, envs[0].var, means=means)
+        b = collect_bandit(len(envs), means.shape[1], envs[0].H_context, envs[0].var, means=means, reward_type=next(iter(rtypes)))
         per_hist.append(_bandit_trajs(b, n_samples))
     trajs = []
     for i in range(len(envs)):           # env-major, then history, then sample -- the reference's order
@@ -98,8 +101,8 @@ def generate_bandit_histories_from_envs(envs, n_hists, n_samples, cov, type):
 def generate_bandit_histories(n_envs, dim, horizon, var, **kwargs):
     """collect_data.py:221-225.  Task draw and rollouts happen on the device."""
     n_hists, n_samples = kwargs.get("n_hists", 1), kwargs.get("n_samples", 1)
-    if kwargs.get("type", "uniform") != "uniform":
-        raise NotImplementedError
+    # the reference draws its envs with bandit_env.sample(dim, horizon, var) -- always type 'uniform' -- and never
+    # reads kwargs['type'] (collect_data.py:158-182, 221-225); so do we
     key = rng.next_key()
     means, opt_idx, opt_a = kernels.bandit_sample_means(n_envs, dim, key, 0)
     per_hist = []

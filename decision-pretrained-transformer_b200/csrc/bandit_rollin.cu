@@ -31,6 +31,7 @@ enum { MODE_PHILOX = 0, MODE_PHILOX_DUMP = 1, MODE_INJECT = 2 };
 struct RollinParams {
   const float* means;
   float var;
+  int rtype;  // DPT_REWARD_*
   Key key;
   uint64_t env_id0;
   int N, H, d, envs_per_cta;
@@ -187,7 +188,7 @@ __device__ __forceinline__ int argmax_first(const float* m, int D) {
 // ---------------------------------------------------------------------------------------------
 // Fast path: compile-time d (2d <= 32), H % 4 == 0, 16 B-aligned outputs.
 // ---------------------------------------------------------------------------------------------
-template <int D, int MODE>
+template <int D, int MODE, int RT>   // RT: DPT_REWARD_* (compile-time: the kernel sits at the issue / HBM balance point)
 __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_fast(const RollinParams p) {
   using thr_t = typename Thr<MODE>::type;
   __shared__ float s_means[RB_MAX_ENVS][D];
@@ -234,7 +235,10 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_fast(const RollinPar
         a0 += (k0 >= t);
         a1 += (k1 >= t);
       }
-      box_muller(w.z, w.w, z0, z1);
+      if (RT == DPT_REWARD_GAUSSIAN)
+        box_muller(w.z, w.w, z0, z1);
+      else
+        z0 = u24(w.z), z1 = u24(w.w);
       if (MODE == MODE_PHILOX_DUMP && h0 < H) {
         if (p.out.u) {
           p.out.u[row] = (double)k0 * 4.656612873077392578125e-10;
@@ -261,8 +265,10 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_fast(const RollinPar
     }
     // r = means[a] + var * z   (envs/bandit_env.py:59)
     {
-      const float r0 = fmaf(p.var, z0, s_means[e][a0]);
-      const float r1 = fmaf(p.var, z1, s_means[e][a1]);
+      const float m0 = s_means[e][a0], m1 = s_means[e][a1];
+      const bool gauss = RT == DPT_REWARD_GAUSSIAN;   // else Bernoulli(mean): envs/bandit_env.py:61
+      const float r0 = gauss ? fmaf(p.var, z0, m0) : (z0 < m0 ? 1.f : 0.f);
+      const float r1 = gauss ? fmaf(p.var, z1, m1) : (z1 < m1 ? 1.f : 0.f);
       st_stream_if(h0 < H, reinterpret_cast<float2*>(p.ctx_r + row), make_float2(r0, r1));
       if (p.stats && h0 < H) {
         const float2 rr = make_float2(r0, r1);
@@ -332,9 +338,13 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_generic(const Rollin
       const uint4 w = philox_words(p.key, p.env_id0 + (uint64_t)env, (uint32_t)(h >> 1), STREAM_ROLLIN_STEP);
       const uint32_t k = ((h & 1) ? w.y : w.x) >> 1;
       for (int j = 0; j < D - 1; ++j) a += (k >= s_thr[e][j]);
-      float z0, z1;
-      box_muller(w.z, w.w, z0, z1);
-      z = (h & 1) ? z1 : z0;
+      if (p.rtype == DPT_REWARD_GAUSSIAN) {
+        float z0, z1;
+        box_muller(w.z, w.w, z0, z1);
+        z = (h & 1) ? z1 : z0;
+      } else {
+        z = u24((h & 1) ? w.w : w.z);
+      }
       if (MODE == MODE_PHILOX_DUMP && h < H) {
         if (p.out.u) p.out.u[row] = (double)k * 4.656612873077392578125e-10;
         if (p.out.z) p.out.z[row] = z;
@@ -350,7 +360,8 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_generic(const Rollin
       z = p.in.z[row];
     }
     if (h < H) {
-      const float r = fmaf(p.var, z, s_means[e][a]);
+      const float ma = s_means[e][a];
+      const float r = p.rtype == DPT_REWARD_GAUSSIAN ? fmaf(p.var, z, ma) : (z < ma ? 1.f : 0.f);
       st_stream(p.ctx_r + row, r);
       if (p.stats) st_r += r, st_r2 = fmaf(r, r, st_r2), st_opt += (float)(a == s_opt[e]);
     }
@@ -379,9 +390,12 @@ static void launch_mode(RollinParams p, bool fast, cudaStream_t st) {
   };
   if (fast) {
     switch (p.d) {
-#define DPT_CASE(DD)                        \
-  case DD:                                  \
-    go(bandit_rollin_fast<DD, MODE>);       \
+#define DPT_CASE(DD)                                                   \
+  case DD:                                                             \
+    if (p.rtype == DPT_REWARD_GAUSSIAN)                                \
+      go(bandit_rollin_fast<DD, MODE, DPT_REWARD_GAUSSIAN>);           \
+    else                                                               \
+      go(bandit_rollin_fast<DD, MODE, DPT_REWARD_BERNOULLI>);          \
     return;
       DPT_CASE(2)
       DPT_CASE(3)
@@ -411,11 +425,13 @@ static int resident_ctas(K kern) {
 
 using namespace dpt;
 
-static int bandit_rollin_impl(const float* means, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
+static int bandit_rollin_impl(const float* means, float var, int reward_type, uint64_t seed, uint64_t env_id0, int N, int H, int d,
                               float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
                               double* return_stats, const dpt_bandit_inject_t* inject, const dpt_bandit_dump_t* dump,
                               double* const* peer_dst, int n_peers, unsigned int* done_counter, void* stream) {
   DPT_CHECK_ARG(N >= 0 && H >= 0, "dpt_bandit_rollin: N=%d H=%d must be >= 0", N, H);
+  DPT_CHECK_ARG(reward_type == DPT_REWARD_GAUSSIAN || reward_type == DPT_REWARD_BERNOULLI,
+                "dpt_bandit_rollin: unknown reward_type %d (0 uniform/gaussian, 1 bernoulli)", reward_type);
   DPT_CHECK_ARG(d >= 1 && d <= RB_MAX_D, "dpt_bandit_rollin: d=%d outside [1,%d]", d, RB_MAX_D);
   if (N == 0 || H == 0) return DPT_OK;
   DPT_CHECK_ARG(means && ctx_states && ctx_actions && ctx_next_states && ctx_rewards,
@@ -423,6 +439,7 @@ static int bandit_rollin_impl(const float* means, float var, uint64_t seed, uint
   RollinParams p{};
   p.means = means;
   p.var = var;
+  p.rtype = reward_type;
   p.key = Key{(uint32_t)seed, (uint32_t)(seed >> 32)};
   p.env_id0 = env_id0;
   p.N = N, p.H = H, p.d = d;
@@ -460,12 +477,12 @@ static int bandit_rollin_impl(const float* means, float var, uint64_t seed, uint
   return DPT_OK;
 }
 
-extern "C" int dpt_bandit_rollin(const float* means, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
+extern "C" int dpt_bandit_rollin(const float* means, float var, int reward_type, uint64_t seed, uint64_t env_id0, int N, int H, int d,
                                  float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
                                  double* return_stats, const dpt_bandit_inject_t* inject,
                                  const dpt_bandit_dump_t* dump, void* stream) {
-  return bandit_rollin_impl(means, var, seed, env_id0, N, H, d, ctx_states, ctx_actions, ctx_next_states, ctx_rewards,
-                            return_stats, inject, dump, nullptr, 0, nullptr, stream);
+  return bandit_rollin_impl(means, var, reward_type, seed, env_id0, N, H, d, ctx_states, ctx_actions, ctx_next_states,
+                            ctx_rewards, return_stats, inject, dump, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int dpt_bandit_rollin_p2p(const float* means, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
@@ -473,8 +490,9 @@ extern "C" int dpt_bandit_rollin_p2p(const float* means, float var, uint64_t see
                                      double* return_stats, double* const* peer_dst, int n_peers,
                                      unsigned int* done_counter, void* stream) {
   DPT_CHECK_ARG(N > 0 && H > 0, "dpt_bandit_rollin_p2p: empty shard (N=%d, H=%d) cannot signal its peers", N, H);
-  return bandit_rollin_impl(means, var, seed, env_id0, N, H, d, ctx_states, ctx_actions, ctx_next_states, ctx_rewards,
-                            return_stats, nullptr, nullptr, peer_dst, n_peers, done_counter, stream);
+  return bandit_rollin_impl(means, var, DPT_REWARD_GAUSSIAN, seed, env_id0, N, H, d, ctx_states, ctx_actions,
+                            ctx_next_states, ctx_rewards, return_stats, nullptr, nullptr, peer_dst, n_peers, done_counter,
+                            stream);
 }
 
 // ---- peer-memory plumbing: buffers that other ranks' kernels can store into over NVLink ----

@@ -407,6 +407,7 @@ struct OnlineGptParams {
   Gpt2Dev m;
   const float* means;
   double var;
+  int rtype;   // DPT_REWARD_*
   int sample;
   Key key;
   uint64_t env_id0;
@@ -485,12 +486,16 @@ __global__ void __launch_bounds__(G_THREADS) gpt2_online_kernel(const OnlineGptP
       z = p.in.reward_z[(size_t)h * N + env];
     } else if ((h & 1) == 0) {
       const uint4 w = philox_words(p.key, gid, (uint32_t)(h >> 1), STREAM_ENV_REWARD);
-      box_muller(w.z, w.w, z, z_next);
+      if (p.rtype == DPT_REWARD_GAUSSIAN)
+        box_muller(w.z, w.w, z, z_next);
+      else
+        z = u24(w.z), z_next = u24(w.w);
     } else {
       z = z_next;
     }
     const float ma = __shfl_sync(0xffffffffu, mean_l, a);
-    const float r = (float)((double)ma + (0.0 + p.var * (double)z));   // envs/bandit_env.py:59
+    const float r = p.rtype == DPT_REWARD_GAUSSIAN ? (float)((double)ma + (0.0 + p.var * (double)z))   // envs/bandit_env.py:59
+                                                   : (z < ma ? 1.f : 0.f);                             // :61 Bernoulli(mean)
     if (lane == 0) {
       if (p.out.reward_z) p.out.reward_z[(size_t)h * N + env] = z;
       if (p.cum_means) p.cum_means[(size_t)h * N + env] = ma;
@@ -661,12 +666,14 @@ extern "C" uint64_t dpt_gpt2_online_kv_bytes(const dpt_gpt2_t* m, int N, int H, 
   return (uint64_t)N * m->dev.L * 2 * G_E * tpad_for(H, precision) * (precision ? 2 : 4);
 }
 
-extern "C" int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, double var, int sample, uint64_t seed,
+extern "C" int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, double var, int reward_type, int sample, uint64_t seed,
                                     uint64_t env_id0, int N, int H, int precision, void* kv_cache, uint64_t kv_bytes,
                                     float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
                                     float* cum_means, double* regret_sums, const dpt_gpt2_online_inject_t* inject,
                                     const dpt_gpt2_online_dump_t* dump, void* stream) {
   DPT_CHECK_ARG(m, "dpt_gpt2_online_loop: null model");
+  DPT_CHECK_ARG(reward_type == DPT_REWARD_GAUSSIAN || reward_type == DPT_REWARD_BERNOULLI,
+                "dpt_gpt2_online_loop: unknown reward_type %d (0 uniform/gaussian, 1 bernoulli)", reward_type);
   DPT_CHECK_ARG(precision == 0 || precision == 1, "dpt_gpt2_online_loop: precision %d (0 = fp32, 1 = bf16 K/V cache)", precision);
   DPT_CHECK_ARG(m->dev.dx == 1, "dpt_gpt2_online_loop: bandit loop needs state_dim == 1 (got %d)", m->dev.dx);
   DPT_CHECK_ARG(N >= 0 && H >= 0, "dpt_gpt2_online_loop: N=%d H=%d", N, H);
@@ -678,7 +685,7 @@ extern "C" int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, double va
                 "dpt_gpt2_online_loop: context pointers must be all NULL or all non-NULL");
   OnlineGptParams p{};
   p.m = m->dev;
-  p.means = means, p.var = var, p.sample = sample;
+  p.means = means, p.var = var, p.rtype = reward_type, p.sample = sample;
   p.key = Key{(uint32_t)seed, (uint32_t)(seed >> 32)};
   p.env_id0 = env_id0;
   p.N = N, p.H = H, p.Tpad = tpad_for(H, precision);

@@ -75,7 +75,7 @@ extern "C" int dpt_bandit_rollin_host(const float* means_host, float var, uint64
     float* buf = reinterpret_cast<float*>(scratch) + (size_t)b * L.total;
     if (k >= 2) cudaStreamWaitEvent(cs, freed[b], 0);  // buffer b's previous D2H has drained
     cudaMemcpyAsync(buf + L.means, means_host + (size_t)e0 * d, sizeof(float) * n * d, cudaMemcpyHostToDevice, cs);
-    rc = dpt_bandit_rollin(buf + L.means, var, seed, env_id0 + (uint64_t)e0, n, H, d, buf + L.s, buf + L.a,
+    rc = dpt_bandit_rollin(buf + L.means, var, DPT_REWARD_GAUSSIAN, seed, env_id0 + (uint64_t)e0, n, H, d, buf + L.s, buf + L.a,
                            buf + L.ns, buf + L.r, nullptr, nullptr, nullptr, cs);
     if (rc != DPT_OK) break;
     cudaEventRecord(done[b], cs);

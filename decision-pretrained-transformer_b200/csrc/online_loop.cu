@@ -38,6 +38,7 @@ struct OnlineParams {
   Key key;
   uint64_t env_id0;
   int N, H, d;
+  int rtype;         // DPT_REWARD_*
   uint32_t magic_d;  // ceil(2^32 / d): floor(x / d) == umulhi(x, magic_d) for the small x used here
   float *ctx_s, *ctx_a, *ctx_ns, *ctx_r, *cum_means;
   double* regret;    // [regret_reps][H][4] accumulators (replicated to spread same-address atomics)
@@ -197,7 +198,10 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
       for (int t = 0; t < T; t += 2) {
         const uint4 w = philox_words(p.key, gid, (uint32_t)((h0 + t) >> 1), STREAM_ENV_REWARD);
         float z0, z1;
-        box_muller(w.z, w.w, z0, z1);
+        if (p.rtype == DPT_REWARD_GAUSSIAN)
+          box_muller(w.z, w.w, z0, z1);
+        else
+          z0 = u24(w.z), z1 = u24(w.w);
         tile.rew[lane][(t + lane) & (OL_T - 1)] = z0;
         tile.rew[lane][(t + 1 + lane) & (OL_T - 1)] = z1;
       }
@@ -287,7 +291,8 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
       const float z = tile.rew[lane][(t + lane) & (OL_T - 1)];
       if (p.out.reward_z && live) p.out.reward_z[(size_t)h * N + env] = z;
       const float ma = s_means[lane][a];
-      const double r = (double)ma + (0.0 + p.var * (double)z);          // envs/bandit_env.py:59
+      const double r = p.rtype == DPT_REWARD_GAUSSIAN ? (double)ma + (0.0 + p.var * (double)z)   // envs/bandit_env.py:59
+                                                      : (z < ma ? 1.0 : 0.0);                    // :61 Bernoulli(mean)
       // ------------------------------------------------ controller statistics --------------
       if (KIND == K_EMP || KIND == K_UCB || KIND == K_THOMPSON) {
         // gather the pulled arm's (sum, count) with selects, update once, scatter back with selects:
@@ -505,12 +510,14 @@ static cudaError_t launch_online_kind(int kind, const OnlineParams& p, cudaStrea
 using namespace dpt;
 
 extern "C" int dpt_online_loop(int ctrl_kind, double p0, double p1, double p2, const float* means, const double* arms,
-                               int lin_d, double var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
+                               int lin_d, double var, int reward_type, uint64_t seed, uint64_t env_id0, int N, int H, int d,
                                float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
                                float* cum_means, double* regret_sums, const dpt_online_inject_t* inject,
                                const dpt_online_dump_t* dump, void* stream) {
   DPT_CHECK_ARG(ctrl_kind >= K_OPT && ctrl_kind <= K_LINUCB, "dpt_online_loop: unknown controller kind %d", ctrl_kind);
   DPT_CHECK_ARG(N >= 0 && H >= 0, "dpt_online_loop: N=%d H=%d must be >= 0", N, H);
+  DPT_CHECK_ARG(reward_type == DPT_REWARD_GAUSSIAN || reward_type == DPT_REWARD_BERNOULLI,
+                "dpt_online_loop: unknown reward_type %d (0 uniform/gaussian, 1 bernoulli)", reward_type);
   DPT_CHECK_ARG(d >= 1 && d <= 32, "dpt_online_loop: d=%d outside [1,32]", d);
   if (N == 0 || H == 0) return DPT_OK;
   DPT_CHECK_ARG(means, "dpt_online_loop: null means");
@@ -528,6 +535,7 @@ extern "C" int dpt_online_loop(int ctrl_kind, double p0, double p1, double p2, c
   p.key = Key{(uint32_t)seed, (uint32_t)(seed >> 32)};
   p.env_id0 = env_id0;
   p.N = N, p.H = H, p.d = d;
+  p.rtype = reward_type;
   p.magic_d = (uint32_t)((0x100000000ull + (uint64_t)d - 1) / (uint64_t)d);
   p.ctx_s = ctx_states, p.ctx_a = ctx_actions, p.ctx_ns = ctx_next_states, p.ctx_r = ctx_rewards;
   p.cum_means = cum_means, p.regret = regret_sums;

@@ -327,5 +327,6 @@ class BanditTransformerController(Controller):
             return None
         return dict(kind="transformer")
 
-    def fused_online_loop(self, means, horizon, var, key, env_id0, include_meta, regret, inject, dump):
-        return self.model.online_loop(means, horizon, var, self.sample, key, env_id0, include_meta, regret, inject, dump)
+    def fused_online_loop(self, means, horizon, var, key, env_id0, include_meta, regret, inject, dump, reward_type="uniform"):
+        return self.model.online_loop(means, horizon, var, self.sample, key, env_id0, include_meta, regret, inject, dump,
+                                      reward_type)

@@ -20,7 +20,7 @@ from ..envs.bandit_env import BanditEnv, BanditEnvVec
 def _fusable(vec_env, controller):
     if not isinstance(vec_env, BanditEnvVec) or not callable(getattr(controller, "fused_spec", None)):
         return None
-    if len({float(e.var) for e in vec_env.envs}) != 1 or any(e.type != "uniform" for e in vec_env.envs):
+    if len({float(e.var) for e in vec_env.envs}) != 1 or len({e.type for e in vec_env.envs}) != 1:
         return None
     return controller.fused_spec()
 
@@ -32,12 +32,13 @@ def deploy_online_vec_device(vec_env, controller, horizon, include_meta=False, r
     if spec is None:
         raise NotImplementedError("controller / env pair has no fused path")
     key = rng.next_key() if seed is None else seed
-    var = float(vec_env.envs[0].var)
+    var, rtype = float(vec_env.envs[0].var), vec_env.envs[0].type
     if spec["kind"] == "transformer":
-        return controller.fused_online_loop(vec_env.means, horizon, var, key, env_id0, include_meta, regret, inject, dump)
+        return controller.fused_online_loop(vec_env.means, horizon, var, key, env_id0, include_meta, regret, inject, dump,
+                                            rtype)
     return kernels.online_loop(spec["kind"], vec_env.means, horizon, var, key, env_id0, spec.get("p0", 0.0),
                                spec.get("p1", 0.0), spec.get("p2", 0.0), spec.get("arms"), include_meta, regret,
-                               inject, dump)
+                               inject, dump, rtype)
 
 
 def deploy_online_vec(vec_env, controller, horizon, include_meta=False):

@@ -54,12 +54,17 @@ def bandit_opt_action(means):
 
 
 # ------------------------------------------------------------------ rollin_bandit --------------
-def bandit_rollin(means, H, var, seed, env_id0=0, inject=None, dump=False, out=None, stats=None, peer=None, peer_slot=0):
+REWARD_TYPES = {"uniform": 0, "bernoulli": 1}   # envs/bandit_env.py:10-16 type names -> DPT_REWARD_*
+
+
+def bandit_rollin(means, H, var, seed, env_id0=0, inject=None, dump=False, out=None, stats=None, peer=None, peer_slot=0,
+                  reward_type="uniform"):
     """Fused rollin_bandit for all envs (collect_data.py:23-53).  ``means`` [N,d] fp32 device tensor.
 
     inject: dict with 'z' [N,H] and either 'actions' [N,H] or ('cov_idx' [N], 'dir_probs' [N,d] f64,
     'rand_idx' [N], 'u' [N,H] f64).  dump=True additionally returns the noise that was used.
     stats: optional f64 [3] device tensor, += (sum r, sum r^2, #optimal-arm pulls).
+    reward_type: 'uniform' (r = mean + var z) or 'bernoulli' (r = [u < mean]; the 'z' noise arrays then hold u).
     peer: optional dist.PeerGather -- the launch then also stores this rank's three totals into slot
     ``peer_slot`` of every rank's gather buffer over NVLink (``stats`` must be zero before the launch).
     Returns dict: context_states [N,H,1], context_actions [N,H,d], context_next_states [N,H,1],
@@ -94,13 +99,13 @@ def bandit_rollin(means, H, var, seed, env_id0=0, inject=None, dump=False, out=N
             setattr(s2, k, ptr(t))
         dump_p = ctypes.byref(s2)
     if peer is not None:
-        assert inject is None and not dump and stats is not None
+        assert inject is None and not dump and stats is not None and reward_type == "uniform"
         check(lib().dpt_bandit_rollin_p2p(ptr(means), var, seed, env_id0, N, H, d, ptr(out["context_states"]),
                                           ptr(out["context_actions"]), ptr(out["context_next_states"]),
                                           ptr(out["context_rewards"]), ptr(stats), peer.dst_array(peer_slot), peer.world,
                                           peer.counter_ptr, stream_ptr()), "dpt_bandit_rollin_p2p")
         return out
-    check(lib().dpt_bandit_rollin(ptr(means), var, seed, env_id0, N, H, d, ptr(out["context_states"]),
+    check(lib().dpt_bandit_rollin(ptr(means), var, REWARD_TYPES[reward_type], seed, env_id0, N, H, d, ptr(out["context_states"]),
                                   ptr(out["context_actions"]), ptr(out["context_next_states"]),
                                   ptr(out["context_rewards"]), ptr(stats), inj_p, dump_p, stream_ptr()), "dpt_bandit_rollin")
     if noise is not None:
@@ -232,7 +237,7 @@ def arm_stats(ctx_actions, ctx_rewards, h=None):
 
 
 def online_loop(kind, means, H, var, seed, env_id0=0, p0=0.0, p1=0.0, p2=0.0, arms=None, materialise=True,
-                regret=True, inject=None, dump=False):
+                regret=True, inject=None, dump=False, reward_type="uniform"):
     """Fused deploy_online_vec for a classical controller (evals/eval_bandit.py:56-103).
 
     Returns dict: cum_means [H,N] fp32, regret_sums [H,4] f64 (sums over envs of reg, reg^2, cumreg, cumreg^2 with
@@ -272,7 +277,8 @@ def online_loop(kind, means, H, var, seed, env_id0=0, p0=0.0, p1=0.0, p2=0.0, ar
         for k, t in noise.items():
             setattr(s2, k, ptr(t))
         dump_p = ctypes.byref(s2)
-    check(lib().dpt_online_loop(CTRL_KINDS[kind], p0, p1, p2, ptr(means), ptr(arms_t), lin_d, float(var), seed, env_id0,
+    check(lib().dpt_online_loop(CTRL_KINDS[kind], p0, p1, p2, ptr(means), ptr(arms_t), lin_d, float(var), REWARD_TYPES[reward_type], seed,
+                                env_id0,
                                 N, H, d, ptr(out.get("context_states")), ptr(out.get("context_actions")),
                                 ptr(out.get("context_next_states")), ptr(out.get("context_rewards")),
                                 ptr(out["cum_means"]), ptr(out.get("regret_sums")), inj_p, dump_p, stream_ptr()),

@@ -182,7 +182,7 @@ class Transformer(nn.Module):
     # ---- fused in-context evaluation loop ---------------------------------------------------
     @torch.no_grad()
     def online_loop(self, means, horizon, var, sample, seed, env_id0=0, materialise=True, regret=True, inject=None,
-                    dump=False):
+                    dump=False, reward_type="uniform"):
         """deploy_online_vec with BanditTransformerController in one launch (KV-cached decode +
         sampling + env step).  Returns the same dict as kernels.online_loop."""
         dev = kernels._dev()
@@ -219,7 +219,7 @@ class Transformer(nn.Module):
             for k, t in noise.items():
                 setattr(s2, k, ptr(t))
             dump_p = ctypes.byref(s2)
-        check(lib().dpt_gpt2_online_loop(h, ptr(means), float(var), 1 if sample else 0, seed, env_id0, N, H, self.precision, ptr(kv),
+        check(lib().dpt_gpt2_online_loop(h, ptr(means), float(var), kernels.REWARD_TYPES[reward_type], 1 if sample else 0, seed, env_id0, N, H, self.precision, ptr(kv),
                                          kv.numel(), ptr(out.get("context_states")), ptr(out.get("context_actions")),
                                          ptr(out.get("context_next_states")), ptr(out.get("context_rewards")),
                                          ptr(out["cum_means"]), ptr(out.get("regret_sums")), inj_p, dump_p, stream_ptr()),

@@ -35,7 +35,13 @@ extern "C" {
 #define DPT_ERR_CUDA (-2)
 #define DPT_ERR_UNSUPPORTED (-3)
 
-#define DPT_ABI_VERSION 1
+#define DPT_ABI_VERSION 2
+
+/* reward_type of the bandit entry points (envs/bandit_env.py:56-63, envs/gpu_bandit_env.py:53-63):
+ * 0 'uniform'  : r = means[a] + var * z, z ~ N(0,1);
+ * 1 'bernoulli': r = (u < means[a]) ? 1 : 0, u ~ U[0,1) (24 bits); injected / dumped `z` arrays then hold u. */
+#define DPT_REWARD_GAUSSIAN 0
+#define DPT_REWARD_BERNOULLI 1
 #define DPT_MAX_PEERS 16
 
 int dpt_version(void);
@@ -77,7 +83,7 @@ typedef struct {
   float* z;
 } dpt_bandit_dump_t;
 
-int dpt_bandit_rollin(const float* means, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
+int dpt_bandit_rollin(const float* means, float var, int reward_type, uint64_t seed, uint64_t env_id0, int N, int H, int d,
                       float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
                       double* return_stats, const dpt_bandit_inject_t* inject, const dpt_bandit_dump_t* dump,
                       void* stream);
@@ -193,7 +199,8 @@ typedef struct {
 } dpt_online_dump_t;
 
 int dpt_online_loop(int ctrl_kind, double p0, double p1, double p2, const float* means, const double* arms,
-                    int lin_d, double var, uint64_t seed, uint64_t env_id0, int N, int H, int d, float* ctx_states,
+                    int lin_d, double var, int reward_type, uint64_t seed, uint64_t env_id0, int N, int H, int d,
+                    float* ctx_states,
                     float* ctx_actions, float* ctx_next_states, float* ctx_rewards, float* cum_means,
                     double* regret_sums, const dpt_online_inject_t* inject, const dpt_online_dump_t* dump,
                     void* stream);
@@ -265,7 +272,8 @@ typedef struct {
 } dpt_gpt2_online_dump_t;
 
 uint64_t dpt_gpt2_online_kv_bytes(const dpt_gpt2_t* m, int N, int H, int precision);
-int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, double var, int sample, uint64_t seed, uint64_t env_id0,
+int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, double var, int reward_type, int sample, uint64_t seed,
+                         uint64_t env_id0,
                          int N, int H, int precision, void* kv_cache, uint64_t kv_bytes, float* ctx_states,
                          float* ctx_actions, float* ctx_next_states, float* ctx_rewards, float* cum_means,
                          double* regret_sums, const dpt_gpt2_online_inject_t* inject,

@@ -141,10 +141,13 @@ def rollin_bandit(means, H, var, noise):
     return xs, us, xs.copy(), rs
 
 
-def rollin_bandit_batch(means, var, cov_idx, dir_probs, rand_idx, u, z):
+def rollin_bandit_batch(means, var, cov_idx, dir_probs, rand_idx, u, z, reward_type="uniform"):
     """Vectorised form of ``rollin_bandit`` over N envs with explicit noise arrays
     (same float64 operations per element, so bit-identical to the loop form).
-    means [N,d], cov_idx [N], dir_probs [N,d], rand_idx [N], u [N,H], z [N,H]."""
+    means [N,d], cov_idx [N], dir_probs [N,d], rand_idx [N], u [N,H], z [N,H].
+    reward_type 'bernoulli' (envs/bandit_env.py:60-61): r ~ Bernoulli(means[a]) drawn as [z < means[a]] with z
+    a uniform in [0,1) -- torch.bernoulli's rule (envs/gpu_bandit_env.py:60); np.random.binomial maps its uniform
+    differently, so for this type parity with the reference is distributional, exact only on the device's own u."""
     means = np.asarray(means, dtype=np.float64)
     N, d = means.shape
     cov = np.asarray(COV_GRID)[np.asarray(cov_idx)][:, None]
@@ -157,7 +160,11 @@ def rollin_bandit_batch(means, var, cov_idx, dir_probs, rand_idx, u, z):
     acts = (cdf[:, None, :] <= u[:, :, None]).sum(-1)          # searchsorted(side='right')
     us = np.zeros((N, u.shape[1], d))
     np.put_along_axis(us, acts[:, :, None], 1.0, axis=2)
-    rs = np.take_along_axis(means, acts, axis=1) + (0.0 + var * np.asarray(z, dtype=np.float64))
+    ma = np.take_along_axis(means, acts, axis=1)
+    if reward_type == "bernoulli":
+        rs = (np.asarray(z, dtype=np.float64) < ma).astype(np.float64)
+    else:
+        rs = ma + (0.0 + var * np.asarray(z, dtype=np.float64))
     xs = np.ones((N, u.shape[1], 1), dtype=np.int64)
     return xs, us, xs.copy(), rs, acts
 
@@ -432,7 +439,7 @@ class TransformerCtrl:
         return a
 
 
-def deploy_online_vec(means, var, H, ctrl, noise, include_meta=True):
+def deploy_online_vec(means, var, H, ctrl, noise, include_meta=True, reward_type="uniform"):
     """evals/eval_bandit.py:56-103 driving envs/bandit_env.py:125-149 (BanditEnvVec.deploy,
     one step per call because BanditEnv.H == 1) and :98-105/:56-64 (step/transit).
 
@@ -451,7 +458,10 @@ def deploy_online_vec(means, var, H, ctrl, noise, include_meta=True):
             u = ctrl.act(ctx_a[:, :h], ctx_r[:, :h, 0], noise, h)
         a = np.argmax(u, axis=-1)
         z = noise.gauss((N,), "reward_z")                      # N x np.random.normal(0, var) in env order
-        r = means[np.arange(N), a] + (0.0 + var * z)
+        if reward_type == "bernoulli":                          # bandit_env.py:60-61; z is then a U[0,1) draw
+            r = (z < means[np.arange(N), a]).astype(np.float64)
+        else:
+            r = means[np.arange(N), a] + (0.0 + var * z)
         ctx_s[:, h, 0] = 1
         ctx_a[:, h] = u
         ctx_ns[:, h, 0] = 1

@@ -29,13 +29,15 @@ def test_header_symbols_exported(dpt):
 
 def test_invalid_args_report_errors(dpt):
     lib = dpt._lib.lib()
-    rc = lib.dpt_bandit_rollin(None, 0.3, 0, 0, 4, 8, 99, None, None, None, None, None, None, None, None)
+    rc = lib.dpt_bandit_rollin(None, 0.3, 0, 0, 0, 4, 8, 99, None, None, None, None, None, None, None, None)
     assert rc == dpt._lib.ERR_INVALID_ARG and b"d=99" in lib.dpt_last_error()
+    rc = lib.dpt_bandit_rollin(None, 0.3, 7, 0, 0, 4, 8, 5, None, None, None, None, None, None, None, None)
+    assert rc == dpt._lib.ERR_INVALID_ARG and b"reward_type" in lib.dpt_last_error()
     rc = lib.dpt_darkroom_rollin(None, None, 10, 7, 0, 0, 4, 8, 1, None, None, None, None, None, None, None, None, None)
     assert rc == dpt._lib.ERR_INVALID_ARG and b"mode" in lib.dpt_last_error()
     with pytest.raises(ValueError):
         dpt._lib.check(rc, "dpt_darkroom_rollin")
-    assert lib.dpt_bandit_rollin(None, 0.3, 0, 0, 0, 8, 5, None, None, None, None, None, None, None, None) == 0  # empty batch
+    assert lib.dpt_bandit_rollin(None, 0.3, 0, 0, 0, 0, 8, 5, None, None, None, None, None, None, None, None) == 0  # empty batch
 
 
 def test_no_cpu_fallback(dpt):

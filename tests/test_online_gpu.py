@@ -298,3 +298,38 @@ def test_regret_curves_statistical_parity(dpt, kind):
     tolc = 5 * np.sqrt(gpu["regret_sem"] ** 2 + cs ** 2) + 1e-3
     assert np.all(np.abs(gpu["regret_mean"] - cm) <= tolc)
     assert gpu["regret_mean"][-1] > 0.5 and gpu["mean"][-1] < gpu["mean"][d]      # it learns: late regret below early regret
+
+
+@pytest.mark.parametrize("kind", ["emp", "ucb", "thompson"])
+def test_online_loop_bernoulli(dpt, kind):
+    """Bernoulli envs (eval.py 'bandit_bernoulli'): the fused loop draws r = [u < means[a]]; replaying the dumped
+    uniforms through the oracle's controllers gives the same arms and rewards."""
+    N, d, H, var, seed = 150, 5, 48, 0.3, 11
+    means, _, _ = dpt.kernels.bandit_sample_means(N, d, seed, 0)
+    m64 = _np(means).astype(np.float64)
+    par = {"emp": dict(p0=1.0), "ucb": dict(p0=1.0), "thompson": dict(p0=var, p1=0.5, p2=1 / 12.0)}[kind]
+    out = dpt.kernels.online_loop(kind, means, H, var, seed, 0, dump=True, reward_type="bernoulli", **par)
+    nz = {k: _np(v).astype(np.float64) for k, v in out["noise"].items()}
+    assert nz["reward_z"].min() >= 0.0 and nz["reward_z"].max() < 1.0
+    ctrl = {"emp": lambda: O.EmpMeanCtrl(d, online=True), "ucb": lambda: O.UCBCtrl(d, 1.0),
+            "thompson": lambda: O.ThompsonCtrl(d, std=var, sample=True, prior_mean=.5, prior_var=1 / 12.0)}[kind]()
+    arrays = {"reward_z": nz["reward_z"]}
+    if kind == "thompson":
+        arrays["thompson_z"] = nz["ctrl_z"]
+    cum, meta = O.deploy_online_vec(m64, var, H, ctrl, O.ReplayNoise(arrays), reward_type="bernoulli")
+    assert np.array_equal(_np(out["context_actions"]).astype(np.float64), meta["context_actions"])
+    assert np.array_equal(_np(out["context_rewards"]).astype(np.float64), meta["context_rewards"])
+    _close(_np(out["cum_means"]), cum)
+
+
+def test_deploy_online_vec_bernoulli_envs_fused(dpt):
+    """deploy_online_vec on a BanditEnvVec of bernoulli envs takes the fused path and returns {0,1} rewards."""
+    from dpt_b200.envs.bandit_env import BanditEnvVec, sample
+    from dpt_b200.ctrls.ctrl_bandit import UCBPolicy
+    from dpt_b200.evals.eval_bandit import deploy_online_vec
+    dpt.seed(3)
+    envs = [sample(5, 40, 0.3, type="bernoulli") for _ in range(64)]
+    vec = BanditEnvVec(envs)
+    cum, meta = deploy_online_vec(vec, UCBPolicy(envs[0], const=1.0, batch_size=64), 40, include_meta=True)
+    assert cum.shape == (40, 64) and set(np.unique(meta["context_rewards"])) <= {0.0, 1.0}
+    assert meta["context_actions"].sum(-1).min() == 1.0

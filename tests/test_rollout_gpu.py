@@ -381,3 +381,50 @@ def test_bandit_rollin_fused_peer_gather_single_rank(dpt):
         assert abs(stats["mean_reward"] - float(ref_stats[0]) / (N * H)) < 1e-12 and stats["env_steps"] == N * H
     finally:
         pg.close()
+
+
+@pytest.mark.parametrize("N,d,H", [(64, 5, 500), (9, 10, 61), (40, 3, 37)])
+def test_bandit_rollin_bernoulli(dpt, N, d, H):
+    """type == 'bernoulli' envs (envs/bandit_env.py:60-61): rewards are Bernoulli(means[a]).  Same action stream
+    as the uniform type; rewards exactly [u < mean] on the dumped uniforms (fast and generic kernels), {0,1}
+    valued, and their frequency matches the pulled arms' means."""
+    seed, env_id0 = 99, 50
+    means, _, _ = dpt.kernels.bandit_sample_means(N, d, seed, env_id0)
+    m64 = _np(means).astype(np.float64)
+    g = dpt.kernels.bandit_rollin(means, H, 0.3, seed, env_id0)
+    b = dpt.kernels.bandit_rollin(means, H, 0.3, seed, env_id0, dump=True, reward_type="bernoulli")
+    assert torch.equal(g["context_actions"], b["context_actions"]) and torch.equal(g["context_states"], b["context_states"])
+    nz = {k: _np(v) for k, v in b["noise"].items()}
+    assert nz["z"].min() >= 0.0 and nz["z"].max() < 1.0
+    xs, us, xps, rs, acts = O.rollin_bandit_batch(m64, 0.3, nz["cov_idx"], nz["dir_probs"], nz["rand_idx"], nz["u"], nz["z"],
+                                                  reward_type="bernoulli")
+    r = _np(b["context_rewards"])[:, :, 0]
+    assert np.array_equal(r.astype(np.float64), rs) and set(np.unique(r)) <= {0.0, 1.0}
+    b2 = dpt.kernels.bandit_rollin(means, H, 0.3, seed, env_id0, reward_type="bernoulli")
+    assert torch.equal(b["context_rewards"], b2["context_rewards"])
+    # injected uniforms reproduce the rewards
+    b3 = dpt.kernels.bandit_rollin(means, H, 0.3, 0, 0, inject={"actions": nz["actions"], "z": nz["z"]}, reward_type="bernoulli")
+    assert torch.equal(b["context_rewards"], b3["context_rewards"])
+    pm = np.take_along_axis(m64, acts, axis=1)
+    se = np.sqrt((pm * (1 - pm)).sum()) / pm.size
+    assert abs(r.mean() - pm.mean()) < 5 * se + 1e-9
+    with pytest.raises(KeyError):
+        dpt.kernels.bandit_rollin(means, H, 0.3, seed, env_id0, reward_type="poisson")
+
+
+def test_rollin_bandit_follows_env_type(dpt):
+    """rollin_bandit / generate_bandit_histories_from_envs take the reward law from env.type (env.transit,
+    collect_data.py:45); generate_bandit_histories ignores its `type` kwarg like the reference (:221-225)."""
+    from dpt_b200 import collect_data
+    from dpt_b200.envs.bandit_env import BanditEnv, sample
+    dpt.seed(5)
+    env = BanditEnv(np.array([0.2, 0.9, 0.5]), 64, var=0.3, type="bernoulli")
+    xs, us, xps, rs = collect_data.rollin_bandit(env, cov=0.0)
+    assert rs.shape == (64,) and set(np.unique(rs)) <= {0.0, 1.0} and us.shape == (64, 3)
+    envs = [sample(4, 32, 0.3, type="bernoulli") for _ in range(6)]
+    trajs = collect_data.generate_bandit_histories_from_envs(envs, n_hists=2, n_samples=1, cov=0.0, type="bernoulli")
+    assert len(trajs) == 12 and all(set(np.unique(t["context_rewards"])) <= {0.0, 1.0} for t in trajs)
+    trajs = collect_data.generate_bandit_histories(5, 4, 16, 0.3, n_hists=1, n_samples=1, cov=0.0, type="bernoulli")
+    assert len(trajs) == 5 and any(len(np.unique(t["context_rewards"])) > 2 for t in trajs)   # gaussian rewards
+    with pytest.raises(NotImplementedError):
+        collect_data.generate_bandit_histories_from_envs([envs[0], BanditEnv(np.ones(4) * .5, 32, var=0.3)], 1, 1, 0.0, "uniform")
