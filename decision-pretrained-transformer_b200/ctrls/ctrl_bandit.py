@@ -211,6 +211,24 @@ class ThompsonSamplingPolicy(Controller):
     def set_batch_numpy_vec(self, batch):
         self._posterior(batch)
 
+    def update_posterior(self, c, arm_rewards):
+        """:184-194 (single env): conjugate update of arm ``c`` from its observed rewards."""
+        n = self.counts[c]
+        if n > 0:
+            arm_mean = np.mean(arm_rewards)
+            prior_weight = self.variance / (self.variance + (n * self.prior_variance))
+            self.means[c] = prior_weight * self.prior_mean + (1 - prior_weight) * arm_mean
+            self.variances[c] = 1 / (1 / self.prior_variance + n / self.variance)
+
+    def update_posterior_all(self, arm_means):
+        """:196-203 (batched): the same update for every (env, arm) with a positive count."""
+        prior_weight = self.variance / (self.variance + (self.counts * self.prior_variance))
+        new_mean = prior_weight * self.prior_mean + (1 - prior_weight) * arm_means
+        new_variance = 1 / (1 / self.prior_variance + self.counts / self.variance)
+        mask = (self.counts > 0)
+        self.means[mask] = new_mean[mask]
+        self.variances[mask] = new_variance[mask]
+
     def _draw(self):
         if self.sample:
             values = np.random.normal(self.means, np.sqrt(self.variances))

@@ -41,6 +41,29 @@ def deploy_online_vec_device(vec_env, controller, horizon, include_meta=False, r
                                inject, dump, rtype)
 
 
+def deploy_online(env, controller, horizon):
+    """evals/eval_bandit.py:24-53 (= eval_linear_bandit.py:22-51): the single-env loop with torch context
+    tensors; the controller sees the first h rows through ``set_batch``.  Returns cum_means [horizon]."""
+    dev = kernels._dev()
+    f = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).to(dev)   # noqa: E731
+    context_states = torch.zeros((1, horizon, env.dx), device=dev)
+    context_actions = torch.zeros((1, horizon, env.du), device=dev)
+    context_next_states = torch.zeros((1, horizon, env.dx), device=dev)
+    context_rewards = torch.zeros((1, horizon, 1), device=dev)
+    cum_means = []
+    for h in range(horizon):
+        controller.set_batch({"context_states": context_states[:, :h, :], "context_actions": context_actions[:, :h, :],
+                              "context_next_states": context_next_states[:, :h, :],
+                              "context_rewards": context_rewards[:, :h, :]})
+        states_lnr, actions_lnr, next_states_lnr, rewards_lnr = env.deploy(controller)
+        context_states[0, h, :] = f(states_lnr[0])
+        context_actions[0, h, :] = f(actions_lnr[0])
+        context_next_states[0, h, :] = f(next_states_lnr[0])
+        context_rewards[0, h, :] = f(rewards_lnr[0])
+        cum_means.append(env.get_arm_value(np.asarray(actions_lnr).flatten()))
+    return np.array(cum_means)
+
+
 def deploy_online_vec(vec_env, controller, horizon, include_meta=False):
     """evals/eval_bandit.py:56-103."""
     if _fusable(vec_env, controller) is not None:

@@ -103,3 +103,54 @@ def online(eval_trajs, model, Heps, H, n_eval, dim, horizon, permuted=False):
     ctrl = DarkroomTransformerController(model, batch_size=n_eval, sample=True)
     all_means = deploy_online_vec(DarkroomEnvVec(envs), ctrl, Heps, H, horizon)
     return all_means, all_means.mean(0), all_means.std(0, ddof=1) / np.sqrt(n_eval)
+
+
+def offline_device(eval_trajs, model, n_eval, H, dim, permuted=False, seed=None, inject_u=None, dump=False):
+    """The learner half of ``offline`` with everything on the device: the context of every env is its eval
+    trajectory (fixed for the whole episode), so ONE batched dense forward gives the logits of all dim*dim
+    query states of every env and ONE rollout launch per policy plays the H-step episode from that table
+    (sampled with the Philox stream or ``inject_u`` f64 [H, N]; greedy = argmax).  Returns a dict of device
+    tensors: ``returns_sample`` / ``returns_greedy`` [n_eval] and the two rollouts."""
+    from .. import rng
+    dev = kernels._dev()
+    trajs = [eval_trajs[i] for i in range(n_eval)]
+    f = lambda k, tail: torch.as_tensor(np.stack([np.asarray(t[k], dtype=np.float64).reshape((-1,) + tail) for t in trajs]),  # noqa: E731
+                                        dtype=torch.float32).to(dev)
+    ctx = {"context_states": f("context_states", (2,)), "context_actions": f("context_actions", (5,)),
+           "context_next_states": f("context_next_states", (2,)), "context_rewards": f("context_rewards", (1,))}
+    if permuted:
+        goals = torch.full((n_eval, 2), dim - 1, dtype=torch.int32, device=dev)            # envs/darkroom_env.py:92
+        perm = torch.as_tensor([int(t["perm_index"]) for t in trajs], dtype=torch.int32).to(dev)
+    else:
+        goals = torch.as_tensor(np.stack([np.asarray(t["goal"]) for t in trajs]), dtype=torch.int32).to(dev)
+        perm = None
+    g = torch.arange(dim, device=dev, dtype=torch.float32)
+    grid = torch.stack(torch.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)              # index x*dim + y
+    was_test = model.test
+    model.test = True
+    logits = model.forward(dict(ctx, query_states=grid.repeat(n_eval, 1).contiguous()), ctx_share=dim * dim)
+    model.test = was_test
+    table = logits.view(n_eval, dim * dim, 5)
+    key = rng.next_key() if seed is None else seed
+    inj = None if inject_u is None else torch.as_tensor(np.asarray(inject_u), dtype=torch.float64).to(dev)
+    smp = kernels.darkroom_policy_rollout(table, goals, dim, H, True, key, 0, 0, perm, inj, dump)
+    grd = kernels.darkroom_policy_rollout(table, goals, dim, H, False, key, 0, 1, perm)
+    return {"returns_sample": smp["returns"], "returns_greedy": grd["returns"], "sample": smp, "greedy": grd, "logits": table}
+
+
+def offline(eval_trajs, model, n_eval, H, dim, permuted=False):
+    """evals/eval_darkroom.py:124-190 without the bar plot.  Returns {'Opt', 'Learner', 'Learner (greedy)'}:
+    per-env returns of an H-step episode for the optimal policy and for the transformer (sampled / greedy)
+    conditioned on each eval trajectory's own context."""
+    trajs = [eval_trajs[i] for i in range(n_eval)]
+    if permuted:
+        goals = np.full((n_eval, 2), dim - 1)
+        perm = np.array([int(t["perm_index"]) for t in trajs])
+    else:
+        goals, perm = np.stack([np.asarray(t["goal"]) for t in trajs]), None
+    # DarkroomOptPolicy from the reset state (:151-155) is the 'expert' rollin of the rollout kernel
+    opt = kernels.darkroom_rollin(goals, dim, H, "expert", 0, 0, perm, 1)
+    rs_opt = opt["context_rewards"][:, :, 0].sum(dim=1)
+    out = offline_device(eval_trajs, model, n_eval, H, dim, permuted)
+    return {"Opt": rs_opt.cpu().numpy().astype(np.float64), "Learner": out["returns_sample"].cpu().numpy().astype(np.float64),
+            "Learner (greedy)": out["returns_greedy"].cpu().numpy().astype(np.float64)}

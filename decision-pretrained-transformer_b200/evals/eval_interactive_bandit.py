@@ -14,6 +14,21 @@ def _sem(v):
     return v.std(axis=0, ddof=1) / np.sqrt(v.shape[0])      # scipy.stats.sem
 
 
+def generate_eval_trajs(n_eval, dim, bandit_type="uniform"):
+    """evals/eval_interactive_bandit.py:29-40: eval bandit instances (means only; no rollout data), drawn on the
+    host ``np.random`` stream like the reference."""
+    eval_trajs = []
+    for _ in range(n_eval):
+        if bandit_type == "uniform":
+            means = np.random.uniform(0, 1, dim)
+        elif bandit_type == "bernoulli":
+            means = np.random.beta(1, 1, dim)
+        else:
+            raise ValueError(f"Unknown bandit_type: {bandit_type}")
+        eval_trajs.append({"means": means})
+    return eval_trajs
+
+
 def run_online_eval(eval_trajs, model, n_eval, horizon, var, bandit_type="uniform", sample_model=False):
     """evals/eval_interactive_bandit.py:73-142: Opt, Interactive (transformer), Emp, UCB, Thompson on the same
     tasks; returns the reference's dict (means, sems, regret_means, regret_sems, all_means, all_means_diff)."""

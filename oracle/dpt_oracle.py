@@ -514,6 +514,31 @@ def deploy_online_vec_darkroom(goals, dim, Heps, H, horizon, logits_fn, noise, p
     return np.stack(cum, axis=1), (cs, ca, cns, cr)
 
 
+def darkroom_episode(goals, dim, horizon, logits_fn, u, perm_indices=None, sample=True):
+    """One DarkroomEnvVec.deploy episode (envs/darkroom_env.py:151-175) under DarkroomTransformerController.act
+    (ctrls/ctrl_darkroom.py:35-66) with a FIXED context: ``logits_fn(query [N,2]) -> [N,5]``; ``u`` [horizon,N]
+    are the uniforms of the categorical draws (env order within a step).  Returns the per-env returns [N] --
+    the learner half of evals/eval_darkroom.py:124-190 (`offline`)."""
+    goals = np.asarray(goals)
+    N = len(goals)
+    perms = None if perm_indices is None else [DARKROOM_PERMS[int(p)] for p in perm_indices]
+    state = np.zeros((N, 2), dtype=np.int64)
+    ret = np.zeros(N)
+    for t in range(horizon):
+        logits = np.asarray(logits_fn(state.astype(np.float64)), dtype=np.float64)
+        if sample:
+            e = np.exp(logits - logits.max(-1, keepdims=True))
+            probs = e / e.sum(-1, keepdims=True)
+            a = np.array([int(choice_cdf(p).searchsorted(u[t][i], side="right")) for i, p in enumerate(probs)])
+        else:
+            a = logits.argmax(-1)
+        for i in range(N):
+            ns, r = darkroom_transit(state[i], int(a[i]), goals[i], dim, None if perms is None else perms[i])
+            state[i] = ns
+            ret[i] += r
+    return ret
+
+
 def regret_stats(opt_means, alg_means):
     """evals/eval_bandit.py:169-178: inputs [N,H]; returns per-step mean, sem and cumulative mean, sem."""
     diff = np.asarray(opt_means) - np.asarray(alg_means)

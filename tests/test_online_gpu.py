@@ -333,3 +333,43 @@ def test_deploy_online_vec_bernoulli_envs_fused(dpt):
     cum, meta = deploy_online_vec(vec, UCBPolicy(envs[0], const=1.0, batch_size=64), 40, include_meta=True)
     assert cum.shape == (40, 64) and set(np.unique(meta["context_rewards"])) <= {0.0, 1.0}
     assert meta["context_actions"].sum(-1).min() == 1.0
+
+
+def test_linear_bandit_offline_eval(dpt):
+    """evals/eval_linear_bandit.py:202-330 `offline` / `offline_graph`: each controller sees the first h context rows
+    and plays one noise-free pull.  'opt' is the best arm's mean, 'linreg' (LinUCB with const = 0) is checked against
+    the oracle's LinUCB on the same context, Thompson(sample=False) against the float64 posterior (its 100-draw mode
+    picks the arm with the largest posterior mean whenever the gap dwarfs the posterior std)."""
+    from dpt_b200 import collect_data
+    from dpt_b200.evals import eval_linear_bandit
+    dpt.seed(21)
+    N, d, lin_d, H, var = 24, 10, 2, 30, 0.3
+    trajs = collect_data.generate_linear_bandit_histories(N, d, lin_d, H, var, n_hists=1, n_samples=1, cov=0.0, data_type="thompson")
+    assert len(trajs) == N and trajs[0]["arms"].shape == (d, lin_d)
+    np.random.seed(0)
+    for h in (1, 7, H):
+        res = eval_linear_bandit.offline(trajs, None, N, h, var)
+        assert set(res) == {"opt", "thmp", "linreg"} and all(v.shape == (N,) for v in res.values())
+        means = np.stack([t["means"] for t in trajs])
+        _close(res["opt"], means.max(1))
+        ca = np.stack([t["context_actions"][:h] for t in trajs])
+        cr = np.stack([np.asarray(t["context_rewards"])[:h, None] for t in trajs])
+        hot = O.LinUCBCtrl(trajs[0]["arms"], 0.0).act(ca, cr, None, h)
+        _close(res["linreg"], (means * hot).sum(1))
+        assert np.all(res["thmp"] <= res["opt"] + 1e-6) and np.all(res["linreg"] <= res["opt"] + 1e-6)
+    hs, sub = eval_linear_bandit.offline_graph(trajs[:6], None, 6, 5, var)
+    assert list(hs) == [1, 2, 3, 4, 5] and set(sub) == {"thmp", "linreg"} and sub["linreg"][0].shape == (5,) and np.all(sub["linreg"][0] >= -1e-6)
+
+
+def test_deploy_online_single_env(dpt):
+    """evals/eval_bandit.py:24-53 `deploy_online`: the single-env loop through set_batch / env.deploy."""
+    from dpt_b200.envs.bandit_env import BanditEnv
+    from dpt_b200.ctrls.ctrl_bandit import EmpMeanPolicy, OptPolicy
+    from dpt_b200.evals import eval_bandit, eval_linear_bandit
+    dpt.seed(2)
+    env = BanditEnv(np.array([0.1, 0.8, 0.3, 0.5]), 1, var=0.1)
+    cm = eval_bandit.deploy_online(env, OptPolicy(env), 6)
+    assert cm.shape == (6,) and np.allclose(cm, 0.8)
+    cm = eval_bandit.deploy_online(env, EmpMeanPolicy(env, online=True), 12)
+    assert cm.shape == (12,) and sorted(cm[:4]) == [0.1, 0.3, 0.5, 0.8] and np.allclose(cm[4:], 0.8)   # each arm once, then the best
+    assert eval_linear_bandit.deploy_online is eval_bandit.deploy_online

@@ -210,3 +210,34 @@ def test_dataset_dropin(tmp_path):
             y = ds[i]
             for k in x:
                 assert torch.equal(x[k].cpu(), y[k]), k
+
+
+def test_host_side_eval_helpers():
+    """Host-only pieces of the eval callers: generate_eval_trajs (evals/eval_interactive_bandit.py:29-40) draws on
+    np.random like the reference; ThompsonSamplingPolicy.update_posterior[_all] (ctrls/ctrl_bandit.py:184-203)."""
+    import dpt_b200
+    from dpt_b200.evals.eval_interactive_bandit import generate_eval_trajs
+    from dpt_b200.ctrls.ctrl_bandit import ThompsonSamplingPolicy
+    np.random.seed(3)
+    t = generate_eval_trajs(4, 5, "uniform")
+    np.random.seed(3)
+    want = [np.random.uniform(0, 1, 5) for _ in range(4)]
+    assert all(np.array_equal(a["means"], b) for a, b in zip(t, want))
+    assert generate_eval_trajs(2, 3, "bernoulli")[0]["means"].shape == (3,)
+    with pytest.raises(ValueError):
+        generate_eval_trajs(1, 3, "poisson")
+
+    class _Env:
+        dim = 3
+    p = ThompsonSamplingPolicy(_Env(), std=0.3, sample=True, prior_mean=0.5, prior_var=1 / 12.0, batch_size=2)
+    p.counts = np.array([[0., 2., 5.], [1., 0., 0.]])
+    arm_means = np.array([[0., .4, .9], [.2, 0., 0.]])
+    p.update_posterior_all(arm_means)
+    w = 0.09 / (0.09 + p.counts / 12.0)
+    assert np.allclose(p.means, np.where(p.counts > 0, w * 0.5 + (1 - w) * arm_means, 0.5))
+    assert np.allclose(p.variances, np.where(p.counts > 0, 1 / (12.0 + p.counts / 0.09), 1 / 12.0))
+    q = ThompsonSamplingPolicy(_Env(), std=0.3, sample=True)
+    q.counts = np.array([0., 3., 0.])
+    q.update_posterior(1, np.array([.5, .7, .9]))
+    q.update_posterior(0, np.array([]))
+    assert np.isclose(q.means[1], (0.09 / (0.09 + 3 / 12.0)) * 0.5 + (1 - 0.09 / (0.09 + 3 / 12.0)) * 0.7) and q.means[0] == 0.5

@@ -403,3 +403,53 @@ def test_interactive_bandit_rows(dpt):
     assert set(res) == {"means", "sems", "regret_means", "regret_sems", "all_means", "all_means_diff"}
     assert set(res["means"]) == {"opt", "Interactive", "Emp", "UCB1.0", "Thomp"}
     assert res["regret_means"]["Thomp"].shape == (12,) and np.all(res["regret_means"]["opt"] == 0)
+
+
+@pytest.mark.parametrize("name", ["darkroom_online", "darkroom_online_perm"])
+def test_darkroom_offline_eval(dpt, name):
+    """evals/eval_darkroom.py:124-190 `offline`: Opt / Learner / Learner (greedy) returns of one H-step episode with
+    each eval trajectory's own context.  The fused path (policy table from one batched forward + one rollout
+    launch) must equal the reference-shaped step-by-step path (DarkroomEnvVec.deploy_eval with the controller
+    classes); the sampled learner is replayed through the oracle loop on the dumped uniforms."""
+    from dpt_b200 import collect_data
+    from dpt_b200.models.net import Transformer
+    from dpt_b200.ctrls.ctrl_darkroom import DarkroomOptPolicy, DarkroomTransformerController
+    from dpt_b200.envs.darkroom_env import DarkroomEnv, DarkroomEnvPermuted, DarkroomEnvVec
+    from dpt_b200.evals import eval_darkroom
+    g = golden(name)
+    dim, H, nl = int(g["dim"]), int(g["horizon"]), int(g["n_layer"])
+    permuted = bool(len(g["perm_indices"]))
+    m = Transformer({"horizon": int(g["H"]), "state_dim": 2, "action_dim": 5, "n_layer": nl, "n_embd": 32, "n_head": 1,
+                     "dropout": 0.0, "test": True})
+    m.load_state_dict({k[3:]: torch.tensor(g[k]) for k in g.files if k.startswith("sd/")}, strict=False)
+    dpt.seed(4)
+    if permuted:
+        trajs = collect_data.generate_darkroom_permuted_histories(g["perm_indices"], dim, H, n_hists=1, n_samples=1, rollin_type="uniform")
+        envs = [DarkroomEnvPermuted(dim, int(t["perm_index"]), H) for t in trajs]
+    else:
+        trajs = collect_data.generate_darkroom_histories(g["goals"], dim, H, n_hists=1, n_samples=1, rollin_type="uniform")
+        envs = [DarkroomEnv(dim, t["goal"], H) for t in trajs]
+    N = len(trajs)
+    res = eval_darkroom.offline(trajs, m, N, H, dim, permuted=permuted)
+    assert set(res) == {"Opt", "Learner", "Learner (greedy)"} and all(v.shape == (N,) for v in res.values())
+    # Opt: DarkroomOptPolicy deployed on each env (:151-155)
+    want_opt = [np.sum(e.deploy_eval(DarkroomOptPolicy(e))[3]) for e in envs]
+    assert np.array_equal(res["Opt"], np.array(want_opt, dtype=np.float64))
+    # greedy learner: the step-by-step controller path on the same batch
+    batch = {"context_states": torch.tensor(np.stack([t["context_states"] for t in trajs]), dtype=torch.float32),
+             "context_actions": torch.tensor(np.stack([t["context_actions"] for t in trajs]), dtype=torch.float32),
+             "context_next_states": torch.tensor(np.stack([t["context_next_states"] for t in trajs]), dtype=torch.float32),
+             "context_rewards": torch.tensor(np.stack([np.asarray(t["context_rewards"])[:, None] for t in trajs]), dtype=torch.float32)}
+    greedy = DarkroomTransformerController(m, batch_size=N, sample=False)
+    greedy.set_batch(batch)
+    rs = DarkroomEnvVec(envs).deploy_eval(greedy)[3]
+    assert np.array_equal(res["Learner (greedy)"], np.sum(rs, axis=-1).astype(np.float64))
+    # sampled learner: dump the uniforms and replay them through the oracle's episode loop on the same logits
+    out = eval_darkroom.offline_device(trajs, m, N, H, dim, permuted=permuted, seed=9, dump=True)
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("sd/")}
+    cs, ca, cns, cr = (batch[k].numpy().astype(np.float64) for k in ("context_states", "context_actions", "context_next_states", "context_rewards"))
+    goals = np.stack([e.goal for e in envs])
+    want = O.darkroom_episode(goals, dim, H, lambda q: O.transformer_forward(sd, q, cs, ca, cns, cr, nl, test=True),
+                              _np(out["sample"]["u"]), [int(t["perm_index"]) for t in trajs] if permuted else None, sample=True)
+    assert np.array_equal(_np(out["returns_sample"]).astype(np.float64), want)
+    assert np.all(res["Learner"] <= res["Opt"]) and np.all(res["Learner (greedy)"] <= res["Opt"])
