@@ -18,7 +18,7 @@ from .models import net                   # noqa: F401
 
 __all__ = ["seed", "kernels", "envs", "collect_data", "install_dropin"]
 
-_DROPIN = ("envs", "ctrls", "evals", "models", "collect_data", "dataset")
+_DROPIN = ("envs", "ctrls", "evals", "models", "collect_data", "dataset", "utils")
 
 
 def install_dropin():

@@ -2,6 +2,7 @@
 (oracle/make_golden.py), the Philox known-answer vectors, and the host-side logic."""
 import numpy as np
 import pytest
+import torch
 
 from conftest import golden
 from oracle import dpt_oracle as O
@@ -241,3 +242,27 @@ def test_host_side_eval_helpers():
     q.update_posterior(1, np.array([.5, .7, .9]))
     q.update_posterior(0, np.array([]))
     assert np.isclose(q.means[1], (0.09 / (0.09 + 3 / 12.0)) * 0.5 + (1 - 0.09 / (0.09 + 3 / 12.0)) * 0.7) and q.means[0] == 0.5
+
+
+def test_utils_filenames_match_reference():
+    """utils.py:15-153 naming contract (dataset pickles / checkpoints).  Expected strings were produced by the
+    reference's own utils.py in the dev container (see the commit that added this test)."""
+    import dpt_b200
+    from dpt_b200 import utils as U
+    cfg = {"n_hists": 1, "n_samples": 2, "horizon": 500, "dim": 5, "var": 0.3, "cov": 0.0, "lin_d": 2, "rollin_type": "uniform",
+           "shuffle": True, "lr": 0.001, "dropout": 0.0, "n_embd": 32, "n_layer": 4, "n_head": 1, "n_envs": 100000, "seed": 1}
+    assert U.build_bandit_data_filename("bandit", 1000, cfg, 0) == "datasets/trajs_bandit_envs1000_hists1_samples2_H500_d5_var0.3_cov0.0_train.pkl"
+    assert U.build_bandit_data_filename("bandit", 1000, cfg, 1) == "datasets/trajs_bandit_envs1000_hists1_samples2_H500_d5_var0.3_cov0.0_test.pkl"
+    assert U.build_bandit_data_filename("bandit", 1000, cfg, 2) == "datasets/trajs_bandit_envs1000_H500_d5_var0.3_cov0.0_eval.pkl"
+    assert U.build_linear_bandit_data_filename("bandit", 1000, cfg, 0) == "datasets/trajs_bandit_envs1000_hists1_samples2_H500_d5_lind2_var0.3_cov0.0_train.pkl"
+    assert U.build_linear_bandit_data_filename("bandit", 1000, cfg, 2) == "datasets/trajs_bandit_envs1000_H500_d5_lind2_var0.3_cov0.0_eval.pkl"
+    assert U.build_darkroom_data_filename("bandit", 1000, cfg, 1) == "datasets/trajs_bandit_envs1000_hists1_samples2_H500_d5_test.pkl"
+    assert U.build_darkroom_data_filename("bandit", 1000, cfg, 2) == "datasets/trajs_bandit_envs1000_H500_d5_uniform_eval.pkl"
+    assert U.build_bandit_model_filename("darkroom_heldout", cfg) == \
+        "darkroom_heldout_shufTrue_lr0.001_do0.0_embd32_layer4_head1_envs100000_hists1_samples2_var0.3_cov0.0_H500_d5_seed1"
+    assert U.build_linear_bandit_model_filename("darkroom_heldout", cfg) == \
+        "darkroom_heldout_shufTrue_lr0.001_do0.0_embd32_layer4_head1_envs100000_hists1_samples2_var0.3_cov0.0_H500_d5_lind2_seed1"
+    assert U.build_darkroom_model_filename("darkroom_heldout", cfg) == \
+        "darkroom_heldout_shufTrue_lr0.001_do0.0_embd32_layer4_head1_envs100000_hists1_samples2_H500_d5_seed1"
+    t = U.convert_to_tensor([[1, 2], [3, 4]], store_gpu=False)
+    assert t.dtype == torch.float32 and t.shape == (2, 2)
