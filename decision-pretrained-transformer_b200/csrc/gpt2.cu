@@ -90,16 +90,92 @@ __device__ __forceinline__ float gelu_new(float x) {  // transformers NewGELUAct
 constexpr int PF_AHEAD = 3;      // K/V L2 prefetch distance in 32-key iterations (fp32 cache: 4 KB each)
 constexpr int PF_MAX_POS = 192;  // only short (latency-bound) sequences prefetch: +20 % at H=100, -2 % at H=500 without the cap
 
-template <bool BF16>
+// D[16x8] += A[16x16] B[16x8], bf16 operands, fp32 accumulate (legacy tensor-core path; tcgen05 needs M = 128 rows
+// that a one-row-per-env decode does not have)
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {   // lo -> bits 0..15 (the lower k / n index)
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// y[N] = x[K] W on the tensor cores, one warp, weights as pre-arranged bf16 B fragments in shared memory (WF_* layout
+// in gpt2_model.cuh).  The activation vector is row 0 of the A tile (lanes 0..3); its products come out in row 0 of
+// the accumulator, again lanes 0..3, and go back to shared memory.  xin / yout: 8 B-aligned, distinct buffers.
+template <int K, int N>
+__device__ __forceinline__ void matvec_mma(const uint4* wf, const float* xin, float* yout, int lane) {
+  const int c = lane & 3;
+  uint32_t a0[K / 16], a2[K / 16];
+#pragma unroll
+  for (int ks = 0; ks < K / 16; ++ks) {
+    a0[ks] = a2[ks] = 0u;
+    if (lane < 4) {
+      const float2 u = *reinterpret_cast<const float2*>(xin + 16 * ks + 2 * c);
+      const float2 w = *reinterpret_cast<const float2*>(xin + 16 * ks + 8 + 2 * c);
+      a0[ks] = pack_bf16(u.x, u.y), a2[ks] = pack_bf16(w.x, w.y);
+    }
+  }
+#pragma unroll
+  for (int ntp = 0; ntp < N / 16; ++ntp) {
+    float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint4 bw = wf[(ks * (N / 16) + ntp) * 32 + lane];
+      mma_bf16_16816(d0, a0[ks], 0u, a2[ks], 0u, bw.x, bw.y);
+      mma_bf16_16816(d1, a0[ks], 0u, a2[ks], 0u, bw.z, bw.w);
+    }
+    if (lane < 4) {
+      *reinterpret_cast<float2*>(yout + 16 * ntp + 2 * c) = make_float2(d0[0], d0[1]);
+      *reinterpret_cast<float2*>(yout + 16 * ntp + 8 + 2 * c) = make_float2(d1[0], d1[1]);
+    }
+  }
+}
+
+// W[K][N] fp32 -> WF_* fragment image (one thread per (group, lane))
+__global__ void pack_wfrag_kernel(const float* __restrict__ W, uint4* __restrict__ dst, int K, int N) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (K / 16) * (N / 16) * 32) return;
+  const int lane = id & 31, grp = id >> 5;
+  const int ks = grp / (N / 16), ntp = grp - ks * (N / 16);
+  const int c = lane & 3, n0 = 16 * ntp + (lane >> 2), n1 = n0 + 8, k0 = 16 * ks + 2 * c;
+  auto w = [&](int k, int n) { return W[(size_t)k * N + n]; };
+  dst[id] = make_uint4(pack_bf16(w(k0, n0), w(k0 + 1, n0)), pack_bf16(w(k0 + 8, n0), w(k0 + 9, n0)),
+                       pack_bf16(w(k0, n1), w(k0 + 1, n1)), pack_bf16(w(k0 + 8, n1), w(k0 + 9, n1)));
+}
+
+// resident CTAs per SM the online-loop kernels are compiled for (register cap = 65536 / (128 * n)); measured on B200
+#ifndef DPT_GPT2_MINB_F32
+#define DPT_GPT2_MINB_F32 9   // 56 registers: 221 ms at C4 against 241 ms (8) / 226 ms (7) / 270 ms (10)
+#endif
+#ifndef DPT_GPT2_MINB_BF16
+#define DPT_GPT2_MINB_BF16 6
+#endif
+#ifndef DPT_GPT2_BF16_PREFETCH_V
+#define DPT_GPT2_BF16_PREFETCH_V 0   // measured: 161 ms with, 155 ms without (C4, bf16 K/V)
+#endif
+
+// WS: the projections run on the tensor cores from bf16 weight fragments in shared memory (`wf`, all layers)
+template <bool BF16, bool WS = false>
 __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int pos, void* kv_, int Tpad, float* sx,
-                                               float* sh, float* ssc, int lane) {
+                                               float* sh, float* ssc, int lane, const uint4* wf = nullptr) {
   for (int l = 0; l < m.L; ++l) {
     const LayerW& w = m.layer[l];
     // ---- attention ----
     sx[lane] = layer_norm(x, w.ln1_w, w.ln1_b, lane);
     __syncwarp();
     float qkv[3];
-    matvec_packed<G_E, 3>(sx, w.attn_wP, w.attn_b, lane, qkv);
+    if constexpr (WS) {
+      matvec_mma<G_E, 3 * G_E>(wf + l * WF_UINT4 + WF_QKV, sx, sh, lane);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 3; ++i) qkv[i] = sh[32 * i + lane] + __ldg(w.attn_b + 32 * i + lane);
+    } else {
+      matvec_packed<G_E, 3>(sx, w.attn_wP, w.attn_b, lane, qkv);
+    }
     float q = qkv[0];
     const float k = qkv[1], v = qkv[2];
     float lmax = -INFINITY, s_self, p_self, inv, osum;
@@ -191,62 +267,58 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
       __syncwarp();
       osum = sx[lane] + p_self * v;
     } else {
-    __syncwarp();
-      // bf16 cache: rows are 64 B; lane = (key group g = lane/4, channel oct b4 = lane%4); one LDG.128
-      // instruction covers 8 keys x 32 channels; 8 are in flight per lane (64 keys per iteration)
+      __syncwarp();
+      // bf16 cache on the tensor cores (mma.sync m16n8k16, fp32 accumulate).  The decode is a GEMV per env (one
+      // query row against that env's private keys), so only row 0 of the 16-row A tile is live; what the MMA buys
+      // is instruction count: 2 HMMA replace ~90 unpack / FMA / shuffle instructions per 8 keys.
+      //   K cache: one 64 B row per key, channels permuted so that lane (g = lane/4, c = lane%4) reads the B
+      //            fragments of key g for both k-steps with ONE 16 B load (kperm below).
+      //   V cache: blocks of 16 keys x 32 channels (1 KB) stored as [channel-in-octet g][key pair c][octet j]
+      //            [keys 2c, 2c+1, 2c+8, 2c+9]: lane (g, c) reads the B fragments of all four channel octets with
+      //            two 16 B loads; a block is zeroed when its first key is appended (P = 0 must meet finite V).
       __nv_bfloat16* K = reinterpret_cast<__nv_bfloat16*>(kv_) + (size_t)(l * 2) * G_E * Tpad;
       __nv_bfloat16* V = K + (size_t)G_E * Tpad;
-      K[(size_t)pos * G_E + lane] = __float2bfloat16_rn(k);
-      V[(size_t)pos * G_E + lane] = __float2bfloat16_rn(v);
+      const int g = lane >> 2, c = lane & 3;
+      {
+        const int r = lane & 15;
+        const int kperm = ((r & 7) >> 1) * 8 + (lane >> 4) * 4 + (r >> 3) * 2 + (r & 1);
+        K[(size_t)pos * G_E + kperm] = __float2bfloat16_rn(k);
+        __nv_bfloat16* vb = V + (size_t)(pos >> 4) * 512;
+        if ((pos & 15) == 0) {
+          reinterpret_cast<uint4*>(vb)[2 * lane] = make_uint4(0, 0, 0, 0);
+          reinterpret_cast<uint4*>(vb)[2 * lane + 1] = make_uint4(0, 0, 0, 0);
+          __syncwarp();
+        }
+        const int kk = pos & 15;
+        vb[(((lane & 7) * 4 + ((kk & 7) >> 1)) * 4 + (lane >> 3)) * 4 + (kk >> 3) * 2 + (kk & 1)] = __float2bfloat16_rn(v);
+      }
       q *= 0.17677669529663687f;
       sx[lane] = q;
       __syncwarp();
-      const int g = lane >> 2, b4 = lane & 3;
-      float qv[8];
-      {
-        const float4 qa = reinterpret_cast<const float4*>(sx)[2 * b4], qb = reinterpret_cast<const float4*>(sx)[2 * b4 + 1];
-        qv[0] = qa.x, qv[1] = qa.y, qv[2] = qa.z, qv[3] = qa.w, qv[4] = qb.x, qv[5] = qb.y, qv[6] = qb.z, qv[7] = qb.w;
+      uint32_t qa0 = 0, qa1 = 0, qa2 = 0, qa3 = 0;   // A fragments (row 0 only): k-step 0 (a0, a2), k-step 1 (a0, a2)
+      if (lane < 4) {
+        qa0 = pack_bf16(sx[2 * c], sx[2 * c + 1]), qa1 = pack_bf16(sx[2 * c + 8], sx[2 * c + 9]);
+        qa2 = pack_bf16(sx[2 * c + 16], sx[2 * c + 17]), qa3 = pack_bf16(sx[2 * c + 24], sx[2 * c + 25]);
       }
-      const uint4* K8 = reinterpret_cast<const uint4*>(K) + b4;   // row stride = 4 uint4
-      const uint4* V8 = reinterpret_cast<const uint4*>(V) + b4;
+      const uint4* K8 = reinterpret_cast<const uint4*>(K) + c;   // row stride = 4 uint4
       __syncwarp();
       for (int k0 = 0; k0 < pos; k0 += 64) {
         uint4 kk[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) kk[i] = __ldcg(K8 + (size_t)(k0 + 8 * i + g) * 4);   // in bounds (Tpad % 64 == 0)
-        float pv[8];
+        // the V blocks of the same 64 keys (4 KB = one 128 B line per lane) start their trip from HBM to L2 now; the
+        // P V pass below then waits an L2 rather than a DRAM latency (this mode is latency-, not bandwidth-bound)
+        if (DPT_GPT2_BF16_PREFETCH_V && k0 + 16 * (lane >> 3) < pos)
+          prefetch_l2(reinterpret_cast<const unsigned char*>(V) + (size_t)(k0 >> 4) * 1024 + lane * 128);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const uint32_t w0 = kk[i].x, w1 = kk[i].y, w2 = kk[i].z, w3 = kk[i].w;
-          float a = qv[0] * __uint_as_float(w0 << 16);
-          a = fmaf(qv[1], __uint_as_float(w0 & 0xffff0000u), a);
-          a = fmaf(qv[2], __uint_as_float(w1 << 16), a);
-          a = fmaf(qv[3], __uint_as_float(w1 & 0xffff0000u), a);
-          a = fmaf(qv[4], __uint_as_float(w2 << 16), a);
-          a = fmaf(qv[5], __uint_as_float(w2 & 0xffff0000u), a);
-          a = fmaf(qv[6], __uint_as_float(w3 << 16), a);
-          pv[i] = fmaf(qv[7], __uint_as_float(w3 & 0xffff0000u), a);
-        }
-        // reduce over the 4 lanes of a key group: 8 partials -> lane b4 keeps chunks i = 2*b4, 2*b4+1
-        const bool u2 = b4 & 2, u1 = b4 & 1;
-        float w4[4], w2_[2];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float send = u2 ? pv[j] : pv[j + 4], keep = u2 ? pv[j + 4] : pv[j];
-          w4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float send = u1 ? w4[j] : w4[j + 2], keep = u1 ? w4[j + 2] : w4[j];
-          w2_[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-        }
-        // lane (u2,u1) holds chunks i = 4*u2 + 2*u1 + {0,1}
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int key = k0 + 8 * ((u2 ? 4 : 0) + (u1 ? 2 : 0) + j) + g;
-          if (key < pos) {
-            ssc[key] = w2_[j];
-            lmax = fmaxf(lmax, w2_[j]);
+          float d[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_bf16_16816(d, qa0, 0u, qa1, 0u, kk[i].x, kk[i].y);
+          mma_bf16_16816(d, qa2, 0u, qa3, 0u, kk[i].z, kk[i].w);
+          const int key = k0 + 8 * i + 2 * c;     // row 0 of the tile: lanes 0..3 hold keys 2c, 2c+1 of the octet
+          if (lane < 4) {
+            if (key < pos) ssc[key] = d[0], lmax = fmaxf(lmax, d[0]);
+            if (key + 1 < pos) ssc[key + 1] = d[1], lmax = fmaxf(lmax, d[1]);
           }
         }
       }
@@ -255,47 +327,45 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
       __syncwarp();
       float lsum = 0.f;
       for (int key = lane; key < pos; key += 32) {
-        const float pr = expf(ssc[key] - lmax);
+        // the normaliser uses the bf16-rounded probabilities that the tensor core will see
+        const float pr = __bfloat162float(__float2bfloat16_rn(expf(ssc[key] - lmax)));
         ssc[key] = pr;
         lsum += pr;
       }
+      for (int key = pos + lane; key < ((pos + 15) & ~15); key += 32) ssc[key] = 0.f;   // tail of the last key block
       p_self = expf(s_self - lmax);
       inv = 1.0f / (warp_sum(lsum) + p_self);
       __syncwarp();
-      float oa[8];
+      float oa[4][4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) oa[j] = 0.f;
+      for (int jn = 0; jn < 4; ++jn) oa[jn][0] = oa[jn][1] = oa[jn][2] = oa[jn][3] = 0.f;
+      const uint4* VB = reinterpret_cast<const uint4*>(V) + 2 * lane;   // block stride = 64 uint4
       for (int k0 = 0; k0 < pos; k0 += 64) {
-        uint4 vv[8];
-        float pr[8];
+        uint4 va[4], vc[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int key = k0 + 8 * i + g;
-          const bool ok = key < pos;
-          vv[i] = ok ? __ldcg(V8 + (size_t)key * 4) : make_uint4(0, 0, 0, 0);
-          pr[i] = ok ? ssc[key] : 0.f;
+        for (int i = 0; i < 4; ++i) {
+          const bool ok = k0 + 16 * i < pos;          // blocks past the last key are uninitialised: never touch them
+          va[i] = ok ? __ldcg(VB + (size_t)((k0 >> 4) + i) * 64) : make_uint4(0, 0, 0, 0);
+          vc[i] = ok ? __ldcg(VB + (size_t)((k0 >> 4) + i) * 64 + 1) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          oa[0] = fmaf(pr[i], __uint_as_float(vv[i].x << 16), oa[0]);
-          oa[1] = fmaf(pr[i], __uint_as_float(vv[i].x & 0xffff0000u), oa[1]);
-          oa[2] = fmaf(pr[i], __uint_as_float(vv[i].y << 16), oa[2]);
-          oa[3] = fmaf(pr[i], __uint_as_float(vv[i].y & 0xffff0000u), oa[3]);
-          oa[4] = fmaf(pr[i], __uint_as_float(vv[i].z << 16), oa[4]);
-          oa[5] = fmaf(pr[i], __uint_as_float(vv[i].z & 0xffff0000u), oa[5]);
-          oa[6] = fmaf(pr[i], __uint_as_float(vv[i].w << 16), oa[6]);
-          oa[7] = fmaf(pr[i], __uint_as_float(vv[i].w & 0xffff0000u), oa[7]);
+        for (int i = 0; i < 4; ++i) {
+          uint32_t pa0 = 0, pa2 = 0;
+          if (lane < 4 && k0 + 16 * i < pos) {
+            const float2 p0 = *reinterpret_cast<const float2*>(ssc + k0 + 16 * i + 2 * c);
+            const float2 p1 = *reinterpret_cast<const float2*>(ssc + k0 + 16 * i + 8 + 2 * c);
+            pa0 = pack_bf16(p0.x, p0.y), pa2 = pack_bf16(p1.x, p1.y);
+          }
+          mma_bf16_16816(oa[0], pa0, 0u, pa2, 0u, va[i].x, va[i].y);
+          mma_bf16_16816(oa[1], pa0, 0u, pa2, 0u, va[i].z, va[i].w);
+          mma_bf16_16816(oa[2], pa0, 0u, pa2, 0u, vc[i].x, vc[i].y);
+          mma_bf16_16816(oa[3], pa0, 0u, pa2, 0u, vc[i].z, vc[i].w);
         }
-      }
-#pragma unroll
-      for (int o_ = 4; o_ <= 16; o_ <<= 1) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) oa[j] += __shfl_xor_sync(0xffffffffu, oa[j], o_);
       }
       __syncwarp();
-      if (lane < 4) {
+      if (lane < 4) {   // row 0 of the output tile: lane c holds channels 8 jn + 2c, 8 jn + 2c + 1
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sx[8 * lane + j] = oa[j];
+        for (int jn = 0; jn < 4; ++jn) *reinterpret_cast<float2*>(sx + 8 * jn + 2 * c) = make_float2(oa[jn][0], oa[jn][1]);
       }
       __syncwarp();
       osum = sx[lane] + p_self * v;
@@ -305,18 +375,37 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
     sx[lane] = o;
     __syncwarp();
     float y;
-    matvec_packed<G_E, 1>(sx, w.proj_wP, w.proj_b, lane, &y);
+    if constexpr (WS) {
+      matvec_mma<G_E, G_E>(wf + l * WF_UINT4 + WF_PROJ, sx, sh, lane);
+      __syncwarp();
+      y = sh[lane] + __ldg(w.proj_b + lane);
+    } else {
+      matvec_packed<G_E, 1>(sx, w.proj_wP, w.proj_b, lane, &y);
+    }
     x += y;
     __syncwarp();
     // ---- MLP ----
     sx[lane] = layer_norm(x, w.ln2_w, w.ln2_b, lane);
     __syncwarp();
     float hh[4];
-    matvec_packed<G_E, 4>(sx, w.fc_wP, w.fc_b, lane, hh);
+    if constexpr (WS) {
+      matvec_mma<G_E, G_FF>(wf + l * WF_UINT4 + WF_FC, sx, sh, lane);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) hh[i] = sh[32 * i + lane] + __ldg(w.fc_b + 32 * i + lane);
+    } else {
+      matvec_packed<G_E, 4>(sx, w.fc_wP, w.fc_b, lane, hh);
+    }
     sh[lane] = gelu_new(hh[0]), sh[32 + lane] = gelu_new(hh[1]), sh[64 + lane] = gelu_new(hh[2]), sh[96 + lane] = gelu_new(hh[3]);
     __syncwarp();
     float y2;
-    matvec_packed<G_FF, 1>(sh, w.fc2_wP, w.fc2_b, lane, &y2);
+    if constexpr (WS) {
+      matvec_mma<G_FF, G_E>(wf + l * WF_UINT4 + WF_FC2, sh, sx, lane);
+      __syncwarp();
+      y2 = sx[lane] + __ldg(w.fc2_b + lane);
+    } else {
+      matvec_packed<G_FF, 1>(sh, w.fc2_wP, w.fc2_b, lane, &y2);
+    }
     x += y2;
     __syncwarp();
   }
@@ -419,14 +508,30 @@ struct OnlineGptParams {
   dpt_gpt2_online_dump_t out;
 };
 
-template <bool BF16>
-__global__ void __launch_bounds__(G_THREADS) gpt2_online_kernel(const OnlineGptParams p) {
+// WS (precision 1): ONE CTA of GW_WARPS warps per SM shares the bf16 weight fragments of all layers in shared memory
+// (24 KB per layer) and every warp runs its env's projections on the tensor cores from there.
+constexpr int GW_WARPS = 24;
+constexpr int GW_THREADS = GW_WARPS * 32;
+
+template <bool BF16, bool WS>
+__global__ void __launch_bounds__(WS ? GW_THREADS : G_THREADS, WS ? 1 : (BF16 ? DPT_GPT2_MINB_BF16 : DPT_GPT2_MINB_F32))
+    gpt2_online_kernel(const OnlineGptParams p) {
   extern __shared__ __align__(16) float g_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int env = blockIdx.x * G_WARPS + warp;
-  if (env >= p.N) return;
   const Gpt2Dev& m = p.m;
-  const WarpScratch ws = warp_scratch(g_smem, warp, p.Tpad);
+  const uint4* wf = nullptr;
+  float* scratch = g_smem;
+  if constexpr (WS) {
+    uint4* dst = reinterpret_cast<uint4*>(g_smem);
+    for (int l = 0; l < m.L; ++l)
+      for (int i = threadIdx.x; i < WF_UINT4; i += GW_THREADS) dst[l * WF_UINT4 + i] = __ldg(m.layer[l].wfrag + i);
+    wf = dst;
+    scratch = g_smem + (size_t)m.L * WF_UINT4 * 4;
+    __syncthreads();
+  }
+  const int env = blockIdx.x * (WS ? GW_WARPS : G_WARPS) + warp;
+  if (env >= p.N) return;
+  const WarpScratch ws = warp_scratch(scratch, warp, p.Tpad);
   char* kv = reinterpret_cast<char*>(p.kv) + (size_t)env * m.L * 2 * G_E * p.Tpad * (BF16 ? 2 : 4);
   const int du = m.du, H = p.H, N = p.N;
   const uint64_t gid = p.env_id0 + (uint64_t)env;
@@ -449,7 +554,7 @@ __global__ void __launch_bounds__(G_THREADS) gpt2_online_kernel(const OnlineGptP
   for (int h = 0; h < H; ++h) {
     float x = e_bias + e_state + __ldg(m.wpe + (size_t)h * G_E + lane);
     if (h > 0) x += __ldg(m.embed_wT + (1 + a_prev) * G_E + lane) + e_next + e_rew * r_prev;
-    x = token_forward<BF16>(m, x, h, kv, p.Tpad, ws.sx, ws.sh, ws.ssc, lane);
+    x = token_forward<BF16, WS>(m, x, h, kv, p.Tpad, ws.sx, ws.sh, ws.ssc, lane, wf);
     const float lg = head_logits(m, x, ws.sx, lane);
     if (p.out.logits && lane < du) p.out.logits[((size_t)h * N + env) * du + lane] = lg;
     int a;
@@ -546,7 +651,7 @@ extern "C" int dpt_gpt2_create(const dpt_gpt2_weights_t* w, dpt_gpt2_t** out, vo
   cudaStream_t st = (cudaStream_t)stream;
   const int L = w->n_layer, du = w->action_dim;
   const size_t per_layer = 4 * G_E + G_E * 3 * G_E + 3 * G_E + G_E * G_E + G_E + G_E * G_FF + G_FF + G_FF * G_E + G_E;
-  const size_t total = (size_t)w->n_positions * G_E + (size_t)din * G_E + G_E + (size_t)G_E * du + du + 2 * G_E + L * (2 * per_layer + WIMG_BYTES / 4) + 4 * (16 + 17 * (size_t)L);
+  const size_t total = (size_t)w->n_positions * G_E + (size_t)din * G_E + G_E + (size_t)G_E * du + du + 2 * G_E + L * (2 * per_layer + WIMG_BYTES / 4 + WF_UINT4 * 4) + 4 * (16 + 18 * (size_t)L);
   dpt_gpt2* m = new dpt_gpt2();
   DPT_CUDA(cudaMalloc(&m->blob, total * sizeof(float)));
   float* cur = m->blob;
@@ -592,6 +697,14 @@ extern "C" int dpt_gpt2_create(const dpt_gpt2_weights_t* w, dpt_gpt2_t** out, vo
     unsigned char* img = reinterpret_cast<unsigned char*>(take(WIMG_BYTES / 4));   // tcgen05 B-operand image (bf16)
     gpt2_pack_wimg(w->attn_w[l], w->proj_w[l], w->fc_w[l], w->fc2_w[l], img, st);
     lw.wimg = reinterpret_cast<const uint4*>(img);
+    uint4* frag = reinterpret_cast<uint4*>(take((size_t)WF_UINT4 * 4));                // mma.sync B fragments (bf16)
+    auto packf = [&](const float* src, int K, int N, int off) {
+      const int n = (K / 16) * (N / 16) * 32;
+      pack_wfrag_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, frag + off, K, N);
+    };
+    packf(w->attn_w[l], G_E, 3 * G_E, WF_QKV), packf(w->proj_w[l], G_E, G_E, WF_PROJ);
+    packf(w->fc_w[l], G_E, G_FF, WF_FC), packf(w->fc2_w[l], G_FF, G_E, WF_FC2);
+    lw.wfrag = frag;
   }
   DPT_LAUNCH_CHECK();
   *out = m;
@@ -694,14 +807,23 @@ extern "C" int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, double va
   p.cum_means = cum_means, p.regret = regret_sums;
   if (inject) p.in = *inject;
   if (dump) p.out = *dump;
-  const size_t smem = (size_t)G_WARPS * (G_E + G_FF + p.Tpad) * sizeof(float);
-  const void* kern = precision ? (const void*)gpt2_online_kernel<true> : (const void*)gpt2_online_kernel<false>;
+  const size_t per_warp = (size_t)(G_E + G_FF + p.Tpad) * sizeof(float);
+  const size_t smem_ws = (size_t)m->dev.L * WF_UINT4 * 16 + GW_WARPS * per_warp;
+  if (precision && smem_ws <= 227 * 1024) {   // weight fragments of all layers + 24 warps' scratch fit one SM
+    int rc = launch_smem((const void*)gpt2_online_kernel<true, true>, smem_ws);
+    if (rc != DPT_OK) return rc;
+    gpt2_online_kernel<true, true><<<(N + GW_WARPS - 1) / GW_WARPS, GW_THREADS, smem_ws, (cudaStream_t)stream>>>(p);
+    DPT_LAUNCH_CHECK();
+    return DPT_OK;
+  }
+  const size_t smem = G_WARPS * per_warp;
+  const void* kern = precision ? (const void*)gpt2_online_kernel<true, false> : (const void*)gpt2_online_kernel<false, false>;
   int rc = launch_smem(kern, smem);
   if (rc != DPT_OK) return rc;
   if (precision)
-    gpt2_online_kernel<true><<<(N + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
+    gpt2_online_kernel<true, false><<<(N + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
   else
-    gpt2_online_kernel<false><<<(N + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
+    gpt2_online_kernel<false, false><<<(N + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
   DPT_LAUNCH_CHECK();
   return DPT_OK;
 }

@@ -19,6 +19,7 @@ struct LayerW {
   const float4 *attn_wP, *proj_wP, *fc_wP, *fc2_wP;
   const float *attn_w, *proj_w, *fc_w, *fc2_w;   // original [in][out] layouts (dense fp32 kernel)
   const uint4* wimg;  // bf16 B-operand image for the tcgen05 dense forward (see gpt2_dense.cu), 40 KB
+  const uint4* wfrag; // bf16 mma.sync B fragments for the KV-cached decode (see gpt2.cu, WF_*), 24 KB
 };
 
 struct Gpt2Dev {
@@ -35,6 +36,14 @@ struct dpt_gpt2 {
 };
 
 namespace dpt {
+// LayerW::wfrag, in uint4 units: for every Conv1D weight W[K][N] and every (k-step ks of 16 inputs, pair ntp of two
+// 8-output tiles) one uint4 per lane = {b0, b1 of tile 2 ntp, b0, b1 of tile 2 ntp + 1} of mma.m16n8k16 (col-major B):
+// lane (g = lane / 4, c = lane % 4): b0 = W[16 ks + 2c, +1][n], b1 = W[16 ks + 2c + 8, +9][n], n = 8 tile + g.
+constexpr int WF_QKV = 0;      // K = 32, N = 96 : 2 x 6 groups of 32 lanes
+constexpr int WF_PROJ = 384;   // K = 32, N = 32 : 2 x 2
+constexpr int WF_FC = 512;     // K = 32, N = 128: 2 x 8
+constexpr int WF_FC2 = 1024;   // K = 128, N = 32: 8 x 2
+constexpr int WF_UINT4 = 1536; // 24576 B per layer
 // byte layout of LayerW::wimg (K64 tiles, see umma.cuh): B[n][k] = W[k][n] for every Conv1D weight W[in][out]
 constexpr int WIMG_QKV = 0;            // [96 rows x 64]   12288 B
 constexpr int WIMG_PROJ = 12288;       // [32 rows x 64]    4096 B
