@@ -22,6 +22,8 @@
 // exceed L2), ~0.9 FLOP/B -- HBM-bound, not tensor-bound.
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -510,7 +512,10 @@ struct OnlineGptParams {
 
 // WS (precision 1): ONE CTA of GW_WARPS warps per SM shares the bf16 weight fragments of all layers in shared memory
 // (24 KB per layer) and every warp runs its env's projections on the tensor cores from there.
-constexpr int GW_WARPS = 24;
+#ifndef DPT_GPT2_GW_WARPS
+#define DPT_GPT2_GW_WARPS 24
+#endif
+constexpr int GW_WARPS = DPT_GPT2_GW_WARPS;
 constexpr int GW_THREADS = GW_WARPS * 32;
 
 template <bool BF16, bool WS>
@@ -524,12 +529,12 @@ __global__ void __launch_bounds__(WS ? GW_THREADS : G_THREADS, WS ? 1 : (BF16 ? 
   if constexpr (WS) {
     uint4* dst = reinterpret_cast<uint4*>(g_smem);
     for (int l = 0; l < m.L; ++l)
-      for (int i = threadIdx.x; i < WF_UINT4; i += GW_THREADS) dst[l * WF_UINT4 + i] = __ldg(m.layer[l].wfrag + i);
+      for (int i = threadIdx.x; i < WF_UINT4; i += blockDim.x) dst[l * WF_UINT4 + i] = __ldg(m.layer[l].wfrag + i);
     wf = dst;
     scratch = g_smem + (size_t)m.L * WF_UINT4 * 4;
     __syncthreads();
   }
-  const int env = blockIdx.x * (WS ? GW_WARPS : G_WARPS) + warp;
+  const int env = blockIdx.x * (int)(blockDim.x >> 5) + warp;   // WS: the host picks <= GW_WARPS warps per CTA
   if (env >= p.N) return;
   const WarpScratch ws = warp_scratch(scratch, warp, p.Tpad);
   char* kv = reinterpret_cast<char*>(p.kv) + (size_t)env * m.L * 2 * G_E * p.Tpad * (BF16 ? 2 : 4);
@@ -812,7 +817,10 @@ extern "C" int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, double va
   if (precision && smem_ws <= 227 * 1024) {   // weight fragments of all layers + 24 warps' scratch fit one SM
     int rc = launch_smem((const void*)gpt2_online_kernel<true, true>, smem_ws);
     if (rc != DPT_OK) return rc;
-    gpt2_online_kernel<true, true><<<(N + GW_WARPS - 1) / GW_WARPS, GW_THREADS, smem_ws, (cudaStream_t)stream>>>(p);
+    // one CTA per SM: keep the wave count of 24-warp CTAs but spread the envs evenly over those waves
+    const long per_wave = (long)sm_count() * GW_WARPS, waves = (N + per_wave - 1) / per_wave;
+    const int nw = (int)std::min<long>(GW_WARPS, std::max<long>(1, (N + waves * sm_count() - 1) / (waves * sm_count())));
+    gpt2_online_kernel<true, true><<<(N + nw - 1) / nw, nw * 32, smem_ws, (cudaStream_t)stream>>>(p);
     DPT_LAUNCH_CHECK();
     return DPT_OK;
   }
