@@ -106,8 +106,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {   // lo -> b
 }
 
 // y[N] = x[K] W on the tensor cores, one warp, weights as pre-arranged bf16 B fragments in shared memory (WF_* layout
-// in gpt2_model.cuh).  The activation vector is row 0 of the A tile (lanes 0..3); its products come out in row 0 of
-// the accumulator, again lanes 0..3, and go back to shared memory.  xin / yout: 8 B-aligned, distinct buffers.
+// in gpt2_model.cuh).  xin / yout: 8 B-aligned, distinct buffers.
 template <int K, int N>
 __device__ __forceinline__ void matvec_mma(const uint4* wf, const float* xin, float* yout, int lane) {
   const int c = lane & 3;
@@ -121,19 +120,17 @@ __device__ __forceinline__ void matvec_mma(const uint4* wf, const float* xin, fl
       a0[ks] = pack_bf16(u.x, u.y), a2[ks] = pack_bf16(w.x, w.y);
     }
   }
+  // transposed product y^T = W^T x^T: the 16 x 16 weight tile is the A operand (16 outputs per HMMA), x is column 0 of
+  // B (lanes 0..3), the outputs are column 0 of the accumulator: lanes with c == 0 hold outputs g and g + 8
 #pragma unroll
   for (int ntp = 0; ntp < N / 16; ++ntp) {
-    float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ks = 0; ks < K / 16; ++ks) {
       const uint4 bw = wf[(ks * (N / 16) + ntp) * 32 + lane];
-      mma_bf16_16816(d0, a0[ks], 0u, a2[ks], 0u, bw.x, bw.y);
-      mma_bf16_16816(d1, a0[ks], 0u, a2[ks], 0u, bw.z, bw.w);
+      mma_bf16_16816(d, bw.x, bw.z, bw.y, bw.w, a0[ks], a2[ks]);
     }
-    if (lane < 4) {
-      *reinterpret_cast<float2*>(yout + 16 * ntp + 2 * c) = make_float2(d0[0], d0[1]);
-      *reinterpret_cast<float2*>(yout + 16 * ntp + 8 + 2 * c) = make_float2(d1[0], d1[1]);
-    }
+    if (c == 0) yout[16 * ntp + (lane >> 2)] = d[0], yout[16 * ntp + 8 + (lane >> 2)] = d[2];
   }
 }
 
@@ -271,8 +268,9 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
     } else {
       __syncwarp();
       // bf16 cache on the tensor cores (mma.sync m16n8k16, fp32 accumulate).  The decode is a GEMV per env (one
-      // query row against that env's private keys), so only row 0 of the 16-row A tile is live; what the MMA buys
-      // is instruction count: 2 HMMA replace ~90 unpack / FMA / shuffle instructions per 8 keys.
+      // query against that env's private keys), so the products are formed transposed -- keys / channels / outputs are
+      // the 16 rows of the A tile and the single query (or probability, or activation) vector is column 0 of B; what
+      // the MMA buys is instruction count: 2 HMMA replace ~180 unpack / FMA / shuffle instructions per 16 keys.
       //   K cache: one 64 B row per key, channels permuted so that lane (g = lane/4, c = lane%4) reads the B
       //            fragments of key g for both k-steps with ONE 16 B load (kperm below).
       //   V cache: blocks of 16 keys x 32 channels (1 KB) stored as [channel-in-octet g][key pair c][octet j]
@@ -297,7 +295,7 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
       q *= 0.17677669529663687f;
       sx[lane] = q;
       __syncwarp();
-      uint32_t qa0 = 0, qa1 = 0, qa2 = 0, qa3 = 0;   // A fragments (row 0 only): k-step 0 (a0, a2), k-step 1 (a0, a2)
+      uint32_t qa0 = 0, qa1 = 0, qa2 = 0, qa3 = 0;   // q as column 0 of the B tile: k-step 0 (b0, b1), k-step 1 (b0, b1)
       if (lane < 4) {
         qa0 = pack_bf16(sx[2 * c], sx[2 * c + 1]), qa1 = pack_bf16(sx[2 * c + 8], sx[2 * c + 9]);
         qa2 = pack_bf16(sx[2 * c + 16], sx[2 * c + 17]), qa3 = pack_bf16(sx[2 * c + 24], sx[2 * c + 25]);
@@ -312,15 +310,16 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
         // P V pass below then waits an L2 rather than a DRAM latency (this mode is latency-, not bandwidth-bound)
         if (DPT_GPT2_BF16_PREFETCH_V && k0 + 16 * (lane >> 3) < pos)
           prefetch_l2(reinterpret_cast<const unsigned char*>(V) + (size_t)(k0 >> 4) * 1024 + lane * 128);
+        // scores^T = K q^T: 16 keys are the rows of the A tile (octets 2m and 2m + 1), q is column 0 of B
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int mt = 0; mt < 4; ++mt) {
           float d[4] = {0.f, 0.f, 0.f, 0.f};
-          mma_bf16_16816(d, qa0, 0u, qa1, 0u, kk[i].x, kk[i].y);
-          mma_bf16_16816(d, qa2, 0u, qa3, 0u, kk[i].z, kk[i].w);
-          const int key = k0 + 8 * i + 2 * c;     // row 0 of the tile: lanes 0..3 hold keys 2c, 2c+1 of the octet
-          if (lane < 4) {
+          mma_bf16_16816(d, kk[2 * mt].x, kk[2 * mt + 1].x, kk[2 * mt].y, kk[2 * mt + 1].y, qa0, qa1);
+          mma_bf16_16816(d, kk[2 * mt].z, kk[2 * mt + 1].z, kk[2 * mt].w, kk[2 * mt + 1].w, qa2, qa3);
+          const int key = k0 + 16 * mt + g;       // column 0 of the tile: lanes with c == 0 hold keys g and g + 8
+          if (c == 0) {
             if (key < pos) ssc[key] = d[0], lmax = fmaxf(lmax, d[0]);
-            if (key + 1 < pos) ssc[key + 1] = d[1], lmax = fmaxf(lmax, d[1]);
+            if (key + 8 < pos) ssc[key + 8] = d[2], lmax = fmaxf(lmax, d[2]);
           }
         }
       }
@@ -338,9 +337,9 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
       p_self = expf(s_self - lmax);
       inv = 1.0f / (warp_sum(lsum) + p_self);
       __syncwarp();
-      float oa[4][4];
+      float oa[2][4];   // out^T = V^T p^T: channel tiles 0..15 and 16..31 are the rows, p is column 0 of B
 #pragma unroll
-      for (int jn = 0; jn < 4; ++jn) oa[jn][0] = oa[jn][1] = oa[jn][2] = oa[jn][3] = 0.f;
+      for (int jn = 0; jn < 2; ++jn) oa[jn][0] = oa[jn][1] = oa[jn][2] = oa[jn][3] = 0.f;
       const uint4* VB = reinterpret_cast<const uint4*>(V) + 2 * lane;   // block stride = 64 uint4
       for (int k0 = 0; k0 < pos; k0 += 64) {
         uint4 va[4], vc[4];
@@ -358,16 +357,14 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
             const float2 p1 = *reinterpret_cast<const float2*>(ssc + k0 + 16 * i + 8 + 2 * c);
             pa0 = pack_bf16(p0.x, p0.y), pa2 = pack_bf16(p1.x, p1.y);
           }
-          mma_bf16_16816(oa[0], pa0, 0u, pa2, 0u, va[i].x, va[i].y);
-          mma_bf16_16816(oa[1], pa0, 0u, pa2, 0u, va[i].z, va[i].w);
-          mma_bf16_16816(oa[2], pa0, 0u, pa2, 0u, vc[i].x, vc[i].y);
-          mma_bf16_16816(oa[3], pa0, 0u, pa2, 0u, vc[i].z, vc[i].w);
+          mma_bf16_16816(oa[0], va[i].x, va[i].z, va[i].y, va[i].w, pa0, pa2);
+          mma_bf16_16816(oa[1], vc[i].x, vc[i].z, vc[i].y, vc[i].w, pa0, pa2);
         }
       }
       __syncwarp();
-      if (lane < 4) {   // row 0 of the output tile: lane c holds channels 8 jn + 2c, 8 jn + 2c + 1
+      if (c == 0) {   // column 0 of the output tiles: lane (g, 0) holds channels 16 jn + g and 16 jn + g + 8
 #pragma unroll
-        for (int jn = 0; jn < 4; ++jn) *reinterpret_cast<float2*>(sx + 8 * jn + 2 * c) = make_float2(oa[jn][0], oa[jn][1]);
+        for (int jn = 0; jn < 2; ++jn) sx[16 * jn + g] = oa[jn][0], sx[16 * jn + 8 + g] = oa[jn][2];
       }
       __syncwarp();
       osum = sx[lane] + p_self * v;
