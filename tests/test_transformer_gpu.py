@@ -453,3 +453,26 @@ def test_darkroom_offline_eval(dpt, name):
                               _np(out["sample"]["u"]), [int(t["perm_index"]) for t in trajs] if permuted else None, sample=True)
     assert np.array_equal(_np(out["returns_sample"]).astype(np.float64), want)
     assert np.all(res["Learner"] <= res["Opt"]) and np.all(res["Learner (greedy)"] <= res["Opt"])
+
+
+def test_bf16_decode_fallback_geometry(dpt):
+    """precision = 1 beyond what one SM's shared memory holds (weight fragments of all layers + 24 warps of score
+    scratch): the loop falls back to 4-warp CTAs with the weights read through L1.  Same 2e-2 bar: the logits the loop
+    saw at the last steps against a fp32 forward (token-sequential kernel, > 512 tokens) over the context it built."""
+    from dpt_b200.models.net import Transformer
+    torch.manual_seed(11)
+    H, d, L, N = 1210, 5, 4, 6
+    m = Transformer({"horizon": H, "state_dim": 1, "action_dim": d, "n_layer": L, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True})
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if "wte" not in k:
+                p.add_(0.05 * torch.randn_like(p))
+    means, _, _ = dpt.kernels.bandit_sample_means(N, d, 3, 0)
+    m.precision = 1
+    out = m.online_loop(means, H, 0.3, True, 3, 0, dump=True)
+    m.precision = 0
+    for h in (H - 1, 700, 64):
+        b = {k: out[k][:, :h] for k in ("context_states", "context_actions", "context_next_states", "context_rewards")}
+        b["query_states"] = torch.ones(N, 1, device="cuda")
+        _close(_np(out["noise"]["logits"][h]), _np(m(b)), 2e-2)
+    assert float(out["context_actions"].sum(-1).min()) == 1.0
