@@ -1,4 +1,9 @@
-"""Darkroom controllers with the reference's interface (ctrls/ctrl_darkroom.py)."""
+"""Darkroom controllers with the reference's interface (ctrls/ctrl_darkroom.py).
+
+``DarkroomTransformerController.act`` is the reference-shaped per-step path (one dense forward per env step,
+dpt_gpt2_forward, then a host-side categorical draw on the ``np.random`` stream); the evaluation loops in
+``evals/eval_darkroom.py`` recognise this class and replace the whole episode by one batched forward over all
+query states plus one rollout launch (``fused`` attribute, default on)."""
 import numpy as np
 import torch
 
@@ -7,48 +12,48 @@ from .ctrl_bandit import Controller
 
 
 class DarkroomOptPolicy(Controller):
-    """ctrls/ctrl_darkroom.py:10-20."""
+    """ctrls/ctrl_darkroom.py:10-20: always the env's own optimal action (x first, then y, then stay)."""
 
     def __init__(self, env):
         super().__init__()
-        self.env = env
-        self.goal = env.goal
+        self.env, self.goal = env, env.goal
 
     def reset(self):
-        return
+        """Stateless."""
 
     def act(self, state):
         return self.env.opt_action(state)
 
 
 class DarkroomTransformerController(Controller):
-    """ctrls/ctrl_darkroom.py:23-66: logits = model(batch) with the current states as query
-    (dpt_gpt2_forward), then softmax(logits / temp) + np.random.choice per env, or argmax."""
+    """ctrls/ctrl_darkroom.py:23-66.  ``set_batch`` (inherited) stores the context; ``act`` queries the model with
+    the current state(s) at sequence position 0 and turns the 5 logits into a one-hot action."""
 
     def __init__(self, model, batch_size=1, sample=False):
-        self.model = model
-        self.state_dim = model.config["state_dim"]
-        self.action_dim = model.config["action_dim"]
-        self.horizon = model.horizon
+        cfg = model.config
+        self.model, self.batch_size, self.sample = model, batch_size, sample
+        self.state_dim, self.action_dim, self.horizon = cfg["state_dim"], cfg["action_dim"], model.horizon
+        self.temp = 1.0          # softmax temperature of the sampled policy (:28)
+        # the reference feeds a zero pad tensor through the batch dict (:29, :44); kept for key compatibility
         self.zeros = torch.zeros(batch_size, self.state_dim ** 2 + self.action_dim + 1, device=kernels._dev())
-        self.sample = sample
-        self.temp = 1.0
-        self.batch_size = batch_size
+
+    def _logits(self, state):
+        query = torch.as_tensor(np.array(state)).float().to(self.zeros.device)
+        self.batch["query_states"] = query[None, :] if self.batch_size == 1 else query
+        self.batch["zeros"] = self.zeros
+        return self.model(self.batch).cpu().numpy().astype(np.float64)
+
+    def _choose(self, logits):
+        if not self.sample:
+            return np.argmax(logits, axis=-1)                                # :62
+        scaled = logits / self.temp
+        weights = np.exp(scaled - scaled.max(axis=-1, keepdims=True))       # scipy.special.softmax (:56)
+        weights /= weights.sum(axis=-1, keepdims=True)
+        arms = np.arange(self.action_dim)
+        return np.array([np.random.choice(arms, p=row) for row in weights])  # one draw per env, env order (:57-59)
 
     def act(self, state):
-        self.batch["zeros"] = self.zeros
-        states = torch.as_tensor(np.array(state)).float().to(self.zeros.device)
-        if self.batch_size == 1:
-            states = states[None, :]
-        self.batch["query_states"] = states
-        actions = self.model(self.batch).cpu().numpy().astype(np.float64)
-        if self.sample:
-            z = actions / self.temp
-            e = np.exp(z - z.max(axis=-1, keepdims=True))
-            probs = e / e.sum(axis=-1, keepdims=True)
-            action_indices = [np.random.choice(np.arange(self.action_dim), p=p) for p in probs]
-        else:
-            action_indices = np.argmax(actions, axis=-1)
-        out = np.zeros((self.batch_size, self.action_dim))
-        out[np.arange(self.batch_size), action_indices] = 1.0
-        return out[0] if self.batch_size == 1 else out
+        picked = self._choose(self._logits(state))
+        onehot = np.zeros((self.batch_size, self.action_dim))
+        onehot[np.arange(self.batch_size), picked] = 1.0
+        return onehot[0] if self.batch_size == 1 else onehot

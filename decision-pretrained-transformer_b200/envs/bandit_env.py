@@ -19,13 +19,10 @@ def sample(dim, H, var, type="uniform"):
     """envs/bandit_env.py:10-18.  (The task draw itself is host-side numpy like the reference;
     use ``collect_data.generate_bandit_histories`` / ``kernels.bandit_sample_means`` for the
     batched device draw.)"""
-    if type == "uniform":
-        means = np.random.uniform(0, 1, dim)
-    elif type == "bernoulli":
-        means = np.random.beta(1, 1, dim)
-    else:
+    draw = {"uniform": lambda: np.random.uniform(0, 1, dim), "bernoulli": lambda: np.random.beta(1, 1, dim)}.get(type)
+    if draw is None:
         raise NotImplementedError
-    return BanditEnv(means, H, var=var, type=type)
+    return BanditEnv(draw(), H, var=var, type=type)
 
 
 def sample_linear(arms, H, var):
@@ -42,19 +39,14 @@ class BanditEnv(BaseEnv):
         if type not in _TYPES:
             raise NotImplementedError
         self.means = np.asarray(means)
-        self.opt_a_index = int(np.argmax(self.means))
-        self.opt_a = np.zeros(self.means.shape)
-        self.opt_a[self.opt_a_index] = 1.0
-        self.dim = len(self.means)
-        self.state = np.array([1])
-        self.var = var
-        self.dx = 1
-        self.du = self.dim
-        self.topk = False
-        self.type = type
-        self.H_context = H   # "some naming issue here" (:44-47): an episode is ONE pull
-        self.H = 1
-        self._vec = None
+        self.dim = self.du = len(self.means)
+        self.dx, self.state = 1, np.array([1])                     # the bandit "state" is the constant [1]
+        self.opt_a_index = int(np.argmax(self.means))              # first maximum
+        self.opt_a = np.eye(self.dim)[self.opt_a_index].reshape(self.means.shape)
+        self.var, self.type, self.topk = var, type, False
+        # the reference's naming (:44-47): H_context is the context length, an "episode" (H) is ONE pull
+        self.H_context, self.H = H, 1
+        self._vec = None                                           # lazily created 1-env device wrapper
 
     def get_arm_value(self, u):
         return np.sum(self.means * u)
@@ -73,19 +65,20 @@ class BanditEnv(BaseEnv):
         return self.state.copy(), float(r[0])
 
     def step(self, action):
+        """:66-74"""
         if self.current_step >= self.H:
             raise ValueError("Episode has already ended")
-        _, r = self.transit(self.state, action)
+        _, reward = self.transit(self.state, action)
         self.current_step += 1
-        done = self.current_step >= self.H
-        return self.state.copy(), r, done, {}
+        return self.state.copy(), reward, self.current_step >= self.H, {}
 
     def deploy_eval(self, ctrl):
-        tmp = self.var      # no variance during evaluation (:76-82)
-        self.var = 0.0
-        res = self.deploy(ctrl)
-        self.var = tmp
-        return res
+        """:76-82 -- evaluation pulls are noise-free: var is zeroed for the duration of the rollout."""
+        saved, self.var = self.var, 0.0
+        try:
+            return self.deploy(ctrl)
+        finally:
+            self.var = saved
 
 
 class LinearBanditEnv(BanditEnv):

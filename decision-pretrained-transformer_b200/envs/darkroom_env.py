@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from .. import kernels
-from .base_env import BaseEnv
+from .base_env import BaseEnv, rollout
 
 
 class _Discrete:
@@ -32,17 +32,16 @@ class DarkroomEnv(BaseEnv):
         self._perm_index = None
 
     def sample_state(self):
+        """:23-24 -- a uniform grid cell from the host ``np.random`` stream (the fused collection draws on the device)."""
         return np.random.randint(0, self.dim, 2)
 
     def sample_action(self):
-        i = np.random.randint(0, 5)
-        a = np.zeros(self.action_space.n)
-        a[i] = 1
-        return a
+        """:26-30 -- a uniform one-hot action."""
+        return np.eye(self.action_space.n)[np.random.randint(0, 5)]
 
     def reset(self):
-        self.current_step = 0
-        self.state = np.array([0, 0])
+        """:32-35 -- every episode starts in the corner (0, 0)."""
+        self.current_step, self.state = 0, np.array([0, 0])
         return self.state
 
     def _perm_arg(self):
@@ -54,12 +53,12 @@ class DarkroomEnv(BaseEnv):
         return ns[0].cpu().numpy().astype(np.int64), int(r[0])
 
     def step(self, action):
+        """:57-64"""
         if self.current_step >= self.horizon:
             raise ValueError("Episode has already ended")
-        self.state, r = self.transit(self.state, action)
+        self.state, reward = self.transit(self.state, action)
         self.current_step += 1
-        done = self.current_step >= self.horizon
-        return self.state.copy(), r, done, {}
+        return self.state.copy(), reward, self.current_step >= self.horizon, {}
 
     def get_obs(self):
         return self.state.copy()
@@ -127,15 +126,7 @@ class DarkroomEnvVec(BaseEnv):
         return next_obs, [int(x) for x in r], dones, {}
 
     def deploy(self, ctrl):
-        ob = self.reset()
-        obs, acts, next_obs, rews = [], [], [], []
-        done = False
-        while not done:
-            act = ctrl.act(ob)
-            obs.append(ob)
-            acts.append(act)
-            ob, rew, done, _ = self.step(act)
-            done = all(done)
-            rews.append(rew)
-            next_obs.append(ob)
-        return np.stack(obs, axis=1), np.stack(acts, axis=1), np.stack(next_obs, axis=1), np.stack(rews, axis=1)
+        """envs/darkroom_env.py:151-175: ``ctrl.act`` sees the list of all envs' states; the four results are
+        stacked env-major: obs [N,horizon,2], acts [N,horizon,5], next_obs [N,horizon,2], rews [N,horizon]."""
+        columns = tuple(zip(*rollout(self, ctrl, all_done=all)))
+        return tuple(np.stack(col, axis=1) for col in columns)
