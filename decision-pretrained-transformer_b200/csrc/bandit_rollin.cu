@@ -216,11 +216,15 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_fast(const RollinPar
   const bool inj_actions = (MODE == MODE_INJECT) && p.in.actions != nullptr;
   float2 st_r = make_float2(0.f, 0.f), st_r2 = make_float2(0.f, 0.f);   // per pair component, packed f32x2 updates
   int st_opt = 0;
-  int e = 0, c = warp;   // (env, chunk) of this warp's task, advanced without a division
-  while (c >= chunks) c -= chunks, ++e;
-  for (; e < ne; c += RB_WARPS) {
-    while (c >= chunks) c -= chunks, ++e;
-    if (e >= ne) break;
+  // (env, chunk) of this warp's task: task index t = warp + i * RB_WARPS = e * chunks + c, advanced by the
+  // constant (de, dc) = divmod(RB_WARPS, chunks) with one predicated carry -- no division, no data-dependent loop
+  const int de = RB_WARPS / chunks, dc = RB_WARPS - de * chunks;
+  int e = warp / chunks, c = warp - e * chunks;
+  for (; e < ne; e += de, c += dc) {
+    if (c >= chunks) {
+      c -= chunks, ++e;
+      if (e >= ne) break;
+    }
     const int env = env0 + e;
     const int h0 = c * 64 + 2 * lane;
     const size_t row = (size_t)env * H + h0;
