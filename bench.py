@@ -308,6 +308,7 @@ def main():
     for i in range(e2e_steps):
         kernels.bandit_rollin_host(means_host, H, VAR, seed + 100 + i, env_id0, out=host_out, scratch=scratch)
     e1.record()
+    d2h_last = int(dpt_b200._lib.lib().dpt_bandit_rollin_host_last_d2h_bytes())
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
@@ -315,9 +316,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t[0])
     e2e = {"value": world * N * H * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": N * DIM * 4,
-           # actions + rewards cross PCIe; the constant state columns are filled on the host
-           "d2h_bytes_per_step": N * H * 4 * (DIM + 1), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-           "api": "dpt_bandit_rollin_host (pinned host buffers, chunked H2D/kernel/D2H pipeline)"}
+           # what crossed PCIe in the last timed call: chunks returned by DMA carry actions + rewards (4*(d+1) B per
+           # step), chunks returned in compact form 5 B per step (expanded by host threads); the constant state
+           # columns are always written on the host
+           "d2h_bytes_per_step": d2h_last, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+           "api": "dpt_bandit_rollin_host (pinned host buffers, chunked H2D/kernel/D2H pipeline, hybrid DMA / host expansion)"}
 
     for w_ in pending:
         w_.wait()

@@ -36,6 +36,7 @@ struct RollinParams {
   uint64_t env_id0;
   int N, H, d, envs_per_cta;
   float *ctx_s, *ctx_a, *ctx_ns, *ctx_r;
+  uint8_t* acts_u8;  // compact form (host pipeline): arm index per step [N,H] instead of the one-hot / state tensors
   double* stats;  // nullable: += (sum r, sum r^2, #pulls of the optimal arm) over all env-steps
   // fused all-gather over NVLink peer memory (nullable): when the LAST CTA of the launch has seen every
   // CTA's contribution, it stores this rank's three totals into slot `peer_slot` of every rank's gather
@@ -322,9 +323,11 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_generic(const Rollin
     rollin_setup_env<MODE, RB_MAX_D>(p, env0 + tid, D, s_means[tid], s_thr[tid]);
     s_opt[tid] = argmax_first(s_means[tid], D);
   }
-  for (size_t i = (size_t)env0 * H + tid; i < (size_t)(env0 + ne) * H; i += RB_THREADS) {
-    st_stream(p.ctx_s + i, 1.0f);
-    st_stream(p.ctx_ns + i, 1.0f);
+  if (!p.acts_u8) {
+    for (size_t i = (size_t)env0 * H + tid; i < (size_t)(env0 + ne) * H; i += RB_THREADS) {
+      st_stream(p.ctx_s + i, 1.0f);
+      st_stream(p.ctx_ns + i, 1.0f);
+    }
   }
   __syncthreads();
 
@@ -368,6 +371,10 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_generic(const Rollin
       const float r = p.rtype == DPT_REWARD_GAUSSIAN ? fmaf(p.var, z, ma) : (z < ma ? 1.f : 0.f);
       st_stream(p.ctx_r + row, r);
       if (p.stats) st_r += r, st_r2 = fmaf(r, r, st_r2), st_opt += (float)(a == s_opt[e]);
+    }
+    if (p.acts_u8) {   // compact: 1 B per step, expanded on the host
+      if (h < H) p.acts_u8[row] = (uint8_t)a;
+      continue;
     }
     const int nvalid = min(32, H - c * 32) * D;
     float* abase = p.ctx_a + ((size_t)env * H + (size_t)c * 32) * D;
@@ -432,15 +439,17 @@ using namespace dpt;
 static int bandit_rollin_impl(const float* means, float var, int reward_type, uint64_t seed, uint64_t env_id0, int N, int H, int d,
                               float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
                               double* return_stats, const dpt_bandit_inject_t* inject, const dpt_bandit_dump_t* dump,
-                              double* const* peer_dst, int n_peers, unsigned int* done_counter, void* stream) {
+                              double* const* peer_dst, int n_peers, unsigned int* done_counter, void* stream,
+                              uint8_t* acts_u8 = nullptr) {
   DPT_CHECK_ARG(N >= 0 && H >= 0, "dpt_bandit_rollin: N=%d H=%d must be >= 0", N, H);
   DPT_CHECK_ARG(reward_type == DPT_REWARD_GAUSSIAN || reward_type == DPT_REWARD_BERNOULLI,
                 "dpt_bandit_rollin: unknown reward_type %d (0 uniform/gaussian, 1 bernoulli)", reward_type);
   DPT_CHECK_ARG(d >= 1 && d <= RB_MAX_D, "dpt_bandit_rollin: d=%d outside [1,%d]", d, RB_MAX_D);
   if (N == 0 || H == 0) return DPT_OK;
-  DPT_CHECK_ARG(means && ctx_states && ctx_actions && ctx_next_states && ctx_rewards,
+  DPT_CHECK_ARG(means && ctx_rewards && (acts_u8 || (ctx_states && ctx_actions && ctx_next_states)),
                 "dpt_bandit_rollin: null means/context pointer");
   RollinParams p{};
+  p.acts_u8 = acts_u8;
   p.means = means;
   p.var = var;
   p.rtype = reward_type;
@@ -468,7 +477,7 @@ static int bandit_rollin_impl(const float* means, float var, int reward_type, ui
     p.out = *dump;
     mode = MODE_PHILOX_DUMP;
   }
-  const bool fast = (H % 4 == 0) && 2 * d <= 32 && aligned16(ctx_states) && aligned16(ctx_actions) &&
+  const bool fast = !acts_u8 && (H % 4 == 0) && 2 * d <= 32 && aligned16(ctx_states) && aligned16(ctx_actions) &&
                     aligned16(ctx_next_states) && aligned16(ctx_rewards);
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == MODE_PHILOX)
@@ -488,6 +497,15 @@ extern "C" int dpt_bandit_rollin(const float* means, float var, int reward_type,
   return bandit_rollin_impl(means, var, reward_type, seed, env_id0, N, H, d, ctx_states, ctx_actions, ctx_next_states,
                             ctx_rewards, return_stats, inject, dump, nullptr, 0, nullptr, stream);
 }
+
+// compact form for the host pipeline (host_paths.cu): same draws, outputs = arm index (1 B) + reward (4 B) per step
+namespace dpt {
+int bandit_rollin_compact(const float* means, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d, uint8_t* acts_u8,
+                          float* ctx_rewards, void* stream) {
+  return bandit_rollin_impl(means, var, DPT_REWARD_GAUSSIAN, seed, env_id0, N, H, d, nullptr, nullptr, nullptr, ctx_rewards,
+                            nullptr, nullptr, nullptr, nullptr, 0, nullptr, stream, acts_u8);
+}
+}  // namespace dpt
 
 extern "C" int dpt_bandit_rollin_p2p(const float* means, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
                                      float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,

@@ -15,6 +15,9 @@ namespace dpt {
 
 void set_error(const char* fmt, ...);
 int sm_count();
+// bandit_rollin.cu: compact form of the rollin launch (arm index + reward per step), used by the host pipeline
+int bandit_rollin_compact(const float* means, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d, uint8_t* acts_u8,
+                          float* ctx_rewards, void* stream);
 // Envs per CTA such that the grid (ceil(N / e) CTAs, `slots` resident at a time) ends close to a whole number
 // of waves: among e in [min_e, max_e] with at least 3 waves, the one with the fullest last wave (ties: larger e).
 int pick_envs_per_cta(int N, int slots, int min_e, int max_e);

@@ -110,11 +110,16 @@ int dpt_peer_buffer_read(const void* dev_ptr, void* host_dst, uint64_t bytes, vo
  * arrays out, all HOST pointers (pinned for full speed).  Uses `scratch` (device, at least
  * dpt_bandit_rollin_host_scratch_bytes(...) bytes) for double-buffered chunks so the D2H copies
  * overlap the kernel; the constant state columns (bandit state == [1]) are written by host threads
- * instead of crossing PCIe.  Synchronises `stream` before returning. */
+ * instead of crossing PCIe, and a self-balancing share of the chunks comes back as arm index + reward (5 B per step)
+ * and is expanded to the one-hot fp32 layout by the same host threads (DPT_HOST_COMPACT=auto|0|1).  Results are
+ * identical whichever way a chunk travels.  Synchronises `stream` before returning. */
 uint64_t dpt_bandit_rollin_host_scratch_bytes(int N, int H, int d);
 int dpt_bandit_rollin_host(const float* means_host, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
                            float* ctx_states_host, float* ctx_actions_host, float* ctx_next_states_host,
                            float* ctx_rewards_host, void* scratch, uint64_t scratch_bytes, void* stream);
+/* Bytes that crossed PCIe device->host in this thread's last dpt_bandit_rollin_host call (the pipeline returns a
+ * self-balancing share of the chunks as arm index + reward, 5 B per step, and expands them on the host cores). */
+uint64_t dpt_bandit_rollin_host_last_d2h_bytes(void);
 
 /* ---------------------------------------------------------------- R3/R4: rollin_mdp --------
  * collect_data.py:83-111 (rollin_mdp) fused with envs/darkroom_env.py:37-55 (transit), :69-82
