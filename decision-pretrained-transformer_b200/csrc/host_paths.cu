@@ -190,7 +190,10 @@ extern "C" int dpt_bandit_rollin_host(const float* means_host, float var, uint64
   }
   jobs.d2h_done.resize(jobs.K);
   for (int kk = 0; kk < jobs.K; ++kk) DPT_CUDA(cudaEventCreateWithFlags(&jobs.d2h_done[kk], cudaEventDisableTiming));
-  const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+  // one process per GPU shares the host cores: torchrun exports LOCAL_WORLD_SIZE
+  unsigned procs = 1;
+  if (const char* lw = getenv("LOCAL_WORLD_SIZE")) procs = (unsigned)std::max(1, atoi(lw));
+  const unsigned hw = std::max(2u, std::thread::hardware_concurrency() / procs);
   const size_t total_rows = (size_t)N * H;
   const int n_workers = (int)std::min<size_t>(std::min(16u, hw), std::max<size_t>(1, total_rows >> 18));
   std::vector<std::thread> fillers;
