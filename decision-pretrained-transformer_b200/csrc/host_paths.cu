@@ -13,7 +13,14 @@
 #include "common.cuh"
 
 namespace dpt {
-constexpr int HOST_CHUNK_ENVS = 8192;
+static int host_chunk_envs() {
+  static const int v = [] {
+    const char* e = getenv("DPT_HOST_CHUNK_ENVS");
+    const int n = e ? atoi(e) : 0;
+    return n >= 256 ? n : 8192;
+  }();
+  return v;
+}
 
 struct ChunkLayout {
   size_t means, s, a, ns, r, total;  // float offsets
@@ -39,7 +46,7 @@ extern "C" uint64_t dpt_bandit_rollin_host_last_d2h_bytes(void) { return t_last_
 
 extern "C" uint64_t dpt_bandit_rollin_host_scratch_bytes(int N, int H, int d) {
   if (N <= 0 || H <= 0 || d <= 0) return 0;
-  const int C = N < HOST_CHUNK_ENVS ? N : HOST_CHUNK_ENVS;
+  const int C = N < host_chunk_envs() ? N : host_chunk_envs();
   return 2 * chunk_layout(C, H, d).total * sizeof(float);
 }
 
@@ -164,7 +171,7 @@ extern "C" int dpt_bandit_rollin_host(const float* means_host, float var, uint64
   DPT_CHECK_ARG(scratch && scratch_bytes >= dpt_bandit_rollin_host_scratch_bytes(N, H, d),
                 "dpt_bandit_rollin_host: scratch too small (%llu < %llu bytes)", (unsigned long long)scratch_bytes,
                 (unsigned long long)dpt_bandit_rollin_host_scratch_bytes(N, H, d));
-  const int C = N < HOST_CHUNK_ENVS ? N : HOST_CHUNK_ENVS;
+  const int C = N < host_chunk_envs() ? N : host_chunk_envs();
   const ChunkLayout L = chunk_layout(C, H, d);
   cudaStream_t cs = (cudaStream_t)stream;
   cudaStream_t copy;  // D2H stream, so chunk k's copies overlap chunk k+1's kernel
