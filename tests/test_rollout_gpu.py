@@ -155,7 +155,7 @@ def test_bandit_rollin_host_path(dpt):
         assert torch.equal(dev[k].cpu(), host[k])
     # >= 4 chunks of 8192 envs: the hybrid pipeline (some chunks cross PCIe as arm index + reward and are expanded
     # by host threads, the others arrive fully formed by DMA) must still reproduce the device result bit for bit
-    for N, d, H in ((40000, 5, 60), (33000, 10, 22), (35000, 3, 41)):
+    for N, d, H in ((40000, 5, 60), (33000, 10, 22), (35000, 3, 41), (33001, 1, 7), (32769, 32, 5), (70000, 2, 9)):
         means, _, _ = dpt.kernels.bandit_sample_means(N, d, seed, 7)
         dev = dpt.kernels.bandit_rollin(means, H, 0.3, seed, 7)
         host, _ = dpt.kernels.bandit_rollin_host(means.cpu().pin_memory(), H, 0.3, seed, 7)
