@@ -436,3 +436,35 @@ def test_rollin_bandit_follows_env_type(dpt):
     assert len(trajs) == 5 and any(len(np.unique(t["context_rewards"])) > 2 for t in trajs)   # gaussian rewards
     with pytest.raises(NotImplementedError):
         collect_data.generate_bandit_histories_from_envs([envs[0], BanditEnv(np.ones(4) * .5, 32, var=0.3)], 1, 1, 0.0, "uniform")
+
+
+def test_entry_points_are_graph_capturable(dpt):
+    """Threads / streams contract: every launch goes to the caller's stream with no hidden synchronisation,
+    so the entry points can be captured into a CUDA graph and replayed (one graph = a whole multi-launch rollout)."""
+    N, d, H = 4096, 5, 64
+    means, _, opt_a = dpt.kernels.bandit_sample_means(N, d, 3, 0)
+    ref = dpt.kernels.bandit_rollin(means, H, 0.3, 11, 0)
+    out = {k: torch.zeros_like(v) for k, v in ref.items()}
+    r = torch.zeros(N, device="cuda")
+    acts = torch.eye(d, device="cuda")[torch.arange(N, device="cuda") % d].contiguous()
+    r_ref = torch.empty(N, device="cuda")
+    dpt.kernels.gpu_bandit_step(means, acts, 0.3, 0, 5, 0, 7, out=r_ref)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        dpt.kernels.bandit_rollin(means, H, 0.3, 11, 0, out=out)       # warm-up outside capture (occupancy queries)
+        dpt.kernels.gpu_bandit_step(means, acts, 0.3, 0, 5, 0, 7, out=r)
+    torch.cuda.current_stream().wait_stream(s)
+    for v in out.values():
+        v.zero_()
+    r.zero_()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        dpt.kernels.bandit_rollin(means, H, 0.3, 11, 0, out=out)
+        dpt.kernels.gpu_bandit_step(means, acts, 0.3, 0, 5, 0, 7, out=r)
+    assert float(out["context_actions"].abs().sum()) == 0.0            # captured, not executed
+    g.replay()
+    torch.cuda.synchronize()
+    for k in ref:
+        assert torch.equal(out[k], ref[k]), k
+    assert torch.equal(r, r_ref)
