@@ -161,6 +161,12 @@ def test_bandit_rollin_host_path(dpt):
         host, _ = dpt.kernels.bandit_rollin_host(means.cpu().pin_memory(), H, 0.3, seed, 7)
         for k in dev:
             assert torch.equal(dev[k].cpu(), host[k]), (N, d, H, k)
+    # pageable (not pinned) caller buffers: slower copies, same result
+    out = {"context_states": torch.empty((N, H, 1)), "context_actions": torch.empty((N, H, d)),
+           "context_next_states": torch.empty((N, H, 1)), "context_rewards": torch.empty((N, H, 1))}
+    host, _ = dpt.kernels.bandit_rollin_host(means.cpu(), H, 0.3, seed, 7, out=out)
+    for k in dev:
+        assert torch.equal(dev[k].cpu(), host[k]), ("pageable", k)
 
 
 # ------------------------------------------------------------------ darkroom ------------------
