@@ -210,3 +210,46 @@ def generate_linear_bandit_histories(n_envs, dim, lin_d, horizon, var, **kwargs)
                               "context_actions": ca, "context_next_states": cns, "context_rewards": cr,
                               "means": env.means, "arms": arms, "theta": env.theta, "var": env.var})
     return trajs
+
+
+# --------------------------------------------------------------------------- dataset files -----
+def build_datasets(env, n_envs, n_eval_envs, n_hists, n_samples, horizon, dim, var=0.0, cov=0.0, lin_d=2, out_dir="."):
+    """The body of the reference's ``__main__`` (collect_data.py:352-485) as a function: train / test / eval
+    trajectory lists for ``env`` in {'bandit', 'linear_bandit', 'darkroom_heldout'} (80 / 20 env split; darkroom:
+    goals shuffled with RandomState(0), 80 / 20 goal split, each goal repeated ``n_envs // dim**2`` times, the eval set
+    cycles the held-out goals to 100 envs), pickled under ``out_dir/datasets/`` with the reference's file names
+    (utils.build_*_data_filename) and the reference's per-trajectory dict keys.  Returns the three paths.
+    Seeding is the caller's (``dpt_b200.seed``), where the reference seeds ``np.random`` (:353-354)."""
+    import os
+    import pickle
+    from . import utils
+    n_train_envs = int(.8 * n_envs)
+    n_test_envs = n_envs - n_train_envs
+    config = {"n_hists": n_hists, "n_samples": n_samples, "horizon": horizon}
+    if env == "bandit":
+        config.update({"dim": dim, "var": var, "cov": cov, "type": "uniform"})
+        sets = [generate_bandit_histories(n, **config) for n in (n_train_envs, n_test_envs, n_eval_envs)]
+        name, n_eval_tag = utils.build_bandit_data_filename, n_eval_envs
+    elif env == "linear_bandit":
+        config.update({"dim": dim, "lin_d": lin_d, "var": var, "cov": cov, "data_type": "thompson"})
+        sets = [generate_linear_bandit_histories(n, **config) for n in (n_train_envs, n_test_envs, n_eval_envs)]
+        name, n_eval_tag = utils.build_linear_bandit_data_filename, n_eval_envs
+    elif env == "darkroom_heldout":
+        config.update({"dim": dim, "rollin_type": "uniform"})
+        goals = np.array([[(j, i) for i in range(dim)] for j in range(dim)]).reshape(-1, 2)
+        np.random.RandomState(seed=0).shuffle(goals)                                  # :408
+        split = int(.8 * len(goals))
+        train_goals, test_goals = goals[:split], goals[split:]
+        eval_goals = np.array(test_goals.tolist() * int(100 // len(test_goals)))      # :413-414
+        train_goals = np.repeat(train_goals, n_envs // (dim * dim), axis=0)
+        test_goals = np.repeat(test_goals, n_envs // (dim * dim), axis=0)
+        sets = [generate_darkroom_histories(g, **config) for g in (train_goals, test_goals, eval_goals)]
+        name, n_eval_tag = utils.build_darkroom_data_filename, 100
+    else:
+        raise NotImplementedError
+    paths = [os.path.join(out_dir, name(env, n, config, mode=m)) for m, n in ((0, n_envs), (1, n_envs), (2, n_eval_tag))]
+    os.makedirs(os.path.join(out_dir, "datasets"), exist_ok=True)
+    for path, trajs in zip(paths, sets):
+        with open(path, "wb") as f:
+            pickle.dump(trajs, f)
+    return tuple(paths)

@@ -474,3 +474,37 @@ def test_entry_points_are_graph_capturable(dpt):
     for k in ref:
         assert torch.equal(out[k], ref[k]), k
     assert torch.equal(r, r_ref)
+
+
+def test_build_datasets_files(dpt, tmp_path):
+    """collect_data.py:352-485 as a function: three pickles with the reference's file names, trajectory keys and splits,
+    loadable by the reference-shaped Dataset (dataset.py:11-91)."""
+    import pickle
+    from dpt_b200 import collect_data
+    from dpt_b200.dataset import Dataset
+    dpt.seed(0)
+    paths = collect_data.build_datasets("bandit", 10, 3, 1, 2, 12, 5, var=0.3, cov=0.0, out_dir=str(tmp_path))
+    assert [p.split("datasets/")[1] for p in paths] == ["trajs_bandit_envs10_hists1_samples2_H12_d5_var0.3_cov0.0_train.pkl",
+                                                        "trajs_bandit_envs10_hists1_samples2_H12_d5_var0.3_cov0.0_test.pkl",
+                                                        "trajs_bandit_envs3_H12_d5_var0.3_cov0.0_eval.pkl"]
+    train, test, ev = (pickle.load(open(p, "rb")) for p in paths)
+    assert (len(train), len(test), len(ev)) == (8 * 2, 2 * 2, 3 * 2)
+    assert set(train[0]) == {"query_state", "optimal_action", "context_states", "context_actions", "context_next_states",
+                             "context_rewards", "means"}
+    assert train[0]["context_actions"].shape == (12, 5) and train[0]["context_rewards"].shape == (12,)
+    ds = Dataset(paths[0], {"horizon": 12, "state_dim": 1, "action_dim": 5, "shuffle": False, "store_gpu": False})
+    assert len(ds) == 16 and ds[0]["context_rewards"].shape == (12, 1)
+    paths = collect_data.build_datasets("darkroom_heldout", 200, 100, 1, 1, 10, 10, out_dir=str(tmp_path))
+    train, test, ev = (pickle.load(open(p, "rb")) for p in paths)
+    assert (len(train), len(test), len(ev)) == (160, 40, 100) and paths[2].endswith("trajs_darkroom_heldout_envs100_H10_d10_uniform_eval.pkl")
+    goals = np.array([[(j, i) for i in range(10)] for j in range(10)]).reshape(-1, 2)
+    np.random.RandomState(seed=0).shuffle(goals)
+    assert np.array_equal(np.stack([t["goal"] for t in train]), np.repeat(goals[:80], 2, axis=0))
+    assert np.array_equal(np.stack([t["goal"] for t in ev]), np.array(goals[80:].tolist() * 5))
+    assert set(train[0]) == {"query_state", "optimal_action", "context_states", "context_actions", "context_next_states",
+                             "context_rewards", "goal"}
+    paths = collect_data.build_datasets("linear_bandit", 10, 2, 1, 1, 8, 6, var=0.3, cov=0.0, lin_d=2, out_dir=str(tmp_path))
+    train = pickle.load(open(paths[0], "rb"))
+    assert len(train) == 8 and {"arms", "theta", "var"} <= set(train[0]) and paths[0].endswith("_H8_d6_lind2_var0.3_cov0.0_train.pkl")
+    with pytest.raises(NotImplementedError):
+        collect_data.build_datasets("miniworld", 10, 2, 1, 1, 8, 6, out_dir=str(tmp_path))
