@@ -508,3 +508,28 @@ def test_build_datasets_files(dpt, tmp_path):
     assert len(train) == 8 and {"arms", "theta", "var"} <= set(train[0]) and paths[0].endswith("_H8_d6_lind2_var0.3_cov0.0_train.pkl")
     with pytest.raises(NotImplementedError):
         collect_data.build_datasets("miniworld", 10, 2, 1, 1, 8, 6, out_dir=str(tmp_path))
+
+
+def test_bench_own_arm_contract(dpt):
+    """`bench.py` (the arm the driver runs on the GPU box) prints ONE JSON line with the contract's keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--gpus", "1", "--steps", "3", "--warmup", "1",
+                          "--no-cpu-baseline", "--no-other"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    r = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks"):
+        assert k in r, k
+    assert r["n_gpus"] == 1 and r["steps"] == 3 and r["warmup"] >= 3 and r["gpu_launches"] == 3 and r["scaling"] == "weak"
+    assert r["unit"] == "env-steps/s" and r["value"] > 1e10 and "workload" in r["config"]
+    rf = r["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    e = r["e2e"]
+    assert e["unit"] == r["unit"] and 0 < e["value"] < r["value"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(r["clocks"])
