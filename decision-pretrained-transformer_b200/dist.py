@@ -181,3 +181,21 @@ def online_eval_sharded(kind, n_envs_total, dim, horizon, var, seed, model=None,
         out = kernels.online_loop(kind, means, horizon, var, seed, lo, materialise=materialise, regret=True, **ctrl)
     sums = all_reduce_sums(out["regret_sums"].clone())
     return out, regret_stats_from_sums(sums.cpu().numpy(), n_envs_total)
+
+
+def collect_darkroom_sharded(goals_total, dim, horizon, seed, rollin_type="uniform", perm_index_total=None, n_samples=1):
+    """BASELINE config 2 over all ranks: rank r runs ``rollin_mdp`` + query states for the env slice
+    ``shard_range(len(goals_total), r, world)`` (global env ids in the Philox counters, so the shards are slices of
+    the single-GPU result).  The exchange is one all-reduce of two integers: total reward and number of env-steps.
+    Returns (local batch dict, {'mean_reward', 'env_steps'})."""
+    from . import kernels
+    rank, ws = world()
+    goals_total = np.asarray(goals_total)
+    lo, hi = shard_range(len(goals_total), rank, ws)
+    perm = None if perm_index_total is None else np.asarray(perm_index_total)[lo:hi]
+    batch = kernels.darkroom_rollin(goals_total[lo:hi], dim, horizon, rollin_type, seed, lo, perm, n_samples)
+    local = torch.stack((batch["context_rewards"].double().sum(), torch.tensor(float((hi - lo) * horizon), dtype=torch.float64,
+                                                                             device=batch["context_rewards"].device)))
+    tot = all_reduce_sums(local).cpu().numpy()
+    batch["env_range"] = (lo, hi)
+    return batch, {"mean_reward": float(tot[0] / max(tot[1], 1.0)), "env_steps": int(tot[1])}

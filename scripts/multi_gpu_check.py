@@ -43,6 +43,10 @@ def main():
     out, curves = D.online_eval_sharded("thompson", N, d, H, var, seed, p0=var, p1=0.5, p2=1 / 12.0)
     cm = digest(out["cum_means"])
     allc = D.all_gather_stats(cm)
+    # darkroom collection (config 2) sharded the same way
+    goals = np.random.RandomState(5).randint(0, 10, (N, 2))
+    dk, dstats = D.collect_darkroom_sharded(goals, 10, 64, seed)
+    alld = D.all_gather_stats(torch.cat([digest(dk[k]) for k in ("context_states", "context_actions", "context_next_states", "context_rewards")]))
     ok = True
     if rank == 0:
         means, _, _ = kernels.bandit_sample_means(N, d, seed, 0)
@@ -54,6 +58,12 @@ def main():
             want = torch.cat([digest(full[k][a:b]) for k in ("context_actions", "context_rewards", "context_states")])
             ok &= bool(torch.equal(want, allh[r]))
             ok &= bool(torch.equal(digest(fo["cum_means"][:, a:b]), allc[r]))
+        fd = kernels.darkroom_rollin(goals, 10, 64, "uniform", seed, 0, None, 1)
+        for r in range(ws):
+            a, b = D.shard_range(N, r, ws)
+            want = torch.cat([digest(fd[k][a:b]) for k in ("context_states", "context_actions", "context_next_states", "context_rewards")])
+            ok &= bool(torch.equal(want, alld[r]))
+        ok &= dstats["env_steps"] == N * 64 and abs(dstats["mean_reward"] - float(fd["context_rewards"].double().mean())) < 1e-12
         ref = D.merge_return_stats(st.cpu().numpy()[None], [N * H])
         ok &= abs(ref["mean_reward"] - stats["mean_reward"]) < 1e-9 and abs(ref["frac_optimal_arm"] - stats["frac_optimal_arm"]) < 1e-12
         rc = D.regret_stats_from_sums(fo["regret_sums"].cpu().numpy(), N)

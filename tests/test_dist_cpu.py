@@ -101,3 +101,14 @@ def test_two_rank_gloo_matches_single_process():
     got = D.regret_stats_from_sums(res[0][5], N)
     m, s, cm, cs = O.regret_stats(np.repeat(means.max(1)[:, None], H, 1), np.take_along_axis(means, acts, 1))
     assert np.allclose(got["mean"], m) and np.allclose(got["sem"], s) and np.allclose(got["regret_mean"], cm) and np.allclose(got["regret_sem"], cs)
+
+
+def test_collect_darkroom_sharded_needs_cuda():
+    """No CPU fallback on the sharded darkroom collection either (it fails loudly without the CUDA path)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import dpt_b200
+    from dpt_b200 import dist as D
+    with pytest.raises(dpt_b200._lib.DptError):
+        D.collect_darkroom_sharded(np.zeros((8, 2), dtype=np.int64), 10, 4, 0)
