@@ -489,6 +489,35 @@ __global__ void __launch_bounds__(G_THREADS) gpt2_forward_kernel(const ForwardPa
 }
 
 // ---------------------------------------------------------------------------------------------
+// One decode step for callers that drive their own loop (interactive trainers' rollout half): append the token of
+// position `pos` to each sequence's K/V cache and return the logits at that position.
+// ---------------------------------------------------------------------------------------------
+struct StepParams {
+  Gpt2Dev m;
+  const float* tokens;   // [N, din]: [state | action | next_state | reward]; position 0 = [query state, 0, ...]
+  int N, pos, Tpad;
+  float* out;            // [N, du]
+  void* kv;
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(G_THREADS) gpt2_decode_step_kernel(const StepParams p) {
+  extern __shared__ __align__(16) float g_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * G_WARPS + warp;
+  if (b >= p.N) return;
+  const Gpt2Dev& m = p.m;
+  const WarpScratch ws = warp_scratch(g_smem, warp, p.Tpad);
+  char* kv = reinterpret_cast<char*>(p.kv) + (size_t)b * m.L * 2 * G_E * p.Tpad * (BF16 ? 2 : 4);
+  const float tok = lane < m.din ? p.tokens[(size_t)b * m.din + lane] : 0.f;
+  float x = __ldg(m.embed_b + lane) + __ldg(m.wpe + (size_t)p.pos * G_E + lane);
+  for (int i = 0; i < m.din; ++i) x = fmaf(__shfl_sync(0xffffffffu, tok, i), __ldg(m.embed_wT + i * G_E + lane), x);
+  x = token_forward<BF16>(m, x, p.pos, kv, p.Tpad, ws.sx, ws.sh, ws.ssc, lane);
+  const float lg = head_logits(m, x, ws.sx, lane);
+  if (lane < m.du) p.out[(size_t)b * m.du + lane] = lg;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fused bandit online loop with the transformer controller
 // ---------------------------------------------------------------------------------------------
 struct OnlineGptParams {
@@ -772,6 +801,30 @@ extern "C" int dpt_gpt2_forward(dpt_gpt2_t* m, const float* query_states, const 
     gpt2_forward_kernel<true><<<(B + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
   else
     gpt2_forward_kernel<false><<<(B + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
+  DPT_LAUNCH_CHECK();
+  return DPT_OK;
+}
+
+extern "C" int dpt_gpt2_decode_step(dpt_gpt2_t* m, const float* tokens, int N, int pos, int T_max, int precision, void* kv_cache,
+                                    uint64_t kv_bytes, float* logits, void* stream) {
+  DPT_CHECK_ARG(m, "dpt_gpt2_decode_step: null model");
+  DPT_CHECK_ARG(precision == 0 || precision == 1, "dpt_gpt2_decode_step: precision %d (0 = fp32, 1 = bf16 K/V cache)", precision);
+  DPT_CHECK_ARG(N >= 0 && T_max >= 1 && pos >= 0 && pos < T_max, "dpt_gpt2_decode_step: N=%d pos=%d T_max=%d", N, pos, T_max);
+  DPT_CHECK_ARG(T_max <= m->dev.n_pos, "dpt_gpt2_decode_step: %d positions exceed n_positions %d", T_max, m->dev.n_pos);
+  if (N == 0) return DPT_OK;
+  DPT_CHECK_ARG(tokens && logits && kv_cache && kv_bytes >= dpt_gpt2_online_kv_bytes(m, N, T_max, precision),
+                "dpt_gpt2_decode_step: null pointer or kv cache too small");
+  StepParams p{};
+  p.m = m->dev;
+  p.tokens = tokens, p.N = N, p.pos = pos, p.Tpad = tpad_for(T_max, precision), p.out = logits, p.kv = kv_cache;
+  const size_t smem = (size_t)G_WARPS * (G_E + G_FF + p.Tpad) * sizeof(float);
+  const void* kern = precision ? (const void*)gpt2_decode_step_kernel<true> : (const void*)gpt2_decode_step_kernel<false>;
+  int rc = launch_smem(kern, smem);
+  if (rc != DPT_OK) return rc;
+  if (precision)
+    gpt2_decode_step_kernel<true><<<(N + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
+  else
+    gpt2_decode_step_kernel<false><<<(N + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
   DPT_LAUNCH_CHECK();
   return DPT_OK;
 }

@@ -179,6 +179,15 @@ class Transformer(nn.Module):
               "dpt_gpt2_forward")
         return out
 
+    # ---- step-by-step K/V-cached decode (callers that choose the pulled arm themselves) -------------
+    def decoder(self, n_seqs, max_transitions=None):
+        """A K/V-cached incremental view of ``forward(...)[:, -1]`` for loops that are driven from outside (the rollout
+        half of train_interactive.py:97-132 / train_explorer_exploiter.py:110-166): ``dec.query(states)`` appends the
+        query token (position 0) and returns the logits on an empty context; each ``dec.append(states, actions,
+        next_states, rewards)`` appends one transition and returns the logits given everything appended so far --
+        O(context) work per step instead of a dense forward over the whole context."""
+        return _Decoder(self, n_seqs, self.horizon if max_transitions is None else max_transitions)
+
     # ---- fused in-context evaluation loop ---------------------------------------------------
     @torch.no_grad()
     def online_loop(self, means, horizon, var, sample, seed, env_id0=0, materialise=True, regret=True, inject=None,
@@ -227,3 +236,44 @@ class Transformer(nn.Module):
         if noise is not None:
             out["noise"] = noise
         return out
+
+
+class _Decoder:
+    """See ``Transformer.decoder``.  Owns its K/V cache (per sequence [L][2][Tpad][32], fp32 or bf16 with
+    ``model.precision``); valid while the query state of a sequence does not change (bandits: the constant [1])."""
+
+    def __init__(self, model, n_seqs, max_transitions):
+        self.model, self.n, self.t_max, self.pos = model, n_seqs, max_transitions + 1, 0
+        self.precision = model.precision
+        dev = kernels._dev()
+        self._h = model.handle()
+        nbytes = lib().dpt_gpt2_online_kv_bytes(self._h, n_seqs, self.t_max, self.precision)
+        self.kv = torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=dev)
+        self.din = 2 * model.state_dim + model.action_dim + 1
+        self._tok = torch.zeros((n_seqs, self.din), dtype=torch.float32, device=dev)
+
+    def _step(self):
+        out = torch.empty((self.n, self.model.action_dim), dtype=torch.float32, device=self._tok.device)
+        check(lib().dpt_gpt2_decode_step(self._h, ptr(self._tok), self.n, self.pos, self.t_max, self.precision, ptr(self.kv),
+                                         self.kv.numel(), ptr(out), stream_ptr()), "dpt_gpt2_decode_step")
+        self.pos += 1
+        return out
+
+    @torch.no_grad()
+    def query(self, query_states):
+        assert self.pos == 0, "the query token is position 0"
+        dx = self.model.state_dim
+        self._tok.zero_()
+        self._tok[:, :dx] = torch.as_tensor(query_states, dtype=torch.float32).to(self._tok.device).reshape(self.n, dx)
+        return self._step()
+
+    @torch.no_grad()
+    def append(self, states, actions, next_states, rewards):
+        assert 0 < self.pos < self.t_max, "query() first; at most max_transitions appends"
+        dx, du, dev = self.model.state_dim, self.model.action_dim, self._tok.device
+        f = lambda a, w: torch.as_tensor(a, dtype=torch.float32).to(dev).reshape(self.n, w)   # noqa: E731
+        self._tok[:, :dx] = f(states, dx)
+        self._tok[:, dx:dx + du] = f(actions, du)
+        self._tok[:, dx + du:2 * dx + du] = f(next_states, dx)
+        self._tok[:, 2 * dx + du:] = f(rewards, 1)
+        return self._step()

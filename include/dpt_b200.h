@@ -284,6 +284,15 @@ int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, double var, int rewa
                          double* regret_sums, const dpt_gpt2_online_inject_t* inject,
                          const dpt_gpt2_online_dump_t* dump, void* stream);
 
+/* One decode step for callers that drive their own loop (the rollout half of train_interactive.py:97-132 /
+ * train_explorer_exploiter.py:110-166, where the arm that is pulled is chosen outside): append the token of position
+ * `pos` (tokens [N, 2*dx+du+1] = [state | action | next_state | reward]; position 0 is the query token
+ * [query_state, 0, ...], models/net.py:45-53) to every sequence's K/V cache and write the logits at that position
+ * (= Transformer.forward(...)[:, -1] over the pos transitions appended so far) to logits [N, du].  Positions must be
+ * appended in order 0, 1, 2, ...; kv_cache as for dpt_gpt2_online_loop: dpt_gpt2_online_kv_bytes(m, N, T_max, precision). */
+int dpt_gpt2_decode_step(dpt_gpt2_t* m, const float* tokens, int N, int pos, int T_max, int precision, void* kv_cache,
+                         uint64_t kv_bytes, float* logits, void* stream);
+
 /* ---------------------------------------------------------------- bring-up / regression ----
  * D[128,N] = A[128,K] * B[N,K]^T through tcgen05.mma (bf16 operands, fp32 accumulate in tensor memory):
  * the self-test of the UMMA helpers (descriptors, 128 B swizzle, TMEM loads) used by the dense forward. */

@@ -476,3 +476,31 @@ def test_bf16_decode_fallback_geometry(dpt):
         b["query_states"] = torch.ones(N, 1, device="cuda")
         _close(_np(out["noise"]["logits"][h]), _np(m(b)), 2e-2)
     assert float(out["context_actions"].sum(-1).min()) == 1.0
+
+
+@pytest.mark.parametrize("precision,tol", [(0, 1e-5), (1, 2e-2)])
+def test_decoder_step_by_step(dpt, precision, tol):
+    """Transformer.decoder: K/V-cached step-by-step logits (arm chosen outside the kernel, as in the interactive
+    trainers' rollouts) equal the dense forward over the context appended so far, step by step."""
+    from dpt_b200.models.net import Transformer
+    torch.manual_seed(5)
+    K, d, L, N = 40, 5, 3, 37
+    m = Transformer({"horizon": K, "state_dim": 1, "action_dim": d, "n_layer": L, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True})
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if "wte" not in k:
+                p.add_(0.1 * torch.randn_like(p))
+    rs = np.random.RandomState(0)
+    acts = torch.tensor(np.eye(d)[rs.randint(0, d, (N, K))], dtype=torch.float32, device="cuda")
+    rews = torch.tensor(rs.normal(0.5, 0.4, (N, K, 1)), dtype=torch.float32, device="cuda")
+    ones = torch.ones(N, K, 1, device="cuda")
+    m.precision = precision
+    dec = m.decoder(N)
+    m.precision = 0                       # dense fp32 reference
+    for t in range(K + 1):
+        lg = dec.query(torch.ones(N, 1)) if t == 0 else dec.append(ones[:, t - 1], acts[:, t - 1], ones[:, t - 1], rews[:, t - 1])
+        ref = m({"query_states": torch.ones(N, 1, device="cuda"), "context_states": ones[:, :t], "context_actions": acts[:, :t],
+                 "context_next_states": ones[:, :t], "context_rewards": rews[:, :t]})
+        _close(_np(lg), _np(ref), tol)
+    with pytest.raises(AssertionError):
+        dec.append(ones[:, 0], acts[:, 0], ones[:, 0], rews[:, 0])       # cache full
