@@ -80,13 +80,50 @@ class GPUBanditEnv(BaseEnv):
         the model produced at every step [K,n_envs,du] and ``target = opt_a_index`` (:134).  Training itself
         (backward through the last forward) is out of scope: a trainer re-runs ``model(batch)`` on
         ``context[:, :K-1]`` with its own autograd-enabled model to get ``last_logits`` with gradients."""
-        if self.type != "uniform":
-            raise NotImplementedError("fused rollout: uniform bandits only")
         K = self.H if K is None else K
         with torch.cuda.device(self._device):
             out = model.online_loop(self.means, K, float(self.var), sample, self._key ^ 0x2545F4914F6CDD1D, self._env_id0,
-                                    materialise=True, regret=False, dump=True)
+                                    materialise=True, regret=False, dump=True, reward_type=self.type)
         self._draws += K
         return {"context_states": out["context_states"], "context_actions": out["context_actions"],
                 "context_next_states": out["context_next_states"], "context_rewards": out["context_rewards"],
                 "logits": out["noise"]["logits"], "target": self.opt_a_index}
+
+    @torch.no_grad()
+    def rollout_explorer_exploiter(self, explorer, exploiter, K=None):
+        """The replay-buffer fill of train_explorer_exploiter.py:110-166 (the no-grad half of an episode): at every step
+        both models score the context so far (K/V-cached ``Transformer.decoder``, one per model), the explorer's sampled
+        arm is what gets RECORDED in the context while the env is stepped with a uniformly random arm (:141-152, as in
+        the reference), and the advantage of step t-1 is the change of the exploiter's cross-entropy against the optimal
+        arm (:160-164).  Returns the context tensors [n_envs,K,.], ``advantages`` [n_envs,K-1,1], both models' logits
+        per step [K,n_envs,du] and ``target``.  Sampling uses torch's device generator like the reference."""
+        K = self.H if K is None else K
+        n, du, dev = self.n_envs, self.du, self._device
+        dec_e, dec_x = explorer.decoder(n, K), exploiter.decoder(n, K)
+        ctx = {"context_states": torch.zeros((n, K, self.dx), device=dev), "context_actions": torch.zeros((n, K, du), device=dev),
+               "context_next_states": torch.zeros((n, K, self.dx), device=dev), "context_rewards": torch.zeros((n, K, 1), device=dev)}
+        advantages = torch.zeros((n, max(K - 1, 0), 1), device=dev)
+        logits_e, logits_x = [], []
+        target = self.opt_a_index.to(dev)
+        state, prev_loss = self.reset(), None
+        for t in range(K):
+            if t == 0:
+                le, lx = dec_e.query(state), dec_x.query(state)
+            else:
+                row = [ctx[k][:, t - 1] for k in ("context_states", "context_actions", "context_next_states", "context_rewards")]
+                le, lx = dec_e.append(*row), dec_x.append(*row)
+            logits_e.append(le), logits_x.append(lx)
+            action = torch.nn.functional.one_hot(torch.distributions.Categorical(logits=le).sample(), num_classes=du).float()
+            random_action = torch.nn.functional.one_hot(torch.randint(0, du, (n,), device=dev), num_classes=du).float()
+            next_state, reward, _, _ = self.step(random_action)
+            ctx["context_states"][:, t] = state.float()
+            ctx["context_actions"][:, t] = action
+            ctx["context_next_states"][:, t] = next_state.float()
+            ctx["context_rewards"][:, t, 0] = reward.float()
+            state = next_state
+            loss = torch.nn.functional.cross_entropy(lx, target, reduction="none")
+            if t > 0:
+                advantages[:, t - 1] = (loss - prev_loss).unsqueeze(-1)
+            prev_loss = loss
+        return dict(ctx, advantages=advantages, explorer_logits=torch.stack(logits_e), exploiter_logits=torch.stack(logits_x),
+                    target=target)

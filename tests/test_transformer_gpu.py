@@ -504,3 +504,40 @@ def test_decoder_step_by_step(dpt, precision, tol):
         _close(_np(lg), _np(ref), tol)
     with pytest.raises(AssertionError):
         dec.append(ones[:, 0], acts[:, 0], ones[:, 0], rews[:, 0])       # cache full
+
+
+def test_explorer_exploiter_rollout(dpt):
+    """train_explorer_exploiter.py:110-166, no-grad half: two models score the same growing context through their own
+    K/V-cached decoders; the recorded logits equal dense forwards over the recorded context, the advantages are the
+    exploiter's cross-entropy differences, and the recorded arm is the explorer's (the env is stepped with a random arm)."""
+    from dpt_b200.models.net import Transformer
+    from dpt_b200.envs.gpu_bandit_env import GPUBanditEnv
+    torch.manual_seed(9)
+    K, d, N = 12, 5, 64
+    cfg = {"horizon": K, "state_dim": 1, "action_dim": d, "n_layer": 2, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True}
+    explorer, exploiter = Transformer(cfg), Transformer(cfg)
+    with torch.no_grad():
+        for mdl in (explorer, exploiter):
+            for k, p in mdl.named_parameters():
+                if "wte" not in k:
+                    p.add_(0.2 * torch.randn_like(p))
+    env = GPUBanditEnv(d, N, K, var=0.3, seed=4)
+    out = env.rollout_explorer_exploiter(explorer, exploiter)
+    assert out["context_actions"].shape == (N, K, d) and float(out["context_actions"].sum(-1).min()) == 1.0
+    assert out["advantages"].shape == (N, K - 1, 1) and out["explorer_logits"].shape == (K, N, d)
+    names = ("context_states", "context_actions", "context_next_states", "context_rewards")
+    losses = []
+    for t in range(K):
+        b = {k: out[k][:, :t] for k in names}
+        b["query_states"] = torch.ones(N, 1, device="cuda")
+        _close(_np(out["exploiter_logits"][t]), _np(exploiter(b)), 1e-5)
+        _close(_np(out["explorer_logits"][t]), _np(explorer(b)), 1e-5)
+        losses.append(torch.nn.functional.cross_entropy(out["exploiter_logits"][t], out["target"], reduction="none"))
+    for t in range(1, K):
+        assert torch.allclose(out["advantages"][:, t - 1, 0], losses[t] - losses[t - 1], atol=1e-6)
+    with pytest.raises(ValueError):
+        env.step(out["context_actions"][:, 0])       # the episode of K steps is over (:59-61)
+    # the single-model fused rollout also serves bernoulli envs now
+    benv = GPUBanditEnv(d, N, K, var=0.3, type="bernoulli", seed=4)
+    r = benv.rollout(explorer, K)
+    assert set(np.unique(_np(r["context_rewards"]))) <= {0.0, 1.0}
