@@ -541,3 +541,26 @@ def test_explorer_exploiter_rollout(dpt):
     benv = GPUBanditEnv(d, N, K, var=0.3, type="bernoulli", seed=4)
     r = benv.rollout(explorer, K)
     assert set(np.unique(_np(r["context_rewards"]))) <= {0.0, 1.0}
+
+
+@pytest.mark.parametrize("du,H,L,N", [(2, 17, 1, 50), (10, 65, 3, 29), (5, 130, 4, 25)])
+def test_bf16_decode_shapes(dpt, du, H, L, N):
+    """precision = 1 loop (tensor-core attention + projections, 16-key V blocks, 64-key K tiles) at horizons that are not
+    multiples of the block sizes, other arm counts and depths, env counts that do not fill a CTA: logits the loop saw
+    against the fp32 dense / token-sequential forward over the context it built (2e-2), one-hot actions throughout."""
+    from dpt_b200.models.net import Transformer
+    torch.manual_seed(du * 7 + H)
+    m = Transformer({"horizon": H, "state_dim": 1, "action_dim": du, "n_layer": L, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True})
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if "wte" not in k:
+                p.add_(0.08 * torch.randn_like(p))
+    means, _, _ = dpt.kernels.bandit_sample_means(N, du, 3, 0)
+    m.precision = 1
+    out = m.online_loop(means, H, 0.3, True, 3, 0, dump=True)
+    m.precision = 0
+    for h in sorted({0, 1, 15, 16, 17, 63, 64, H - 1} & set(range(H))):
+        b = {k: out[k][:, :h] for k in ("context_states", "context_actions", "context_next_states", "context_rewards")}
+        b["query_states"] = torch.ones(N, 1, device="cuda")
+        _close(_np(out["noise"]["logits"][h]), _np(m(b)), 2e-2)
+    assert float(out["context_actions"].sum(-1).min()) == 1.0 and float(out["context_actions"].sum(-1).max()) == 1.0
