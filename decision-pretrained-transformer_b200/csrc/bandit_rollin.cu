@@ -16,6 +16,8 @@
 // HBM traffic is write-only: 4*(2+d+1) B per env-step (32 B for d=5), inputs are < 0.1 B/step.
 #include <string.h>
 
+#include <unordered_map>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -388,13 +390,26 @@ __global__ void __launch_bounds__(RB_THREADS) bandit_rollin_generic(const Rollin
   if (p.stats) reduce_stats(p, st_r, st_r2, st_opt);
 }
 
+// resident CTAs per SM of a kernel (occupancy API), cached per kernel POINTER: every instantiation has the same
+// function type, so a function-local static inside a generic lambda would be shared by all of them
+template <typename K>
+static int resident_ctas(K kern) {
+  static thread_local std::unordered_map<const void*, int> cache;
+  const void* key = reinterpret_cast<const void*>(kern);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, RB_THREADS, 0) != cudaSuccess || n < 1) n = 4;
+  cache[key] = n;
+  return n;
+}
+
 template <int MODE>
 static void launch_mode(RollinParams p, bool fast, cudaStream_t st) {
   // envs per CTA: up to 32, few enough that the grid covers the machine >= 3 times, and chosen so that the
   // last wave is nearly full (the kernel's real occupancy decides what a wave is)
   auto go = [&](auto kern) {
-    static int per_sm = 0;
-    if (per_sm == 0) per_sm = resident_ctas(kern);
+    const int per_sm = resident_ctas(kern);
     p.envs_per_cta = pick_envs_per_cta(p.N, sm_count() * per_sm, 1, RB_MAX_ENVS);
     const int grid = (p.N + p.envs_per_cta - 1) / p.envs_per_cta;
     kern<<<grid, RB_THREADS, 0, st>>>(p);
@@ -422,14 +437,6 @@ static void launch_mode(RollinParams p, bool fast, cudaStream_t st) {
     }
   }
   go(bandit_rollin_generic<MODE>);
-}
-
-// resident CTAs per SM of a kernel (occupancy API), cached per kernel pointer
-template <typename K>
-static int resident_ctas(K kern) {
-  int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, RB_THREADS, 0) != cudaSuccess || n < 1) n = 4;
-  return n;
 }
 
 }  // namespace dpt
@@ -543,6 +550,11 @@ extern "C" int dpt_peer_buffer_close(void* dev_ptr) {
 }
 extern "C" int dpt_peer_buffer_destroy(void* dev_ptr) {
   if (dev_ptr) DPT_CUDA(cudaFree(dev_ptr));
+  return DPT_OK;
+}
+extern "C" int dpt_peer_buffer_zero(void* dev_ptr, uint64_t bytes, void* stream) {
+  DPT_CHECK_ARG(dev_ptr, "dpt_peer_buffer_zero: null pointer");
+  DPT_CUDA(cudaMemsetAsync(dev_ptr, 0, bytes, (cudaStream_t)stream));
   return DPT_OK;
 }
 extern "C" int dpt_peer_buffer_read(const void* dev_ptr, void* host_dst, uint64_t bytes, void* stream) {

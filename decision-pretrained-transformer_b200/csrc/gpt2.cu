@@ -683,7 +683,17 @@ extern "C" int dpt_gpt2_create(const dpt_gpt2_weights_t* w, dpt_gpt2_t** out, vo
   const int L = w->n_layer, du = w->action_dim;
   const size_t per_layer = 4 * G_E + G_E * 3 * G_E + 3 * G_E + G_E * G_E + G_E + G_E * G_FF + G_FF + G_FF * G_E + G_E;
   const size_t total = (size_t)w->n_positions * G_E + (size_t)din * G_E + G_E + (size_t)G_E * du + du + 2 * G_E + L * (2 * per_layer + WIMG_BYTES / 4 + WF_UINT4 * 4) + 4 * (16 + 18 * (size_t)L);
-  dpt_gpt2* m = new dpt_gpt2();
+  struct Guard {   // frees the half-built model on every early return below
+    dpt_gpt2* m;
+    ~Guard() {
+      if (m) {
+        cudaFree(m->blob);
+        delete m;
+      }
+    }
+  } guard{new dpt_gpt2()};
+  dpt_gpt2* m = guard.m;
+  m->blob = nullptr;
   DPT_CUDA(cudaMalloc(&m->blob, total * sizeof(float)));
   float* cur = m->blob;
   auto take = [&](size_t n) {
@@ -738,6 +748,7 @@ extern "C" int dpt_gpt2_create(const dpt_gpt2_weights_t* w, dpt_gpt2_t** out, vo
     lw.wfrag = frag;
   }
   DPT_LAUNCH_CHECK();
+  guard.m = nullptr;
   *out = m;
   return DPT_OK;
 }

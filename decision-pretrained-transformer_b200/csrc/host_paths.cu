@@ -1,9 +1,11 @@
 // Host-buffer entry points (the e2e path): the same kernels driven from HOST arrays, with the
 // host<->device copies pipelined against the kernel in env chunks (double-buffered scratch).
 #include <emmintrin.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -159,6 +161,56 @@ struct HostJobs {
   }
 };
 }  // namespace
+
+// ---- host memory write peak (measurement aid for the e2e roofline) ----------------------------------------
+// The host half of the e2e path is a pure write stream into the caller's arrays.  This measures what the box's
+// cores can stream with non-temporal stores: `n_threads` threads (0 = every core this process may run on) each
+// write their own contiguous slice of `dst` (NULL: an internal malloc'ed, first-touched buffer) of `bytes` bytes,
+// three passes after one warm-up pass, best pass reported in GB/s.  Debug / bench export, not on the product path.
+static int usable_cores() {
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+    const int n = CPU_COUNT(&set);
+    if (n > 0) return n;
+  }
+  return (int)std::max(1u, std::thread::hardware_concurrency());
+}
+
+extern "C" double dpt_host_write_peak(void* dst, uint64_t bytes, int n_threads) {
+  if (bytes < (1u << 20)) bytes = 1ull << 30;
+  const int T = n_threads > 0 ? n_threads : usable_cores();
+  void* own = nullptr;
+  if (!dst) {
+    if (posix_memalign(&own, 4096, bytes) != 0) return 0.0;
+    dst = own;
+  }
+  float* base = reinterpret_cast<float*>(dst);
+  const size_t n = bytes / sizeof(float);
+  double best = 0.0;
+  for (int pass = 0; pass < 4; ++pass) {
+    std::atomic<int> ready{0};
+    std::atomic<bool> go{false};
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t)
+      th.emplace_back([&, t] {
+        float* lo = base + ((n * t / T) & ~size_t(15));
+        float* hi = (t == T - 1) ? base + n : base + ((n * (t + 1) / T) & ~size_t(15));
+        ready.fetch_add(1);
+        while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
+        fill_ones_nt(lo, hi);
+        _mm_sfence();
+      });
+    while (ready.load() < T) std::this_thread::yield();
+    const auto t0 = std::chrono::steady_clock::now();
+    go.store(true, std::memory_order_release);
+    for (auto& x : th) x.join();
+    const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (pass > 0) best = std::max(best, (double)bytes / s / 1e9);   // pass 0 first-touches the pages
+  }
+  free(own);
+  return best;
+}
 
 extern "C" int dpt_bandit_rollin_host(const float* means_host, float var, uint64_t seed, uint64_t env_id0, int N,
                                       int H, int d, float* ctx_states_host, float* ctx_actions_host,

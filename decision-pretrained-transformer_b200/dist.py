@@ -127,6 +127,14 @@ class PeerGather:
         off = ((slot * self.world + self.rank) * self.width) * 8
         return (ct.c_void_p * self.world)(*[p + off for p in self.peer_ptrs])
 
+    def publish_zeros(self, slot):
+        """What a rank with an EMPTY env shard does instead of launching: zero element [slot, my rank, :] of every
+        rank's buffer (cudaMemsetAsync on the current stream through the peer mappings)."""
+        from ._lib import check, lib, stream_ptr
+        off = ((slot * self.world + self.rank) * self.width) * 8
+        for p in self.peer_ptrs:
+            check(lib().dpt_peer_buffer_zero(self._ctypes.c_void_p(p + off), self.width * 8, stream_ptr()), "dpt_peer_buffer_zero")
+
     def read(self):
         """This rank's buffer as a numpy array [slots, world, width] (synchronises the current stream)."""
         from ._lib import check, lib, stream_ptr
@@ -147,18 +155,26 @@ class PeerGather:
 # ------------------------------------------------------------------ sharded entry points -------
 def collect_bandit_sharded(n_envs_total, dim, horizon, var, seed, device=None, peer=None, peer_slot=0):
     """BASELINE config 5: bandit collection over all ranks.  Returns (local batch dict, global
-    statistics dict).  The local batch holds this rank's env slice only."""
+    statistics dict).  The local batch holds this rank's env slice only (possibly empty when
+    ``n_envs_total < world``: such a rank launches nothing and contributes zeros)."""
     from . import kernels
     rank, ws = world()
     lo, hi = shard_range(n_envs_total, rank, ws)
     means, opt_idx, opt_a = kernels.bandit_sample_means(hi - lo, dim, seed, lo, device)
     stats = torch.zeros(3, dtype=torch.float64, device=means.device)
     if peer is not None:   # fused all-gather over NVLink peer memory, no collective launch
-        batch = kernels.bandit_rollin(means, horizon, float(var), seed, lo, stats=stats, peer=peer, peer_slot=peer_slot)
+        if hi > lo:
+            batch = kernels.bandit_rollin(means, horizon, float(var), seed, lo, stats=stats, peer=peer, peer_slot=peer_slot)
+        else:              # empty shard: no launch; publish zeros so that every rank's slot row is defined
+            batch = kernels.bandit_rollin(means, horizon, float(var), seed, lo)
+            peer.publish_zeros(peer_slot)
         torch.cuda.synchronize()
         if ws > 1:
-            dist.barrier()
-        gathered = peer.read()[peer_slot]
+            dist.barrier()           # every rank's launch (and its NVLink stores) has completed
+        gathered = peer.read()[peer_slot].copy()
+        if ws > 1:
+            dist.barrier()           # nobody re-uses `peer_slot` before every rank has read it (ADVICE r1: a fast
+                                     # rank's next launch could otherwise overwrite a slow rank's unread slot)
     else:
         batch = kernels.bandit_rollin(means, horizon, float(var), seed, lo, stats=stats)
         gathered = all_gather_stats(stats).cpu().numpy()
@@ -167,14 +183,20 @@ def collect_bandit_sharded(n_envs_total, dim, horizon, var, seed, device=None, p
     return batch, merge_return_stats(gathered, steps)
 
 
-def online_eval_sharded(kind, n_envs_total, dim, horizon, var, seed, model=None, materialise=False, **ctrl):
-    """Online in-context evaluation over all ranks: each rank draws and evaluates its env slice with
+def online_eval_sharded(kind, n_envs_total, dim, horizon, var, seed, model=None, materialise=False, means_local=None, **ctrl):
+    """Online in-context evaluation over all ranks: each rank draws (or receives) and evaluates its env slice with
     the fused loop, then the [H,4] regret sums are all-reduced.  ``kind``: 'opt' | 'emp' | 'ucb' |
-    'thompson' | 'linucb' | 'transformer'.  Returns (local result dict, global regret curves)."""
+    'thompson' | 'linucb' | 'transformer'.  ``means_local``: optional [hi-lo, dim] fp32 task means of THIS rank's slice
+    (host -- ideally pinned -- or device tensor); default: drawn on the device from Philox(seed, global env id).
+    Returns (local result dict, global regret curves)."""
     from . import kernels
     rank, ws = world()
     lo, hi = shard_range(n_envs_total, rank, ws)
-    means, _, _ = kernels.bandit_sample_means(hi - lo, dim, seed, lo)
+    if means_local is not None:
+        assert tuple(means_local.shape) == (hi - lo, dim), "means_local must be this rank's [%d, %d] slice" % (hi - lo, dim)
+        means = means_local.to(device=kernels._dev(), dtype=torch.float32, non_blocking=True)
+    else:
+        means, _, _ = kernels.bandit_sample_means(hi - lo, dim, seed, lo)
     if kind == "transformer":
         out = model.online_loop(means, horizon, var, ctrl.get("sample", True), seed, lo, materialise, True)
     else:

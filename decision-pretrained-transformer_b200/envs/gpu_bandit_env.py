@@ -39,6 +39,7 @@ class GPUBanditEnv(BaseEnv):
         self.current_step = torch.zeros(n_envs, device=self._device)
         self._step = 0        # host mirror of current_step (all envs advance together)
         self._draws = 0
+        self._rollouts = 0    # fused rollouts so far: each gets its own Philox key (a re-used env object must not replay noise)
 
     def get_arm_value(self, actions):
         return torch.sum(self.means * actions, dim=1)
@@ -56,10 +57,20 @@ class GPUBanditEnv(BaseEnv):
         self._draws += 1
         return self.state.detach(), r
 
-    def step(self, actions):
+    def set_means(self, means):
+        """Replace the drawn tasks (tests / callers that bring their own tasks): means [n_envs, dims]."""
+        self.means = kernels._as(means, torch.float32, self._device)
+        assert tuple(self.means.shape) == (self.n_envs, self.dims)
+        with torch.cuda.device(self._device):
+            idx, self.opt_a = kernels.bandit_opt_action(self.means)
+        self.opt_a_index = idx.long()
+
+    def step(self, actions, inject=None):
+        """``inject``: optional [n_envs] noise to consume instead of the Philox draw (parity runs): the standard
+        normals of type 'uniform' / the uniforms of type 'bernoulli'."""
         if self._step >= self.H:
             raise ValueError("Episode has already ended")
-        _, r = self.transit(self.state, actions)
+        _, r = self.transit(self.state, actions, inject=inject)
         self._step += 1
         self.current_step += 1
         done = self.current_step >= self.H
@@ -82,9 +93,11 @@ class GPUBanditEnv(BaseEnv):
         ``context[:, :K-1]`` with its own autograd-enabled model to get ``last_logits`` with gradients."""
         K = self.H if K is None else K
         with torch.cuda.device(self._device):
-            out = model.online_loop(self.means, K, float(self.var), sample, self._key ^ 0x2545F4914F6CDD1D, self._env_id0,
+            key = (self._key ^ 0x2545F4914F6CDD1D) + 0x9E3779B97F4A7C15 * self._rollouts & 0xFFFFFFFFFFFFFFFF
+            out = model.online_loop(self.means, K, float(self.var), sample, key, self._env_id0,
                                     materialise=True, regret=False, dump=True, reward_type=self.type)
         self._draws += K
+        self._rollouts += 1
         return {"context_states": out["context_states"], "context_actions": out["context_actions"],
                 "context_next_states": out["context_next_states"], "context_rewards": out["context_rewards"],
                 "logits": out["noise"]["logits"], "target": self.opt_a_index}

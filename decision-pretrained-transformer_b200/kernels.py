@@ -134,6 +134,17 @@ def bandit_rollin_host(means_host, H, var, seed, env_id0=0, out=None, scratch=No
     return out, scratch
 
 
+def host_write_peak(buf=None, nbytes=1 << 30, n_threads=0):
+    """GB/s the host cores reach with non-temporal stores (dpt_host_write_peak): into ``buf`` (a CPU tensor, e.g. the
+    pinned output arrays of the e2e path) or an internal buffer.  Needs no GPU."""
+    if buf is not None:
+        nbytes = buf.numel() * buf.element_size()
+    v = lib().dpt_host_write_peak(ptr(buf), int(nbytes), int(n_threads))
+    if not v > 0.0:
+        raise _lib.DptError("dpt_host_write_peak failed")
+    return float(v)
+
+
 # ------------------------------------------------------------------ darkroom -------------------
 def darkroom_rollin(goals, dim, H, mode, seed, env_id0=0, perm_index=None, n_samples=1, inject=None, dump=False):
     """Fused rollin_mdp (collect_data.py:83-111, :200-201).  goals [N,2] int; mode 'uniform'|'expert'.

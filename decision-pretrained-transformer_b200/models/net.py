@@ -253,6 +253,10 @@ class _Decoder:
         self._tok = torch.zeros((n_seqs, self.din), dtype=torch.float32, device=dev)
 
     def _step(self):
+        # the handle is owned by the model and destroyed when its weights change (handle() repacks): a decoder must
+        # never launch on a freed blob, and its K/V cache belongs to the old weights anyway
+        if self.model.handle() is not self._h:
+            raise RuntimeError("the model's weights changed since this decoder was created: build a new decoder")
         out = torch.empty((self.n, self.model.action_dim), dtype=torch.float32, device=self._tok.device)
         check(lib().dpt_gpt2_decode_step(self._h, ptr(self._tok), self.n, self.pos, self.t_max, self.precision, ptr(self.kv),
                                          self.kv.numel(), ptr(out), stream_ptr()), "dpt_gpt2_decode_step")

@@ -105,6 +105,13 @@ int dpt_peer_buffer_open(const unsigned char handle[64], void** dev_ptr);
 int dpt_peer_buffer_close(void* dev_ptr);
 int dpt_peer_buffer_destroy(void* dev_ptr);
 int dpt_peer_buffer_read(const void* dev_ptr, void* host_dst, uint64_t bytes, void* stream);  /* D2H + stream sync */
+int dpt_peer_buffer_zero(void* dev_ptr, uint64_t bytes, void* stream);  /* cudaMemsetAsync through a (peer) mapping:
+                                                                         * what a rank with an empty env shard publishes */
+/* Protocol notes for dpt_bandit_rollin_p2p / the peer buffers (reference: none -- the reference is single-process):
+ *  - the done-counter is reset by the launch that drains it, so all launches that share one counter must be issued
+ *    on ONE stream (stream order is what separates consecutive launches' counts);
+ *  - a slot may be re-used only after every rank has read it: order readers with stream-sync + barrier BEFORE the
+ *    read and a second barrier AFTER it (dist.collect_bandit_sharded does both). */
 
 /* Host-buffer form of the same call (the e2e path): means_host [N,d] in, the four context
  * arrays out, all HOST pointers (pinned for full speed).  Uses `scratch` (device, at least
@@ -120,6 +127,10 @@ int dpt_bandit_rollin_host(const float* means_host, float var, uint64_t seed, ui
 /* Bytes that crossed PCIe device->host in this thread's last dpt_bandit_rollin_host call (the pipeline returns a
  * self-balancing share of the chunks as arm index + reward, 5 B per step, and expands them on the host cores). */
 uint64_t dpt_bandit_rollin_host_last_d2h_bytes(void);
+/* Measurement aid for the e2e roofline (no reference counterpart): GB/s that `n_threads` host threads (0 = every
+ * core this process may run on) reach with non-temporal stores into `dst` (NULL: an internal buffer) of `bytes`
+ * bytes, best of three passes after a first-touch pass.  The host half of dpt_bandit_rollin_host is such a stream. */
+double dpt_host_write_peak(void* dst, uint64_t bytes, int n_threads);
 
 /* ---------------------------------------------------------------- R3/R4: rollin_mdp --------
  * collect_data.py:83-111 (rollin_mdp) fused with envs/darkroom_env.py:37-55 (transit), :69-82

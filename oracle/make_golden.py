@@ -354,6 +354,66 @@ def offline_eval(ref, name, seed, N, d, H, var, n_layer):
     print("ok", name)
 
 
+def gpu_bandit_env(ref, name, seed, N, d, H, var):
+    """envs/gpu_bandit_env.py:12-82 run on CPU with torch.randn / torch.bernoulli patched to record the noise they
+    return (bernoulli: the uniforms behind torch's own rule ``u < p``), H steps + the ValueError of step H+1."""
+    import torch
+    out = dict(N=N, d=d, H=H, var=var, seed=seed)
+    G = ref.gpu_bandit_env
+    for typ in ("uniform", "bernoulli"):
+        torch.manual_seed(seed)
+        env = G.GPUBanditEnv(d, N, H, var=var, type=typ, device=torch.device("cpu"))
+        attrs = {k: getattr(env, k) for k in ("dims", "dim", "n_envs", "H_context", "H", "var", "dx", "du", "topk", "type")}
+        assert attrs == dict(dims=d, dim=d, n_envs=N, H_context=H, H=H, var=var, dx=1, du=d, topk=False, type=typ)
+        out[typ + "_means"] = env.means.numpy().copy()
+        out[typ + "_opt_a_index"] = env.opt_a_index.numpy().copy()
+        out[typ + "_opt_a"] = env.opt_a.numpy().copy()
+        rec = []
+        real_randn, real_bern = torch.randn, torch.bernoulli
+
+        def randn(*a, **k):
+            z = real_randn(*a, **k)
+            rec.append(z.numpy().copy())
+            return z
+
+        def bernoulli(p_, *a, **k):
+            u = torch.rand(p_.shape)
+            rec.append(u.numpy().copy())
+            return (u < p_).to(p_.dtype)
+        torch.randn, torch.bernoulli = randn, bernoulli
+        try:
+            s0 = env.reset()
+            assert s0.shape == (N, 1) and bool((s0 == 1).all())
+            acts, rs, dones = [], [], []
+            g = torch.Generator().manual_seed(seed + 1)
+            for t in range(H):
+                a = torch.nn.functional.one_hot(torch.randint(0, d, (N,), generator=g), d).float()
+                st, r, done, info = env.step(a)
+                assert st.shape == (N, 1) and bool((st == 1).all()) and info == {} and done.dtype == torch.bool
+                acts.append(a.numpy().argmax(1)), rs.append(r.numpy().copy()), dones.append(done.numpy().copy())
+            try:
+                env.step(a)
+                raise AssertionError("reference did not raise past H")
+            except ValueError as e:
+                out[typ + "_error"] = str(e)
+            out[typ + "_arm_value"] = env.get_arm_value(a).numpy().copy()
+            out[typ + "_last_action"] = a.numpy().argmax(1)
+        finally:
+            torch.randn, torch.bernoulli = real_randn, real_bern
+        out[typ + "_actions"] = np.stack(acts).astype(np.int8)
+        out[typ + "_noise"] = np.stack(rec)
+        out[typ + "_rewards"] = np.stack(rs)
+        out[typ + "_done"] = np.stack(dones)
+        # the numpy restatement of transit (:53-63) reproduces the recorded rewards from the recorded noise
+        m = out[typ + "_means"]
+        for t in range(H):
+            ma = m[np.arange(N), acts[t]]
+            want = (ma + rec[t] * np.float32(var)) if typ == "uniform" else (rec[t] < ma).astype(np.float32)
+            _eq(rs[t], want.astype(np.float32), (name, typ, t))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("ok", name)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
@@ -375,11 +435,14 @@ def main():
                     goals=[(0, 0), (5, 5), (2, 3), (5, 0), (1, 4), (3, 3), (0, 5)])
     darkroom_online(ref, "darkroom_online_perm", seed=3, dim=5, horizon=6, H=12, Heps=4, n_layer=3, perm_indices=[0, 7, 57, 119])
     offline_eval(ref, "offline_bandit", seed=6, N=40, d=5, H=20, var=0.3, n_layer=2)
+    gpu_bandit_env(ref, "gpu_bandit_env", seed=8, N=64, d=5, H=4, var=0.3)
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "offline":
         offline_eval(ref_loader.load(), "offline_bandit", seed=6, N=40, d=5, H=20, var=0.3, n_layer=2)
+    elif len(sys.argv) > 1 and sys.argv[1] == "gpu_bandit_env":
+        gpu_bandit_env(ref_loader.load(), "gpu_bandit_env", seed=8, N=64, d=5, H=4, var=0.3)
     elif len(sys.argv) > 1 and sys.argv[1] == "darkroom_online":
         ref_ = ref_loader.load()
         darkroom_online(ref_, "darkroom_online", seed=2, dim=6, horizon=8, H=16, Heps=5, n_layer=2,

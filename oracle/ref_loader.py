@@ -7,20 +7,54 @@ top-level module names (``envs``, ``ctrls``, ``evals``, ``models``,
 ``collect_data``, ``utils`` ...) are moved out of ``sys.modules`` after import so
 that they never collide with the drop-in modules of this repo.
 
-``/root/reference`` does not exist on the GPU box: nothing that runs there
-(`-m gpu` tests, smoke(), bench.py) may call this module.
+``/root/reference`` does not exist on the GPU box.  ``stage()`` (called by ``__graft_entry__.build()``
+in the dev container) copies the reference's ``*.py`` files, unmodified, to the git-ignored
+``baseline/_ref/`` -- the place the bench contract reserves for the reference install -- which DOES
+travel to the box; ``bench.py``'s CPU legs (``cpu_baseline`` and ``--impl reference``) then time the
+reference's OWN functions from there.  The `-m gpu` tests and smoke() never call this module.
 """
 import importlib
 import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("DPT_REF", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGED = os.path.join(_REPO, "baseline", "_ref")
+LIVE = "/root/reference"
+
+
+def _pick_root():
+    env = os.environ.get("DPT_REF")
+    if env:
+        return env
+    return LIVE if os.path.isdir(os.path.join(LIVE, "envs")) else STAGED
+
+
+REF_ROOT = _pick_root()
 _TOP = ("envs", "ctrls", "evals", "models", "collect_data", "utils", "common_args", "dataset")
 
 
 def available():
     return os.path.isdir(os.path.join(REF_ROOT, "envs"))
+
+
+def stage(src=LIVE, dst=STAGED):
+    """Copy the reference's Python sources, byte for byte, to ``baseline/_ref`` (git-ignored, not
+    gpurun-ignored).  Returns the number of files copied (0 when ``src`` is absent)."""
+    import shutil
+    if not os.path.isdir(os.path.join(src, "envs")):
+        return 0
+    n = 0
+    for base, dirs, files in os.walk(src):
+        dirs[:] = [d for d in dirs if not d.startswith(".")]
+        for f in files:
+            if f.endswith((".py", ".txt", ".md")):
+                rel = os.path.relpath(os.path.join(base, f), src)
+                out = os.path.join(dst, rel)
+                os.makedirs(os.path.dirname(out), exist_ok=True)
+                shutil.copyfile(os.path.join(base, f), out)
+                n += 1
+    return n
 
 
 def _shims():

@@ -39,7 +39,20 @@ def main():
     flag = torch.tensor([1.0 if p2p_ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     p2p_ok = bool(flag.item() == 1.0)
+    # fewer envs than ranks: the ranks with an empty shard launch nothing and publish zeros (no hang, same totals)
+    b3, stats3 = D.collect_bandit_sharded(1, d, H, var, seed, peer=pg, peer_slot=0)
+    m1, _, _ = kernels.bandit_sample_means(1, d, seed, 0)
+    st1 = torch.zeros(3, dtype=torch.float64, device="cuda")
+    kernels.bandit_rollin(m1, H, var, seed, 0, stats=st1)
+    tiny_ok = abs(stats3["mean_reward"] - float(st1[0]) / H) < 1e-12 and stats3["env_steps"] == H
     pg.close()
+    # transformer controller (config 4 shape, small): sharded K/V-cached loop == slices of the single-GPU loop
+    from dpt_b200.models.net import Transformer
+    torch.manual_seed(0)
+    net = Transformer({"horizon": 48, "state_dim": 1, "action_dim": d, "n_layer": 2, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True})
+    NT = 3000
+    tout, tcurves = D.online_eval_sharded("transformer", NT, d, 48, var, seed, model=net)
+    allt = D.all_gather_stats(digest(tout["cum_means"]))
     out, curves = D.online_eval_sharded("thompson", N, d, H, var, seed, p0=var, p1=0.5, p2=1 / 12.0)
     cm = digest(out["cum_means"])
     allc = D.all_gather_stats(cm)
@@ -68,7 +81,14 @@ def main():
         ok &= abs(ref["mean_reward"] - stats["mean_reward"]) < 1e-9 and abs(ref["frac_optimal_arm"] - stats["frac_optimal_arm"]) < 1e-12
         rc = D.regret_stats_from_sums(fo["regret_sums"].cpu().numpy(), N)
         ok &= bool(np.allclose(rc["regret_mean"], curves["regret_mean"], rtol=1e-9)) and bool(np.allclose(rc["sem"], curves["sem"], rtol=1e-6))
-        ok &= p2p_ok
+        ok &= p2p_ok and tiny_ok
+        tm, _, _ = kernels.bandit_sample_means(NT, d, seed, 0)
+        tf = net.online_loop(tm, 48, var, True, seed, 0, False, True)
+        for r in range(ws):
+            a, b = D.shard_range(NT, r, ws)
+            ok &= bool(torch.equal(digest(tf["cum_means"][:, a:b]), allt[r]))
+        trc = D.regret_stats_from_sums(tf["regret_sums"].cpu().numpy(), NT)
+        ok &= bool(np.allclose(trc["regret_mean"], tcurves["regret_mean"], rtol=1e-9))
         print("multi_gpu_check world=%d: %s [p2p gather %s] (mean reward %.5f, final cumulative regret %.3f +- %.3f)" % (
             ws, "OK" if ok else "MISMATCH", "OK" if p2p_ok else "MISMATCH", stats["mean_reward"], curves["regret_mean"][-1], curves["regret_sem"][-1]))
     dist.barrier()

@@ -300,6 +300,49 @@ def test_gpu_bandit_env_matches_reference_semantics(dpt):
         GPUBanditEnv(5, 10, 4, type="gaussian")
 
 
+def test_gpu_bandit_env_golden(dpt):
+    """E5 pin: tests/golden/gpu_bandit_env.npz holds the reference's own GPUBanditEnv (envs/gpu_bandit_env.py:12-82) run
+    on CPU with torch.randn / torch.bernoulli patched to record their noise (oracle/make_golden.py:gpu_bandit_env)."""
+    from dpt_b200.envs.gpu_bandit_env import GPUBanditEnv
+    g = golden("gpu_bandit_env")
+    N, d, H, var = int(g["N"]), int(g["d"]), int(g["H"]), float(g["var"])
+    for typ in ("uniform", "bernoulli"):
+        env = GPUBanditEnv(d, N, H, var=var, type=typ, seed=1)
+        for k, v in dict(dims=d, dim=d, n_envs=N, H_context=H, H=H, var=var, dx=1, du=d, topk=False, type=typ).items():
+            assert getattr(env, k) == v, k
+        env.set_means(torch.tensor(g[typ + "_means"]))
+        assert np.array_equal(env.opt_a_index.cpu().numpy(), g[typ + "_opt_a_index"])          # int64 argmax: bit-exact
+        assert env.opt_a_index.dtype == torch.int64 and np.array_equal(env.opt_a.cpu().numpy(), g[typ + "_opt_a"])
+        s0 = env.reset()
+        assert s0.shape == (N, 1) and bool((s0 == 1).all())
+        for t in range(H):
+            a = torch.nn.functional.one_hot(torch.tensor(g[typ + "_actions"][t].astype(np.int64)), d).float().cuda()
+            st, r, done, info = env.step(a, inject=torch.tensor(g[typ + "_noise"][t]))
+            ref = g[typ + "_rewards"][t].astype(np.float64)
+            got = r.cpu().numpy().astype(np.float64)
+            if typ == "bernoulli":
+                assert np.array_equal(got, ref)                                                 # {0,1}: bit-exact
+            else:
+                assert np.all(np.abs(got - ref) <= 1e-5 * np.maximum(1.0, np.abs(ref)))
+            assert st.shape == (N, 1) and bool((st == 1).all()) and info == {} and done.dtype == torch.bool
+            assert np.array_equal(done.cpu().numpy(), g[typ + "_done"][t])
+        with pytest.raises(ValueError, match=str(g[typ + "_error"])):
+            env.step(a)
+        assert np.allclose(env.get_arm_value(a).cpu().numpy(), g[typ + "_arm_value"], rtol=1e-6, atol=0)
+
+
+def test_gpu_bandit_env_rollout_fresh_noise(dpt):
+    """A re-used env object must not replay the noise of its previous fused rollout."""
+    from dpt_b200.envs.gpu_bandit_env import GPUBanditEnv
+    from dpt_b200.models.net import Transformer
+    torch.manual_seed(0)
+    net = Transformer({"horizon": 8, "state_dim": 1, "action_dim": 5, "n_layer": 2, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True})
+    env = GPUBanditEnv(5, 256, 8, var=0.3, seed=5)
+    r1 = env.rollout(net)["context_rewards"].clone()
+    r2 = env.rollout(net)["context_rewards"].clone()
+    assert not torch.equal(r1, r2)
+
+
 def test_bandit_env_classes(dpt):
     from dpt_b200.envs.bandit_env import BanditEnv, BanditEnvVec, LinearBanditEnv
     dpt.seed(0)
