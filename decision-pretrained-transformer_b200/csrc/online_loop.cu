@@ -16,87 +16,11 @@
 // A thread's own rows are strided by H*d*4 B, so rows are staged per warp in shared memory (1 B per
 // action, 4 B per reward, 32 envs x 32 steps) and flushed as contiguous, 16 B-aligned float4 runs
 // (32 steps * d * 4 B per env).
-#include <type_traits>
+#include <cstdlib>
 
-#include "common.cuh"
-#include "philox.cuh"
+#include "online_loop.cuh"
 
 namespace dpt {
-
-constexpr int OL_WARPS = 2;    // max warps per CTA (small CTAs: 11 x 2 warps fit one SM's shared memory at d <= 5)
-constexpr int OL_THREADS = OL_WARPS * 32;
-constexpr int OL_T = 32;       // steps buffered per flush
-constexpr int OL_MAX_LD = 8;   // max lin_d
-
-enum { K_OPT = 0, K_EMP = 1, K_UCB = 2, K_THOMPSON = 3, K_LINUCB = 4, K_LINUCB2 = 5 /* internal: lin_d == 2, state in registers */ };
-
-struct OnlineParams {
-  double p0, p1, p2, var;
-  const float* means;
-  const double* arms;
-  int lin_d;
-  Key key;
-  uint64_t env_id0;
-  int N, H, d;
-  int rtype;         // DPT_REWARD_*
-  uint32_t magic_d;  // ceil(2^32 / d): floor(x / d) == umulhi(x, magic_d) for the small x used here
-  float *ctx_s, *ctx_a, *ctx_ns, *ctx_r, *cum_means;
-  double* regret;    // [regret_reps][H][4] accumulators (replicated to spread same-address atomics)
-  int regret_reps;   // power of two
-  dpt_online_inject_t in;
-  dpt_online_dump_t out;
-  bool vec;  // float4 flush allowed
-};
-
-struct WarpTile {
-  // env-major tiles written by lane = env and read back by lane = step; element (e, t) of the float tiles
-  // lives in column (t + e) & 31, which keeps both access directions bank-conflict free without padding
-  unsigned char acts[32][OL_T];
-  float rew[32][OL_T];
-  float creg[32][OL_T];       // cumulative regret of each env after each buffered step
-};
-
-template <int DMAX>
-struct ArmState {
-  double sum[DMAX];   // reward sum b
-  double aux0[DMAX];  // EMP/UCB: mean; THOMPSON: posterior mean
-  double aux1[DMAX];  // UCB: bonus; THOMPSON: posterior std
-  int cnt[DMAX];
-};
-
-// 4 standard normals per Philox block (two Box-Muller pairs)
-__device__ __forceinline__ void normals4(uint4 w, float z[4]) {
-  box_muller(w.x, w.y, z[0], z[1]);
-  box_muller(w.z, w.w, z[2], z[3]);
-}
-
-template <int LD>
-__device__ __forceinline__ void inv_small(const double* S, double* Si, int ld) {
-  // Gauss-Jordan with partial pivoting on [S | I] (S is SPD = I + A^T A, so it never fails)
-  double a[OL_MAX_LD][2 * OL_MAX_LD];
-  for (int i = 0; i < ld; ++i)
-    for (int j = 0; j < ld; ++j) a[i][j] = S[i * ld + j], a[i][ld + j] = (i == j) ? 1.0 : 0.0;
-  for (int c = 0; c < ld; ++c) {
-    int piv = c;
-    for (int r = c + 1; r < ld; ++r)
-      if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
-    if (piv != c)
-      for (int j = 0; j < 2 * ld; ++j) {
-        const double t = a[c][j];
-        a[c][j] = a[piv][j];
-        a[piv][j] = t;
-      }
-    const double inv = 1.0 / a[c][c];
-    for (int j = 0; j < 2 * ld; ++j) a[c][j] *= inv;
-    for (int r = 0; r < ld; ++r)
-      if (r != c) {
-        const double f = a[r][c];
-        for (int j = 0; j < 2 * ld; ++j) a[r][j] -= f * a[c][j];
-      }
-  }
-  for (int i = 0; i < ld; ++i)
-    for (int j = 0; j < ld; ++j) Si[i * ld + j] = a[i][ld + j];
-}
 
 // dynamic shared memory: [nwarps] WarpTile | [nwarps*32][DMAX] float means | (8 B-aligned) [d][lin_d] double arms
 __host__ __device__ inline size_t ol_arms_offset(int nwarps, int dmax) {
@@ -195,16 +119,12 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
     if (IO && p.in.reward_z) {
       for (int t = 0; t < T; ++t) tile.rew[lane][(t + lane) & (OL_T - 1)] = live ? p.in.reward_z[(size_t)(h0 + t) * N + env] : 0.f;
     } else {
-#pragma unroll 4
-      for (int t = 0; t < T; t += 2) {
-        const uint4 w = philox_words(p.key, gid, (uint32_t)((h0 + t) >> 1), STREAM_ENV_REWARD);
-        float z0, z1;
-        if (p.rtype == DPT_REWARD_GAUSSIAN)
-          box_muller(w.z, w.w, z0, z1);
-        else
-          z0 = u24(w.z), z1 = u24(w.w);
-        tile.rew[lane][(t + lane) & (OL_T - 1)] = z0;
-        tile.rew[lane][(t + 1 + lane) & (OL_T - 1)] = z1;
+#pragma unroll 2
+      for (int t = 0; t < T; t += 4) {   // one Philox block per 4 steps: (x, y) -> steps 4k, 4k+1; (z, w) -> 4k+2, 4k+3
+        float z4[4];
+        reward_noise4(p.key, gid, (uint32_t)((h0 + t) >> 2), p.rtype, z4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tile.rew[lane][(t + k + lane) & (OL_T - 1)] = z4[k];
       }
     }
     // ---- phase B: the sequential controller / env steps ----
@@ -456,7 +376,8 @@ __global__ void __launch_bounds__(256) regret_reduce_kernel(const double* __rest
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   double acc = 0.0;
-  for (int r = 0; r < n_reps; ++r) acc += reps[(size_t)r * n + i];
+#pragma unroll 8
+  for (int r = 0; r < n_reps; ++r) acc += reps[(size_t)r * n + i];   // (fixed order; independent loads, 8 in flight)
   regret[i] += acc;
 }
 
@@ -548,23 +469,37 @@ extern "C" int dpt_online_loop(int ctrl_kind, double p0, double p1, double p2, c
   cudaStream_t st = (cudaStream_t)stream;
   // Every warp adds its 32 envs' partial sums to the same [H,4] block, tile by tile and nearly in lockstep:
   // spread them over replicated accumulators (stream-ordered scratch, <= 4 MB) and fold the replicas afterwards.
+  // DPT_OL_IMPL: 0 / unset = warp-specialised kernel where it applies (d <= 10, lin_d == 2), 1 = always the general kernel
+  static const int impl = [] {
+    const char* s = getenv("DPT_OL_IMPL");
+    return s ? atoi(s) : 0;
+  }();
+  const bool ws = impl != 1 && online_ws_supported(ctrl_kind, p);
   double* reps = nullptr;
+  unsigned char* scratch = nullptr;
   p.regret_reps = 1;
-  if (regret_sums && N > 32 * 8) {
-    int r = 64;
+  int r = 1;
+  if (ws) {
+    if (regret_sums) r = N > 32 * 64 ? 16 : 1;      // regret_pass_kernel: one atomic set per warp (32 envs) and 16-step tile
+  } else if (regret_sums && N > 32 * 8) {
+    r = 64;
     while (r > 1 && (size_t)r * H * 32 > (4u << 20)) r >>= 1;
-    if (r > 1) {
-      keep_pool_memory();
-      e = cudaMallocAsync(reinterpret_cast<void**>(&reps), (size_t)r * H * 32, st);
-      if (e == cudaSuccess) e = cudaMemsetAsync(reps, 0, (size_t)r * H * 32, st);
-      if (e != cudaSuccess) {
-        set_error("dpt_online_loop: regret scratch: %s", cudaGetErrorString(e));
-        return DPT_ERR_CUDA;
-      }
-      p.regret = reps, p.regret_reps = r;
-    }
   }
-  if (d <= 5)
+  const size_t reps_bytes = (ws ? (regret_sums != nullptr) : r > 1) ? (size_t)r * H * 32 : 0;
+  const size_t tab_bytes = ws ? 2 * (size_t)(H + 1) * sizeof(double) : 0;
+  if (reps_bytes + tab_bytes) {
+    keep_pool_memory();
+    e = cudaMallocAsync(reinterpret_cast<void**>(&scratch), reps_bytes + tab_bytes, st);
+    if (e == cudaSuccess && reps_bytes) e = cudaMemsetAsync(scratch, 0, reps_bytes, st);
+    if (e != cudaSuccess) {
+      set_error("dpt_online_loop: scratch: %s", cudaGetErrorString(e));
+      return DPT_ERR_CUDA;
+    }
+    if (reps_bytes) reps = reinterpret_cast<double*>(scratch), p.regret = reps, p.regret_reps = r;
+  }
+  if (ws)
+    e = launch_online_ws(ctrl_kind, p, reinterpret_cast<double*>(scratch + reps_bytes), regret_sums, st);
+  else if (d <= 5)
     e = launch_online_kind<5>(ctrl_kind, p, st);
   else if (d <= 10)
     e = launch_online_kind<10>(ctrl_kind, p, st);
@@ -572,13 +507,11 @@ extern "C" int dpt_online_loop(int ctrl_kind, double p0, double p1, double p2, c
     e = launch_online_kind<16>(ctrl_kind, p, st);
   else
     e = launch_online_kind<32>(ctrl_kind, p, st);
-  if (reps) {
-    if (e == cudaSuccess) {
-      regret_reduce_kernel<<<(H * 4 + 255) / 256, 256, 0, st>>>(reps, p.regret_reps, H * 4, regret_sums);
-      e = cudaGetLastError();
-    }
-    cudaFreeAsync(reps, st);
+  if (!ws && reps && e == cudaSuccess) {
+    regret_reduce_kernel<<<(H * 4 + 255) / 256, 256, 0, st>>>(reps, p.regret_reps, H * 4, regret_sums);
+    e = cudaGetLastError();
   }
+  if (scratch) cudaFreeAsync(scratch, st);
   if (e != cudaSuccess) {
     set_error("dpt_online_loop launch failed: %s", cudaGetErrorString(e));
     return DPT_ERR_CUDA;

@@ -1,0 +1,541 @@
+// Fast fused online evaluation loop for the classical bandit controllers (d <= 10).
+//
+// Same contract as online_loop.cu's general kernel (reference evals/eval_bandit.py:56-103 + envs/bandit_env.py:56-64,
+// :98-149 + ctrls/ctrl_bandit.py act_numpy_vec / set_batch_numpy_vec), re-cut around what ncu showed of that kernel
+// (39-52 % issue utilisation, 21 warps per SM at 100k envs, 145-540 instructions per warp-step of which the
+// controller proper is a minority).  One warp owns 32 envs (lane = env) for all H steps:
+//   per step   pick arm -> reward -> O(1) statistics update -> stage the arm (as a byte and as a bit of the step quad's
+//       one-hot bit string) and the reward in shared memory, store cum_means[h, env] (coalesced across the warp).
+//       The per-arm (sum, count) live in shared memory (only the pulled arm is touched), the cached decision
+//       statistics in registers: 64 registers per thread, so that 32 warps are resident per SM and 100k envs
+//       (21.1 warps per SM) are ONE wave.  Everything that depends on a count only (1/n, the UCB bonus, Thompson's
+//       1/(var + n prior_var) and posterior std) comes from a [2][H+1] float64 table, so a step has no float64
+//       division or square root.  float64 like the reference: the arm is the reference's arm.
+//       Reward noise: one Philox block + two Box-Muller pairs per step quad, off the controller's dependency chain.
+//   per tile (WT steps)   the warp drains its own staging tile: rewards and one-hot rows leave as contiguous 16 B stores --
+//       a float4 of an env's one-hot run is one nibble of the quad's bit string, i.e. one shared load + one 16-entry
+//       table lookup -- in batches of four independent load / lookup / store chains.
+//   The per-step regret sums [H,4] are NOT accumulated here: regret_pass_kernel (below) streams cum_means [H,N]
+//   once afterwards.
+// Measured dead end kept in DESIGN.md: the warp-specialised form of this kernel (3 controller warps + 1 flush / noise
+// warp per CTA, tiles handed over through mbarriers) -- the single helper warp runs ~50-230 dependent instructions
+// per step for its three controllers and becomes the bottleneck (controllers stalled 12 % of their time on the
+// "tile drained" barrier); letting every warp drain its own tile has no hand-over and the same instruction count.
+// HBM traffic per env-step: 4 (2 + d + 1) B of context rows + 4 B of cum_means (36 B at d = 5).
+#include "online_loop.cuh"
+
+namespace dpt {
+
+#ifndef DPT_WS_WT5
+#define DPT_WS_WT5 32
+#endif
+#ifndef DPT_WS_WT10
+#define DPT_WS_WT10 16
+#endif
+#ifndef DPT_WS_NCONS
+#define DPT_WS_NCONS 4
+#endif
+// steps per staging tile (multiple of 4): 32 at d <= 5, 16 at d <= 10 (shared memory per warp: 32 warps must stay resident)
+template <int DMAX>
+constexpr int ws_wt() { return DMAX <= 5 ? DPT_WS_WT5 : DPT_WS_WT10; }
+constexpr int WS_NCONS = DPT_WS_NCONS; // warps per CTA
+
+template <int DMAX>
+struct alignas(16) WsTile {
+  static constexpr int WT = ws_wt<DMAX>(), WQ = WT / 4;   // steps / float4 slots per env and tile
+  static constexpr int BWQ = (4 * DMAX + 31) / 32;   // words of one-hot bits per step quad (4 DMAX bits)
+  static constexpr int BROW = (WQ * BWQ) | 1;        // odd row lengths: lane = env accesses are bank-conflict free
+  float4 rew[32][WQ];        // rewards; float4 slot q of env e lives in column q ^ swz(e) (conflict-free 16 B accesses)
+  uint32_t acts[32][WQ | 1]; // pulled arm per step, one byte each
+  uint32_t bits[32][BROW];   // one-hot rows of each step quad as a bit string (DMAX bits per step): nibble f of quad q is
+                             // float4 q DMAX + f of the env's run of T d floats
+};
+
+template <int DMAX, bool STATS>
+struct alignas(16) WsCons {
+  WsTile<DMAX> tile;
+  float means[32][DMAX];
+  double sum[STATS ? DMAX : 1][32];   // reward sum per arm   (only the pulled arm is touched in a step)
+  int cnt[STATS ? DMAX : 1][32];      // pull count per arm
+};
+
+// a quarter warp (8 envs) x one float4 slot must hit 8 distinct 16 B bank groups: rows are WQ groups long
+template <int WQ>
+__device__ __forceinline__ int swz_t(int e) { return WQ >= 8 ? (e & 7) : ((e / (8 / (WQ >= 8 ? 8 : WQ))) & (WQ - 1)); }
+
+// a / n for a count n >= 1 with rc = RN(1 / n) from the table: two FMA corrections give the correctly rounded
+// quotient (Markstein), i.e. the reference's b / max(1, counts) bit for bit -- checked by dpt_selftest_div
+__device__ __forceinline__ double div_by_count(double a, int n, double rc) {
+  const double nd = (double)n;
+  double q = a * rc;
+  q = fma(fma(-nd, q, a), rc, q);
+  q = fma(fma(-nd, q, a), rc, q);
+  return q;
+}
+
+template <int DMAX, int KIND, bool IO>
+struct WsKernel {
+  static constexpr bool STATS = (KIND == K_EMP || KIND == K_UCB || KIND == K_THOMPSON);
+  using Cons = WsCons<DMAX, STATS>;
+  using Tile = WsTile<DMAX>;
+  static constexpr int BWQ = Tile::BWQ, WT = Tile::WT, WQ = Tile::WQ;
+  static __device__ __forceinline__ int swz(int e) { return swz_t<WQ>(e); }
+  static constexpr int NB2 = (2 * DMAX + 3) / 4;   // Philox blocks of control normals per step pair (Thompson)
+
+  // ------------------------------------------------------------------------------- drain one staging tile
+  static __device__ __forceinline__ void flush(const OnlineParams& p, const Tile& tl, const float4* s_nib, int env0, int nl, int h0, int T,
+                                               bool bits_ok, bool vec_r, int lane) {
+    const int H = p.H, d = p.d;
+    // rewards: T * 4 B per env and tile
+    if (vec_r) {
+#pragma unroll
+      for (int it = 0; it < WQ; ++it) {
+        const int e = it * (32 / WQ) + lane / WQ, q = lane % WQ;
+        if (e < nl && 4 * q < T)
+          st_stream(reinterpret_cast<float4*>(p.ctx_r + (size_t)(env0 + e) * H + h0) + q, tl.rew[e][q ^ swz(e)]);
+      }
+    } else {
+      for (int i = lane; i < nl * WT; i += 32) {
+        const int e = i / WT, t = i % WT;
+        if (t < T) {
+          const float4 r4 = tl.rew[e][(t >> 2) ^ swz(e)];
+          const int u = t & 3;
+          st_stream(p.ctx_r + (size_t)(env0 + e) * H + h0 + t, u == 0 ? r4.x : u == 1 ? r4.y : u == 2 ? r4.z : r4.w);
+        }
+      }
+    }
+    // one-hot rows
+    if (bits_ok) {   // d == DMAX and T % 4 == 0: float4 g of an env's run of T*d floats is nibble g % DMAX of step quad g / DMAX
+      // lane = (env of a group of 4, 8 consecutive float4): every store covers whole 128 B lines of 4 envs
+      const int nbn = (T >> 2) * DMAX;                 // float4 per env in this tile
+      const int gl = lane & 7;
+      const size_t estride = ((size_t)H * DMAX) >> 2;
+      float4* dst0 = reinterpret_cast<float4*>(p.ctx_a + ((size_t)env0 * H + h0) * DMAX) + gl;
+      constexpr int NK = (WQ * DMAX + 7) / 8;          // iterations over g = 8 k + gl
+#pragma unroll 2
+      for (int e = lane >> 3; e < nl; e += 4) {
+        const uint32_t* brow = tl.bits[e];
+        float4* dst = dst0 + (size_t)e * estride;
+        uint32_t nib[NK];
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+          const int g = min(8 * k + gl, WQ * DMAX - 1);
+          const int q = g / DMAX, f = g - q * DMAX;
+          nib[k] = (brow[q * BWQ + (f >> 3)] >> (4 * (f & 7))) & 15u;
+        }
+#pragma unroll
+        for (int k = 0; k < NK; ++k) st_stream_if(8 * k + gl < nbn, dst + 8 * k, s_nib[nib[k]]);
+      }
+    } else {
+      const int per = T * d;
+      for (int e = 0; e < nl; ++e)
+        for (int el = lane; el < per; el += 32) {
+          const int t = (d == 1) ? el : (int)__umulhi((uint32_t)el, p.magic_d);
+          const int a = (tl.acts[e][t >> 2] >> (8 * (t & 3))) & 255;
+          st_stream(p.ctx_a + ((size_t)(env0 + e) * H + h0) * d + el, (a == el - t * d) ? 1.f : 0.f);
+        }
+    }
+  }
+
+  // ------------------------------------------------------------------------------- controller warp
+  struct State {
+    double st0[STATS ? DMAX : 1];              // EMP: mean; UCB: mean + bonus; THOMPSON: posterior mean
+    double st1[KIND == K_THOMPSON ? DMAX : 1]; // THOMPSON: posterior std
+    double s00, s01, s11, b0, b1;              // LinUCB (lin_d = 2): Sigma = I + sum x x^T, b = sum x r
+    uint32_t untried;
+  };
+
+  // one step quad (4 steps; FULL: all four exist).  Returns nothing; stages rewards / arms / one-hot bits of the quad.
+  template <bool FULL>
+  static __device__ __forceinline__ void quad(const OnlineParams& p, Cons& cs, Tile& tl, State& S, const double* s_arms,
+                                              const double* __restrict__ tab0, const double* __restrict__ tab1, int h, int nsteps, int q,
+                                              int opt, int env, bool live, uint64_t gid, float*& cmp, double sigma2tc0, bool stage, int lane) {
+    const int N = p.N, H = p.H, d = p.d;
+    // reward noise of the quad: one Philox block + two Box-Muller pairs, off the controller's dependency chain
+    float zz[4];
+    if (IO && p.in.reward_z) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) zz[t] = (live && h + t < H) ? p.in.reward_z[(size_t)(h + t) * N + env] : 0.f;
+    } else {
+      reward_noise4(p.key, gid, (uint32_t)(h >> 2), p.rtype, zz);   // h is a multiple of 4 (tiles and quads are)
+    }
+    if (IO && p.out.reward_z && live) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (h + t < H) p.out.reward_z[(size_t)(h + t) * N + env] = zz[t];
+    }
+    float rr[4] = {0.f, 0.f, 0.f, 0.f};
+    uint32_t aw = 0u;
+    uint64_t bq = 0ull;
+    float zc[KIND == K_THOMPSON ? 2 * DMAX : 1];                  // control normals of the current step pair
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!FULL && u >= nsteps) break;
+      const int hh = h + u;
+      // ------------------------------------------------ controller: pick an arm ------------
+      int a = 0;
+      if (KIND == K_OPT) {
+        a = opt;                                                        // ctrl_bandit.py:35-37
+      } else if (KIND == K_EMP || KIND == K_UCB) {
+        double best = -INFINITY;   // padding arms j >= d carry -inf and are never picked
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j)
+          if (S.st0[j] > best) best = S.st0[j], a = j;                  // np.argmax: first maximum  :106 | :369-370
+        if ((KIND == K_UCB || p.p0 != 0.0) && S.untried) a = __ffs(S.untried) - 1;   // np.argmin(counts) when min == 0  :110-113 | :373-375
+      } else if (KIND == K_THOMPSON) {
+        if ((u & 1) == 0) {               // control normals of steps hh, hh + 1: NB2 Philox blocks per step pair
+          if (IO && p.in.ctrl_z) {
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+              for (int j = 0; j < DMAX; ++j)
+                zc[s2 * DMAX + j] = (live && j < d && hh + s2 < H) ? p.in.ctrl_z[((size_t)(hh + s2) * N + env) * d + j] : 0.f;
+          } else {
+#pragma unroll
+            for (int bk = 0; bk < NB2; ++bk) {
+              float z4n[4];
+              normals4(philox_words(p.key, gid, (uint32_t)((hh >> 1) * NB2 + bk), STREAM_CTRL), z4n);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (4 * bk + k < 2 * DMAX) zc[4 * bk + k] = z4n[k];
+            }
+          }
+        }
+        double best = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j) {
+          const float zj = zc[(u & 1) * DMAX + j];
+          if (IO && p.out.ctrl_z && live && j < d) p.out.ctrl_z[((size_t)hh * N + env) * d + j] = zj;
+          const double v = fma(S.st1[j], (double)zj, S.st0[j]);         // np.random.normal(means, sqrt(variances)) :234
+          if (v > best) best = v, a = j;                                // (padding arms: mean -inf, std 0)
+        }
+      } else if (KIND == K_LINUCB2) {
+        if (hh == 0) {                                                  // :496-500 uniform random first arm
+          if (IO && p.in.first_arm)
+            a = live ? p.in.first_arm[env] : 0;
+          else
+            a = (int)bounded(philox_words(p.key, gid, 0u, STREAM_CTRL).x, (uint32_t)d);
+          if (IO && p.out.first_arm && live) p.out.first_arm[env] = a;
+        } else {   // lin_d == 2: closed-form inverse, everything in registers
+          const double idet = 1.0 / (S.s00 * S.s11 - S.s01 * S.s01);
+          const double i00 = S.s11 * idet, i01 = -S.s01 * idet, i11 = S.s00 * idet;
+          const double t0 = i00 * S.b0 + i01 * S.b1, t1 = i01 * S.b0 + i11 * S.b1;   // theta = cov_inv @ A^T r  :513
+          double best = -INFINITY;
+          for (int j = 0; j < d; ++j) {
+            const double x0 = s_arms[2 * j], x1 = s_arms[2 * j + 1];
+            const double qf = x0 * (i00 * x0 + i01 * x1) + x1 * (i01 * x0 + i11 * x1);
+            const double v = (t0 * x0 + t1 * x1) + p.p0 * sqrt(qf);                 // :519
+            if (v > best) best = v, a = j;                                           // strict >: first maximum :520
+          }
+        }
+      }
+      // ------------------------------------------------ env step ---------------------------
+      const float z = zz[u];
+      const float ma = cs.means[lane][a];
+      const double r = p.rtype == DPT_REWARD_GAUSSIAN ? (double)ma + (0.0 + p.var * (double)z)   // envs/bandit_env.py:59
+                                                      : (z < ma ? 1.0 : 0.0);                    // :61 Bernoulli(mean)
+      // ------------------------------------------------ controller statistics --------------
+      if (STATS) {
+        const double sa = cs.sum[a][lane] + r;
+        const int ca = cs.cnt[a][lane] + 1;
+        cs.sum[a][lane] = sa, cs.cnt[a][lane] = ca;
+        S.untried &= ~(1u << a);
+        double n0, n1 = 0.0;
+        if (KIND == K_THOMPSON) {   // update_posterior_all :196-203, over the common denominator var + n*prior_var
+          n0 = fma(p.p2, sa, sigma2tc0) * __ldg(tab0 + ca);   // = w*prior_mean + (1-w)*sum/n,  w = var/(var + n*prior_var)
+          n1 = __ldg(tab1 + ca);                              // = sqrt(1 / (1/prior_var + n/var))
+        } else {
+          n0 = div_by_count(sa, ca, __ldg(tab0 + ca));        // b / max(1, counts)
+          if (KIND == K_UCB) n0 += __ldg(tab1 + ca);          // + const / max(1, sqrt(counts)) :366
+        }
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j) {
+          const bool hit = (j == a);
+          S.st0[j] = hit ? n0 : S.st0[j];
+          if (KIND == K_THOMPSON) S.st1[j] = hit ? n1 : S.st1[j];
+        }
+      } else if (KIND == K_LINUCB2) {
+        const double x0 = s_arms[2 * a], x1 = s_arms[2 * a + 1];
+        S.b0 += x0 * r, S.b1 += x1 * r;
+        S.s00 += x0 * x0, S.s01 += x0 * x1, S.s11 += x1 * x1;
+      }
+      // ------------------------------------------------ outputs ----------------------------
+      if (live) st_stream(cmp, ma);                                     // get_arm_value :151-153 -> cum_means[hh, env]
+      cmp += N;
+      rr[u] = (float)r;
+      aw |= (uint32_t)a << (8 * u);
+      bq |= (uint64_t)(1u << a) << (u * DMAX);                          // one-hot row of step u at bit u * DMAX of the quad's string
+    }
+    if (stage) {
+      tl.rew[lane][q ^ swz(lane)] = make_float4(rr[0], rr[1], rr[2], rr[3]);
+      tl.acts[lane][q] = aw;
+      tl.bits[lane][q * BWQ] = (uint32_t)bq;
+      if (BWQ > 1) tl.bits[lane][q * BWQ + 1] = (uint32_t)(bq >> 32);
+    }
+  }
+
+  static __device__ __forceinline__ void controller(const OnlineParams& p, Cons& cs, const double* s_arms, const float4* s_nib,
+                                                    const double* __restrict__ tab0, const double* __restrict__ tab1, int env, bool live, int lane) {
+    const int N = p.N, H = p.H, d = p.d;
+    const bool stage = p.ctx_a != nullptr;     // context materialised: tiles go through the flush warp
+    const uint64_t gid = p.env_id0 + (uint64_t)env;
+    float mmax = -INFINITY;
+    int opt = 0;
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j) {
+      const float mj = (live && j < d) ? p.means[(size_t)env * d + j] : -INFINITY;
+      if (mj > mmax) mmax = mj, opt = j;
+      cs.means[lane][j] = mj;
+      if (STATS) cs.sum[j][lane] = 0.0, cs.cnt[j][lane] = 0;
+    }
+    __syncwarp();
+    State S;
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j) {   // before the first pull: EMP mean 0, UCB 0 + bonus(0) = const, THOMPSON the prior;
+      const bool real = j < d;         // padding arms (j >= d) can never win an argmax
+      if (KIND == K_EMP) S.st0[j] = real ? 0.0 : -INFINITY;
+      if (KIND == K_UCB) S.st0[j] = real ? 0.0 + p.p0 : -INFINITY;
+      if (KIND == K_THOMPSON) S.st0[j] = real ? p.p1 : -INFINITY, S.st1[j] = real ? sqrt(p.p2) : 0.0;
+    }
+    S.untried = (d >= 32) ? 0xffffffffu : ((1u << d) - 1u);
+    S.s00 = 1.0, S.s01 = 0.0, S.s11 = 1.0, S.b0 = 0.0, S.b1 = 0.0;
+    const double sigma2tc0 = p.p0 * p.p0 * p.p1;                  // Thompson: std^2 (ctrls/ctrl_bandit.py:126) * prior_mean
+    const int ntiles = (H + WT - 1) / WT;
+    float* cmp = p.cum_means + env;       // (never NULL here: online_ws_supported)
+    const int env0 = env - lane, nl = min(32, N - env0);
+    const bool bits_ok = p.vec && d == DMAX && (H % 4 == 0);
+    const bool vec_r = (H % 4 == 0) && (reinterpret_cast<uintptr_t>(p.ctx_r) & 15) == 0;
+    if (stage) {   // constant states (bandit dx = 1): this warp's envs are one contiguous run
+      fill_range(p.ctx_s, (size_t)env0 * H, (size_t)(env0 + nl) * H, 1.0f, lane, 32);
+      fill_range(p.ctx_ns, (size_t)env0 * H, (size_t)(env0 + nl) * H, 1.0f, lane, 32);
+    }
+    Tile& tl = cs.tile;
+    for (int i = 0; i < ntiles; ++i) {
+      const int h0 = i * WT, T = min(WT, H - h0);
+      const int nq = T >> 2;
+#pragma unroll 1
+      for (int q = 0; q < nq; ++q)
+        quad<true>(p, cs, tl, S, s_arms, tab0, tab1, h0 + 4 * q, 4, q, opt, env, live, gid, cmp, sigma2tc0, stage, lane);
+      if (T & 3) quad<false>(p, cs, tl, S, s_arms, tab0, tab1, h0 + 4 * nq, T & 3, nq, opt, env, live, gid, cmp, sigma2tc0, stage, lane);
+      if (stage) {
+        __syncwarp();
+        flush(p, tl, s_nib, env0, nl, h0, T, bits_ok, vec_r, lane);
+        __syncwarp();
+      }
+    }
+  }
+};
+
+// threads per SM the kernel is compiled for: 1024 (64 registers) so that 100k envs (21.1 warps per SM) are ONE wave;
+// Thompson at d = 10 keeps 40 float64 statistics in registers and gets 512
+template <int DMAX, int KIND>
+constexpr int ws_min_blocks() { return ((DMAX > 5 && KIND == K_THOMPSON) ? 512 : 1024) / (WS_NCONS * 32); }
+
+template <int DMAX, int KIND, bool IO>
+__global__ void __launch_bounds__(WS_NCONS * 32, ws_min_blocks<DMAX, KIND>()) online_loop_ws_kernel(const OnlineParams p, const double* __restrict__ tab) {
+  using K = WsKernel<DMAX, KIND, IO>;
+  using Cons = typename K::Cons;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float4 s_nib[16];   // 4-bit pattern -> four 0/1 floats (one-hot flush)
+  Cons* cons = reinterpret_cast<Cons*>(smem_raw);
+  double* s_arms = reinterpret_cast<double*>(smem_raw + sizeof(Cons) * WS_NCONS);   // [d][2] (LinUCB)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 16) s_nib[tid] = make_float4((tid & 1) ? 1.f : 0.f, (tid & 2) ? 1.f : 0.f, (tid & 4) ? 1.f : 0.f, (tid & 8) ? 1.f : 0.f);
+  if (KIND == K_LINUCB2)
+    for (int i = tid; i < p.d * 2; i += blockDim.x) s_arms[i] = p.arms[i];
+  __syncthreads();
+  const int env = (blockIdx.x * WS_NCONS + warp) * 32 + lane;
+  if (env - lane < p.N)            // warp-uniform
+    K::controller(p, cons[warp], s_arms, s_nib, tab, tab + (p.H + 1), env, env < p.N, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Regret statistics (evals/eval_bandit.py:169-178) from cum_means [H,N]: sums over envs, per step, of the regret
+// reg = max(means) - cum_means, reg^2, the cumulative regret and its square.  One warp per 32 envs: lane = env for
+// the loads (128 B per step row) and the float64 prefix over steps, lane = step for the sums over the 32 envs
+// (32 x 32 tile through shared memory), then one atomic per (step, statistic) and warp into replicated accumulators.
+// ---------------------------------------------------------------------------------------------
+constexpr int RP_WARPS = 4;
+constexpr int RP_T = 16;      // steps per tile: 32 envs x 16 steps (6.5 KB of shared memory per warp, so 100k envs are one wave)
+__global__ void __launch_bounds__(RP_WARPS * 32, 6) regret_pass_kernel(const float* __restrict__ cum_means, const float* __restrict__ means, int N,
+                                                                       int H, int d, double* __restrict__ reps, int n_reps) {
+  __shared__ float s_cm[RP_WARPS][32][RP_T + 1];
+  __shared__ double s_cr[RP_WARPS][32][RP_T + 1];
+  __shared__ float s_mx[RP_WARPS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * RP_WARPS + warp, env0 = gw * 32;
+  if (env0 >= N) return;
+  const int env = env0 + lane, nl = min(32, N - env0);
+  const bool live = env < N;
+  float mmax = -INFINITY;
+  if (live)
+    for (int j = 0; j < d; ++j) mmax = fmaxf(mmax, means[(size_t)env * d + j]);
+  s_mx[warp][lane] = mmax;
+  double creg = 0.0;
+  double* acc = reps + 3 * (size_t)(gw & (n_reps - 1)) * H;    // [n_reps][H][3]: sum reg, sum reg^2, sum creg^2
+  const int t = lane & (RP_T - 1), half = lane >> 4;           // sums over envs: lane = (half of the envs, step)
+  const float* src = cum_means + env;
+  float cm[RP_T], nx[RP_T];
+#pragma unroll
+  for (int k = 0; k < RP_T; ++k) nx[k] = (live && k < H) ? __ldcs(src + (size_t)k * N) : 0.f;
+  for (int h0 = 0; h0 < H; h0 += RP_T) {
+    const int T = min(RP_T, H - h0);
+#pragma unroll
+    for (int k = 0; k < RP_T; ++k) cm[k] = nx[k];
+#pragma unroll
+    for (int k = 0; k < RP_T; ++k)   // next tile's loads are in flight while this one is reduced
+      nx[k] = (live && h0 + RP_T + k < H) ? __ldcs(src + (size_t)(h0 + RP_T + k) * N) : 0.f;
+#pragma unroll
+    for (int k = 0; k < RP_T; ++k) {
+      creg += (double)mmax - (double)cm[k];
+      s_cm[warp][lane][k] = cm[k];
+      s_cr[warp][lane][k] = creg;
+    }
+    __syncwarp();
+    double s1 = 0.0, s2 = 0.0, c2 = 0.0;
+#pragma unroll 4
+    for (int e = half; e < nl; e += 2) {
+      const double reg = (double)s_mx[warp][e] - (double)s_cm[warp][e][t];
+      const double cr = s_cr[warp][e][t];
+      s1 += reg, s2 = fma(reg, reg, s2), c2 = fma(cr, cr, c2);
+    }
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 16), s2 += __shfl_xor_sync(0xffffffffu, s2, 16), c2 += __shfl_xor_sync(0xffffffffu, c2, 16);
+    if (lane < T) {
+      double* dst = acc + 3 * (size_t)(h0 + lane);
+      atomicAdd(dst, s1), atomicAdd(dst + 1, s2), atomicAdd(dst + 2, c2);
+    }
+    __syncwarp();
+  }
+}
+
+// regret[h] += (S1, S2, C1, C2)[h]: S1, S2, C2 folded over the replicas in a fixed order; the sum over envs of the cumulative
+// regret is linear in the per-step sums, C1[h] = sum_{h' <= h} S1[h'], so it is a prefix over steps (one block, carry per chunk)
+__global__ void __launch_bounds__(1024) regret_finish_kernel(const double* __restrict__ reps, int n_reps, int H, double* __restrict__ regret) {
+  __shared__ double s_warp[32];
+  __shared__ double s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0.0;
+  __syncthreads();
+  for (int h0 = 0; h0 < H; h0 += 1024) {
+    const int h = h0 + threadIdx.x;
+    double s1 = 0.0, s2 = 0.0, c2 = 0.0;
+    if (h < H) {
+#pragma unroll 16
+      for (int r = 0; r < n_reps; ++r) {   // fixed order; independent loads
+        const double* src = reps + 3 * ((size_t)r * H + h);
+        s1 += src[0], s2 += src[1], c2 += src[2];
+      }
+    }
+    double sc = s1;                         // inclusive scan of s1 over the 1024 steps of this chunk
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double v = __shfl_up_sync(0xffffffffu, sc, o);
+      if (lane >= o) sc += v;
+    }
+    if (lane == 31) s_warp[warp] = sc;
+    __syncthreads();
+    if (warp == 0) {
+      double w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double v = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += v;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const double c1 = s_carry + (warp ? s_warp[warp - 1] : 0.0) + sc;
+    if (h < H) {
+      double* dst = regret + 4 * (size_t)h;
+      dst[0] += s1, dst[1] += s2, dst[2] += c1, dst[3] += c2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = c1;
+    __syncthreads();
+  }
+}
+
+// count-indexed float64 terms, n = 0..H.  EMP / UCB: tab0 = 1 / max(1, n), tab1 = const / max(1, sqrt(n));
+// THOMPSON: tab0 = 1 / (var + n prior_var), tab1 = sqrt(var prior_var tab0)  -- the expressions of online_loop.cu
+__global__ void online_ws_table_kernel(int kind, double p0, double p2, int H, double* __restrict__ tab) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n > H) return;
+  double t0, t1;
+  if (kind == K_THOMPSON) {
+    const double sigma2 = p0 * p0;
+    t0 = 1.0 / (sigma2 + (double)n * p2);
+    t1 = sqrt(sigma2 * p2 * t0);
+  } else {
+    t0 = 1.0 / fmax(1.0, (double)n);
+    t1 = p0 / fmax(1.0, sqrt((double)n));
+  }
+  tab[n] = t0, tab[(H + 1) + n] = t1;
+}
+
+// selftest: div_by_count(a, n, RN(1/n)) == a / n bit for bit
+__global__ void selftest_div_kernel(const double* __restrict__ a, const int* __restrict__ n, int count, int* __restrict__ mismatches) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const double want = a[i] / (double)n[i];
+  const double got = div_by_count(a[i], n[i], 1.0 / (double)n[i]);
+  if (__double_as_longlong(want) != __double_as_longlong(got)) atomicAdd(mismatches, 1);
+}
+
+bool online_ws_supported(int kind, const OnlineParams& p) {
+  if (p.d > 10) return false;
+  if (!p.cum_means) return false;               // cum_means is the kernel's primary output (and what the regret pass reads)
+  if (kind == K_LINUCB && p.lin_d != 2) return false;
+  return true;
+}
+
+template <int DMAX, int KIND>
+static cudaError_t launch_ws(const OnlineParams& p, double* tab, cudaStream_t st) {
+  const bool io = p.in.reward_z || p.in.ctrl_z || p.in.first_arm || p.out.reward_z || p.out.ctrl_z || p.out.first_arm;
+  auto kern = io ? online_loop_ws_kernel<DMAX, KIND, true> : online_loop_ws_kernel<DMAX, KIND, false>;
+  using Cons = typename WsKernel<DMAX, KIND, false>::Cons;
+  const size_t smem = sizeof(Cons) * WS_NCONS + (KIND == K_LINUCB2 ? sizeof(double) * 2 * p.d : 0);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  if (KIND == K_EMP || KIND == K_UCB || KIND == K_THOMPSON)
+    online_ws_table_kernel<<<(p.H + 1 + 255) / 256, 256, 0, st>>>(KIND, p.p0, p.p2, p.H, tab);
+  const int warps_total = (p.N + 31) / 32;
+  kern<<<(warps_total + WS_NCONS - 1) / WS_NCONS, WS_NCONS * 32, smem, st>>>(p, tab);
+  return cudaGetLastError();
+}
+
+template <int DMAX>
+static cudaError_t launch_ws_kind(int kind, const OnlineParams& p, double* tab, cudaStream_t st) {
+  switch (kind) {
+    case K_OPT: return launch_ws<DMAX, K_OPT>(p, tab, st);
+    case K_EMP: return launch_ws<DMAX, K_EMP>(p, tab, st);
+    case K_UCB: return launch_ws<DMAX, K_UCB>(p, tab, st);
+    case K_THOMPSON: return launch_ws<DMAX, K_THOMPSON>(p, tab, st);
+    default: return launch_ws<DMAX, K_LINUCB2>(p, tab, st);
+  }
+}
+
+cudaError_t launch_online_ws(int kind, const OnlineParams& p, double* tab, double* regret_out, cudaStream_t st) {
+  if (!online_ws_supported(kind, p)) return cudaErrorNotSupported;
+  cudaError_t e = p.d <= 5 ? launch_ws_kind<5>(kind, p, tab, st) : launch_ws_kind<10>(kind, p, tab, st);
+  if (e == cudaSuccess && regret_out) {   // [H,4] regret sums from cum_means: p.regret = zeroed [regret_reps][H][3] scratch
+    const int ctas = ((p.N + 31) / 32 + RP_WARPS - 1) / RP_WARPS;   // one atomic set per warp (32 envs) and 16-step tile
+    regret_pass_kernel<<<ctas, RP_WARPS * 32, 0, st>>>(p.cum_means, p.means, p.N, p.H, p.d, p.regret, p.regret_reps);
+    regret_finish_kernel<<<1, 1024, 0, st>>>(p.regret, p.regret_reps, p.H, regret_out);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+}  // namespace dpt
+
+using namespace dpt;
+
+extern "C" int dpt_selftest_div(const double* a, const int* n, int count, int* mismatches, void* stream) {
+  DPT_CHECK_ARG(a && n && mismatches && count >= 0, "dpt_selftest_div: bad arguments");
+  if (count == 0) return DPT_OK;
+  selftest_div_kernel<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a, n, count, mismatches);
+  DPT_LAUNCH_CHECK();
+  return DPT_OK;
+}

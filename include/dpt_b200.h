@@ -189,6 +189,10 @@ int dpt_gpu_bandit_step(const float* means, const float* actions, float var, int
  * steps, first h used), ctx_rewards fp32 [N,Hs,1] -> sums f64 [N,d], counts int32 [N,d]. */
 int dpt_arm_stats(const float* ctx_actions, const float* ctx_rewards, int N, int h, int H_stride, int d,
                   double* sums, int32_t* counts, void* stream);
+/* Selftest of the online loop's count division (no reference counterpart): counts how many of the `count` pairs
+ * (a[i], n[i] >= 1) give a / n != the table-reciprocal + two-FMA-correction quotient the fused loop uses in place of
+ * the reference's `b / np.maximum(1, counts)` (ctrls/ctrl_bandit.py:105).  Must be 0. */
+int dpt_selftest_div(const double* a, const int32_t* n, int count, int32_t* mismatches, void* stream);
 
 /* ---------------------------------------------------------------- L1: deploy_online_vec ----
  * evals/eval_bandit.py:56-103 fused with BanditEnvVec.deploy/step (envs/bandit_env.py:98-149) and

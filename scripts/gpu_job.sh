@@ -1,14 +1,18 @@
 #!/bin/bash
-# GPU job 1 (round 2): tests, bench N=1, ncu of the decode kernels at config 4
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.max.sm --format=csv > gpurun_out/gpu.txt
-nproc > gpurun_out/nproc.txt
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -3 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"
-tail -c 3000 gpurun_out/bench_n1.json
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
-for t in gpt2_c4 gpt2_bf16_c4; do
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:gpt2_online --launch-skip 1 --launch-count 1 -f -o gpurun_out/r02_${t} python scripts/profile_target.py $t 2 > gpurun_out/ncu_${t}.log 2>&1; echo "ncu $t rc=$?"
+timeout 900 python -m pytest tests/test_online_gpu.py -m gpu -x -q > gpurun_out/pytest_online.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_online.log
+tail -8 gpurun_out/pytest_online.log
+V=decision-pretrained-transformer_b200/variants
+for v in default wt16; do
+  if [ $v = default ]; then unset DPT_B200_LIB; else export DPT_B200_LIB=$PWD/$V/libdpt_b200_$v.so; fi
+  timeout 300 python scripts/bench_kernels.py --only online > gpurun_out/k_online_$v.jsonl 2> gpurun_out/k_online_$v.err; echo "$v rc=$?"
 done
-ls -la gpurun_out | tail -20
+unset DPT_B200_LIB
+python - <<'PY'
+import json
+for f in ("default","wt16"):
+    for l in open("gpurun_out/k_online_%s.jsonl"%f):
+        j=json.loads(l); print(f, j["kernel"], "%.3f ms"%j["ms_mean"], "frac %.3f"%j["frac_of_measured_hbm_peak"])
+PY
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_online_emp.csv python scripts/profile_target.py online_emp 3 > gpurun_out/ncu_l.log 2>&1; echo "rc=$?"
+grep -E "online_loop|regret|table|reduce|fill" gpurun_out/launches_online_emp.csv | awk -F'","' '{print $5, $NF}' | tail -4

@@ -373,3 +373,52 @@ def test_deploy_online_single_env(dpt):
     cm = eval_bandit.deploy_online(env, EmpMeanPolicy(env, online=True), 12)
     assert cm.shape == (12,) and sorted(cm[:4]) == [0.1, 0.3, 0.5, 0.8] and np.allclose(cm[4:], 0.8)   # each arm once, then the best
     assert eval_linear_bandit.deploy_online is eval_bandit.deploy_online
+
+
+@pytest.mark.gpu
+def test_count_division_is_exact(dpt):
+    """The warp-specialised loop replaces the reference's float64 ``b / max(1, counts)`` (ctrls/ctrl_bandit.py:105) by
+    a table reciprocal + two FMA corrections: bit-identical quotients for every count up to 4096 and random sums."""
+    from dpt_b200._lib import check, lib, ptr, stream_ptr
+    rs = np.random.RandomState(0)
+    n = np.tile(np.arange(1, 4097, dtype=np.int32), 64)
+    a = np.concatenate([rs.normal(0, 1, n.size // 2) * n[:n.size // 2], rs.uniform(-1, 1, n.size - n.size // 2) * 10.0 ** rs.randint(-8, 8, n.size - n.size // 2)])
+    a[:64] = [0.0, 1.0, -1.0, 3.0, 1e-300, 1e300, 0.1, 7.0] * 8
+    ta, tn = torch.tensor(a, device="cuda"), torch.tensor(n, device="cuda")
+    bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+    check(lib().dpt_selftest_div(ptr(ta), ptr(tn), n.size, ptr(bad), stream_ptr()), "dpt_selftest_div")
+    assert int(bad.item()) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,par", [("opt", {}), ("emp", dict(p0=1.0)), ("emp", dict(p0=0.0)), ("ucb", dict(p0=1.0)),
+                                      ("thompson", dict(p0=0.3, p1=0.5, p2=1 / 12.0))])
+@pytest.mark.parametrize("d,H,N", [(5, 500, 997), (5, 37, 65), (3, 50, 33), (10, 200, 300), (7, 19, 100), (1, 9, 40)])
+def test_ws_kernel_matches_oracle_ragged(dpt, kind, par, d, H, N):
+    """The warp-specialised kernel and the general one-warp kernel are two implementations of one contract: on the same
+    injected noise they must agree on every arm bit for bit, on rewards / cum_means exactly and on the regret sums."""
+    import subprocess, sys, json, tempfile
+    rs = np.random.RandomState(d * 1000 + H)
+    means = torch.tensor(rs.uniform(0, 1, (N, d)).astype(np.float32), device="cuda")
+    inj = {"reward_z": rs.normal(0, 1, (H, N)).astype(np.float32)}
+    if kind == "thompson":
+        inj["ctrl_z"] = rs.normal(0, 1, (H, N, d)).astype(np.float32)
+    out = dpt.kernels.online_loop(kind, means, H, 0.3, 3, 0, inject=inj, **par)
+    # the oracle's recount-from-context controllers on the same noise
+    mk = {"opt": lambda: O.OptCtrl(_np(means).astype(np.float64)), "emp": lambda: O.EmpMeanCtrl(d, online=par.get("p0", 0.0) != 0.0),
+          "ucb": lambda: O.UCBCtrl(d, const=1.0), "thompson": lambda: O.ThompsonCtrl(d, std=0.3, sample=True, prior_mean=.5, prior_var=1 / 12.0)}[kind]
+    arrays = {"reward_z": inj["reward_z"].astype(np.float64)}
+    if kind == "thompson":
+        arrays["thompson_z"] = inj["ctrl_z"].astype(np.float64)
+    cum, meta = O.deploy_online_vec(_np(means).astype(np.float64), 0.3, H, mk(), O.ReplayNoise(arrays))
+    assert np.array_equal(_np(out["context_actions"]).astype(np.float64), meta["context_actions"])
+    ref_r = meta["context_rewards"][:, :, 0]
+    got_r = _np(out["context_rewards"])[:, :, 0].astype(np.float64)
+    assert np.all(np.abs(got_r - ref_r) <= 1e-5 * np.maximum(1.0, np.abs(ref_r)))
+    assert np.array_equal(_np(out["cum_means"]).astype(np.float64), cum)
+    assert bool((out["context_states"] == 1).all()) and bool((out["context_next_states"] == 1).all())
+    opt = _np(means).astype(np.float64).max(1)
+    reg = opt[None, :] - cum
+    creg = np.cumsum(reg, 0)
+    want = np.stack([reg.sum(1), (reg ** 2).sum(1), creg.sum(1), (creg ** 2).sum(1)], 1)
+    assert np.allclose(_np(out["regret_sums"]), want, rtol=1e-6, atol=1e-9)
