@@ -139,7 +139,7 @@ def cpu_online_leg(pool, n_per_core=None):
     """The reference's deploy_online_vec + BanditTransformerController (full recompute, no K/V cache) at reduced N."""
     if pool.kind != "reference":
         return None
-    n = n_per_core or int(os.environ.get("DPT_CPU_OE_ENVS_PER_CORE", 1))
+    n = max(2, n_per_core or int(os.environ.get("DPT_CPU_OE_ENVS_PER_CORE", 2)))   # the reference controller needs batch_size >= 2
     r = pool.run("gpt2_online", n, H, seed0=300, dim=DIM, var=VAR)
     return {"value": _rate(r, "trajs"), "unit": "trajs/s", "env_steps_per_s": _rate(r), "cores": r["cores"], "kind": "reference",
             "sample": "%d cores x %d envs x H=%d, evals/eval_bandit.deploy_online_vec + ctrls.BanditTransformerController(sample=True) of "
