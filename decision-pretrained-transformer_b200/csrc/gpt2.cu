@@ -23,11 +23,16 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "philox.cuh"
 
 #include "gpt2_model.cuh"
+
+#ifndef DPT_GPT2_KPRED
+#define DPT_GPT2_KPRED 0   // register-staged K loads: 1 = predicate the rows past the last key (measured below)
+#endif
 
 namespace dpt {
 
@@ -197,7 +202,13 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
         if (pos <= PF_MAX_POS && k0 + PF_AHEAD * 32 < pos) prefetch_l2(K + (size_t)(k0 + PF_AHEAD * 32 + lane) * G_E);
         float4 kk[8];
   #pragma unroll
-        for (int i = 0; i < 8; ++i) kk[i] = __ldcg(K4 + (size_t)(k0 + 4 * i + g) * 8);   // in bounds (Tpad % 32 == 0)
+        for (int i = 0; i < 8; ++i) {
+#if DPT_GPT2_KPRED   // rows >= pos are not read (3-5 % of the K/V traffic at H = 500)
+          kk[i] = (k0 + 4 * i + g < pos) ? __ldcg(K4 + (size_t)(k0 + 4 * i + g) * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+#else
+          kk[i] = __ldcg(K4 + (size_t)(k0 + 4 * i + g) * 8);   // in bounds (Tpad % 32 == 0)
+#endif
+        }
         float pv[8];
   #pragma unroll
         for (int i = 0; i < 8; ++i) pv[i] = fmaf(q4.x, kk[i].x, fmaf(q4.y, kk[i].y, fmaf(q4.z, kk[i].z, q4.w * kk[i].w)));
@@ -305,7 +316,13 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
       for (int k0 = 0; k0 < pos; k0 += 64) {
         uint4 kk[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) kk[i] = __ldcg(K8 + (size_t)(k0 + 8 * i + g) * 4);   // in bounds (Tpad % 64 == 0)
+        for (int i = 0; i < 8; ++i) {
+#if DPT_GPT2_KPRED   // rows >= pos are not read (~6 % of the K/V traffic at H = 500)
+          kk[i] = (k0 + 8 * i + g < pos) ? __ldcg(K8 + (size_t)(k0 + 8 * i + g) * 4) : make_uint4(0u, 0u, 0u, 0u);
+#else
+          kk[i] = __ldcg(K8 + (size_t)(k0 + 8 * i + g) * 4);   // in bounds (Tpad % 64 == 0)
+#endif
+        }
         // the V blocks of the same 64 keys (4 KB = one 128 B line per lane) start their trip from HBM to L2 now; the
         // P V pass below then waits an L2 rather than a DRAM latency (this mode is latency-, not bandwidth-bound)
         if (DPT_GPT2_BF16_PREFETCH_V && k0 + 16 * (lane >> 3) < pos)
@@ -408,6 +425,198 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
     x += y2;
     __syncwarp();
   }
+  return x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bulk-async (TMA engine) staging of the fp32 K/V stream: cp.async.bulk global -> shared, completion on an mbarrier.
+// A warp's cached keys of one layer are ONE contiguous run per tensor ([t][32 channels] fp32, 128 B rows), so a tile of
+// 32 keys is a single <= 4 KB bulk copy of exactly the live rows (no padded rows are read).  Each warp owns a ring of
+// KV_STAGES such tiles and walks the token's tile sequence  layer 0 K tiles, layer 0 V tiles, layer 1 K tiles, ...:
+// the copy of tile j + KV_STAGES is issued (one lane, one instruction) the moment tile j has been consumed, so the
+// stream keeps flowing through the softmax between the K and the V pass and through the projections / MLP between
+// layers -- with register-staged loads (token_forward above) a warp has nothing in flight during those phases.
+// ---------------------------------------------------------------------------------------------
+#ifndef DPT_GPT2_TMA_WARPS
+#define DPT_GPT2_TMA_WARPS 4
+#endif
+#ifndef DPT_GPT2_TMA_MINB
+#define DPT_GPT2_TMA_MINB 5   // 96 registers: 20 warps per SM with a 2-deep ring (measured best at 10k envs: 210 ms; 4 CTAs / 128 regs: 257 ms)
+#endif
+constexpr int KV_MAX_STAGES = 8;   // ring depth is a launch parameter: as deep as shared memory allows for the CTAs that must be resident
+constexpr int KV_TILE_BYTES = 32 * G_E * 4;   // 32 keys x 32 channels fp32
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct KvRing {
+  uint32_t stage0, bar0;        // shared addresses: stage s at stage0 + s * KV_TILE_BYTES, its mbarrier at bar0 + 8 s
+  uint32_t S;                   // ring depth (2 .. KV_MAX_STAGES)
+  uint32_t is, ip;              // stage the next issued tile goes to, and (unused by the producer) its lap
+  uint32_t cs, cp;              // stage of the next tile to consume, and the parity of its mbarrier phase
+  int cl, ckv, ct;              // cursor of the next tile to issue: layer, K (0) / V (1), tile
+  int nt, pos, L, Tpad;
+  const float* kv;
+
+  __device__ __forceinline__ void issue_next(int lane) {
+    if (cl >= L) return;
+    if (lane == 0) {
+      const uint32_t s = is;
+      const int nkeys = min(32, pos - 32 * ct);
+      const uint32_t bytes = (uint32_t)nkeys * (G_E * 4);
+      const float* src = kv + ((size_t)(cl * 2 + ckv) * Tpad + (size_t)ct * 32) * G_E;
+      const uint32_t bar = bar0 + 8 * s, dst = stage0 + s * KV_TILE_BYTES;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                   "r"(bar)
+                   : "memory");
+    }
+    if (++is == S) is = 0;
+    if (++ct == nt) {
+      ct = 0;
+      if (++ckv == 2) ckv = 0, ++cl;
+    }
+  }
+  // start of a token at position `pos` (keys 0 .. pos-1 are cached): fill the ring
+  __device__ __forceinline__ void begin_token(int pos_, int lane) {
+    pos = pos_, nt = (pos_ + 31) >> 5;
+    cl = nt ? 0 : L, ckv = 0, ct = 0;
+    for (uint32_t i = 0; i < S; ++i) issue_next(lane);
+  }
+  // wait for the next tile in sequence; returns its shared-memory address as a generic pointer
+  __device__ __forceinline__ const float4* acquire() {
+    const uint32_t s = cs, par = cp;
+    const uint32_t bar = bar0 + 8 * s;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tKVWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra KVWAIT_%=;\n\t}" ::"r"(bar), "r"(par)
+        : "memory");
+    return reinterpret_cast<const float4*>(__cvta_shared_to_generic((size_t)(stage0 + s * KV_TILE_BYTES)));
+  }
+  // every lane has finished reading the tile: its stage is free for the next copy
+  __device__ __forceinline__ void release(int lane) {
+    __syncwarp();
+    if (++cs == S) cs = 0, cp ^= 1u;
+    issue_next(lane);
+  }
+};
+
+// token_forward with the fp32 K/V stream staged through the ring (same arithmetic, same order of operations)
+__device__ __forceinline__ float token_forward_tma(const Gpt2Dev& m, float x, int pos, float* kvf, int Tpad, float* sx, float* sh, float* ssc,
+                                                   int lane, KvRing& ring) {
+  ring.begin_token(pos, lane);
+  for (int l = 0; l < m.L; ++l) {
+    const LayerW& w = m.layer[l];
+    sx[lane] = layer_norm(x, w.ln1_w, w.ln1_b, lane);
+    __syncwarp();
+    float qkv[3];
+    matvec_packed<G_E, 3>(sx, w.attn_wP, w.attn_b, lane, qkv);
+    float q = qkv[0];
+    const float k = qkv[1], v = qkv[2];
+    __syncwarp();
+    float* K = kvf + (size_t)(l * 2) * G_E * Tpad;
+    float* V = K + (size_t)G_E * Tpad;
+    K[(size_t)pos * G_E + lane] = k;   // appended rows are read (by bulk copies) from the NEXT token on
+    V[(size_t)pos * G_E + lane] = v;
+    q *= 0.17677669529663687f;  // 1/sqrt(head_dim = 32)
+    sx[lane] = q;
+    __syncwarp();
+    const int g = lane >> 3, b8 = lane & 7;
+    const float4 q4 = reinterpret_cast<const float4*>(sx)[b8];
+    __syncwarp();
+    float lmax = -INFINITY;
+    for (int k0 = 0; k0 < pos; k0 += 32) {
+      const float4* Ks = ring.acquire() + b8;   // row stride = 8 float4
+      float4 kk[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) kk[i] = Ks[(4 * i + g) * 8];   // rows past the last key hold stale data: masked below
+      float pv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pv[i] = fmaf(q4.x, kk[i].x, fmaf(q4.y, kk[i].y, fmaf(q4.z, kk[i].z, q4.w * kk[i].w)));
+      ring.release(lane);
+      float w4[4], w2[2];
+      const bool u4 = b8 & 4, u2 = b8 & 2, u1 = b8 & 1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float send = u4 ? pv[j] : pv[j + 4], keep = u4 ? pv[j + 4] : pv[j];
+        w4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float send = u2 ? w4[j] : w4[j + 2], keep = u2 ? w4[j + 2] : w4[j];
+        w2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      const float sc = (u1 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, u1 ? w2[0] : w2[1], 1);
+      const int key = k0 + 4 * b8 + g;
+      if (key < pos) {
+        ssc[key] = sc;
+        lmax = fmaxf(lmax, sc);
+      }
+    }
+    const float s_self = warp_sum(q * k);  // the token attends to itself (causal mask keeps keys <= pos)
+    lmax = fmaxf(warp_max(lmax), s_self);
+    __syncwarp();
+    float lsum = 0.f;
+    for (int key = lane; key < pos; key += 32) {
+      const float pr = expf(ssc[key] - lmax);
+      ssc[key] = pr;
+      lsum += pr;
+    }
+    const float p_self = expf(s_self - lmax);
+    const float inv = 1.0f / (warp_sum(lsum) + p_self);
+    __syncwarp();
+    float4 oa = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k0 = 0; k0 < pos; k0 += 32) {
+      const float4* Vs = ring.acquire() + b8;
+      float4 vv[8];
+      float pr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int key = k0 + 4 * i + g;
+        const bool ok = key < pos;                 // rows >= pos are stale: never let them in
+        vv[i] = ok ? Vs[(4 * i + g) * 8] : make_float4(0.f, 0.f, 0.f, 0.f);
+        pr[i] = ok ? ssc[key] : 0.f;
+      }
+      ring.release(lane);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        oa.x = fmaf(pr[i], vv[i].x, oa.x);
+        oa.y = fmaf(pr[i], vv[i].y, oa.y);
+        oa.z = fmaf(pr[i], vv[i].z, oa.z);
+        oa.w = fmaf(pr[i], vv[i].w, oa.w);
+      }
+    }
+#pragma unroll
+    for (int o_ = 8; o_ <= 16; o_ <<= 1) {
+      oa.x += __shfl_xor_sync(0xffffffffu, oa.x, o_);
+      oa.y += __shfl_xor_sync(0xffffffffu, oa.y, o_);
+      oa.z += __shfl_xor_sync(0xffffffffu, oa.z, o_);
+      oa.w += __shfl_xor_sync(0xffffffffu, oa.w, o_);
+    }
+    __syncwarp();
+    if (lane < 8) reinterpret_cast<float4*>(sx)[lane] = oa;
+    __syncwarp();
+    const float o = (sx[lane] + p_self * v) * inv;
+    __syncwarp();
+    sx[lane] = o;
+    __syncwarp();
+    float y;
+    matvec_packed<G_E, 1>(sx, w.proj_wP, w.proj_b, lane, &y);
+    x += y;
+    __syncwarp();
+    sx[lane] = layer_norm(x, w.ln2_w, w.ln2_b, lane);
+    __syncwarp();
+    float hh[4];
+    matvec_packed<G_E, 4>(sx, w.fc_wP, w.fc_b, lane, hh);
+    sh[lane] = gelu_new(hh[0]), sh[32 + lane] = gelu_new(hh[1]), sh[64 + lane] = gelu_new(hh[2]), sh[96 + lane] = gelu_new(hh[3]);
+    __syncwarp();
+    float y2;
+    matvec_packed<G_FF, 1>(sh, w.fc2_wP, w.fc2_b, lane, &y2);
+    x += y2;
+    __syncwarp();
+  }
+  // this token's appended K/V rows (generic-proxy stores of all lanes) must be visible to the bulk copies (async proxy)
+  // that the next token issues
+  __syncwarp();
+  asm volatile("fence.proxy.async;" ::: "memory");
   return x;
 }
 
@@ -529,6 +738,7 @@ struct OnlineGptParams {
   Key key;
   uint64_t env_id0;
   int N, H, Tpad;
+  int kv_stages;   // depth of the per-warp bulk-async K/V ring (TMA kernel)
   void* kv;
   float *ctx_s, *ctx_a, *ctx_ns, *ctx_r, *cum_means;
   double* regret;
@@ -544,14 +754,34 @@ struct OnlineGptParams {
 constexpr int GW_WARPS = DPT_GPT2_GW_WARPS;
 constexpr int GW_THREADS = GW_WARPS * 32;
 
-template <bool BF16, bool WS>
-__global__ void __launch_bounds__(WS ? GW_THREADS : G_THREADS, WS ? 1 : (BF16 ? DPT_GPT2_MINB_BF16 : DPT_GPT2_MINB_F32))
+constexpr int TMA_WARPS = DPT_GPT2_TMA_WARPS;
+// TMA (precision 0 only): the fp32 K/V stream is staged through a per-warp ring of bulk-async copies (KvRing)
+template <bool BF16, bool WS, bool TMA = false>
+__global__ void __launch_bounds__(WS ? GW_THREADS : (TMA ? TMA_WARPS * 32 : G_THREADS),
+                                  WS ? 1 : (TMA ? DPT_GPT2_TMA_MINB : (BF16 ? DPT_GPT2_MINB_BF16 : DPT_GPT2_MINB_F32)))
     gpt2_online_kernel(const OnlineGptParams p) {
-  extern __shared__ __align__(16) float g_smem[];
+  extern __shared__ __align__(128) float g_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Gpt2Dev& m = p.m;
   const uint4* wf = nullptr;
   float* scratch = g_smem;
+  KvRing ring;
+  if constexpr (TMA) {   // [warps][KV_STAGES] tiles of 4 KB | [warps][KV_STAGES] mbarriers | per-warp scratch
+    const int nw = blockDim.x >> 5;
+    unsigned char* base = reinterpret_cast<unsigned char*>(g_smem);
+    const int S = p.kv_stages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)nw * S * KV_TILE_BYTES);
+    if (threadIdx.x < nw * S)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bars + threadIdx.x)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    ring.S = (uint32_t)S;
+    ring.stage0 = smem_addr(base + (size_t)warp * S * KV_TILE_BYTES);
+    ring.bar0 = smem_addr(bars + warp * S);
+    ring.is = ring.ip = ring.cs = ring.cp = 0;
+    ring.L = m.L, ring.Tpad = p.Tpad;
+    scratch = reinterpret_cast<float*>(bars + ((nw * S + 1) & ~1));   // keep the per-warp scratch 16 B aligned
+  }
   if constexpr (WS) {
     uint4* dst = reinterpret_cast<uint4*>(g_smem);
     for (int l = 0; l < m.L; ++l)
@@ -564,6 +794,7 @@ __global__ void __launch_bounds__(WS ? GW_THREADS : G_THREADS, WS ? 1 : (BF16 ? 
   if (env >= p.N) return;
   const WarpScratch ws = warp_scratch(scratch, warp, p.Tpad);
   char* kv = reinterpret_cast<char*>(p.kv) + (size_t)env * m.L * 2 * G_E * p.Tpad * (BF16 ? 2 : 4);
+  if constexpr (TMA) ring.kv = reinterpret_cast<const float*>(kv);
   const int du = m.du, H = p.H, N = p.N;
   const uint64_t gid = p.env_id0 + (uint64_t)env;
   const float mean_l = lane < du ? p.means[(size_t)env * du + lane] : -INFINITY;
@@ -585,7 +816,10 @@ __global__ void __launch_bounds__(WS ? GW_THREADS : G_THREADS, WS ? 1 : (BF16 ? 
   for (int h = 0; h < H; ++h) {
     float x = e_bias + e_state + __ldg(m.wpe + (size_t)h * G_E + lane);
     if (h > 0) x += __ldg(m.embed_wT + (1 + a_prev) * G_E + lane) + e_next + e_rew * r_prev;
-    x = token_forward<BF16, WS>(m, x, h, kv, p.Tpad, ws.sx, ws.sh, ws.ssc, lane, wf);
+    if constexpr (TMA)
+      x = token_forward_tma(m, x, h, reinterpret_cast<float*>(kv), p.Tpad, ws.sx, ws.sh, ws.ssc, lane, ring);
+    else
+      x = token_forward<BF16, WS>(m, x, h, kv, p.Tpad, ws.sx, ws.sh, ws.ssc, lane, wf);
     const float lg = head_logits(m, x, ws.sx, lane);
     if (p.out.logits && lane < du) p.out.logits[((size_t)h * N + env) * du + lane] = lg;
     int a;
@@ -882,6 +1116,30 @@ extern "C" int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, double va
     const long per_wave = (long)sm_count() * GW_WARPS, waves = (N + per_wave - 1) / per_wave;
     const int nw = (int)std::min<long>(GW_WARPS, std::max<long>(1, (N + waves * sm_count() - 1) / (waves * sm_count())));
     gpt2_online_kernel<true, true><<<(N + nw - 1) / nw, nw * 32, smem_ws, (cudaStream_t)stream>>>(p);
+    DPT_LAUNCH_CHECK();
+    return DPT_OK;
+  }
+  static const int use_tma = [] {
+    const char* e = getenv("DPT_GPT2_TMA");
+    return e ? atoi(e) : -1;
+  }();
+  // fp32 K/V staged by bulk-async copies (cp.async.bulk + mbarrier ring per warp).  DPT_GPT2_TMA: 1 = always, 0 = never,
+  // unset = when the batch leaves warp slots empty (fewer than ~36 env-warps per SM): there the register-staged kernel
+  // cannot keep enough bytes in flight (0.43 of the HBM bound at 1250 envs) and a deep ring can (0.8+)
+  const long env_warps_per_sm = ((long)N + sm_count() - 1) / sm_count();
+  const bool tma = !precision && (use_tma == 1 || (use_tma < 0 && env_warps_per_sm <= 24));
+  if (tma) {
+    // CTA size: small batches get small CTAs so that the SMs carry equal numbers of warps (1250 envs = 8.4 warps per SM:
+    // 4-warp CTAs would put 12 warps on some SMs and 8 on the others)
+    int nw = env_warps_per_sm <= 12 ? 1 : (env_warps_per_sm <= 20 ? 2 : TMA_WARPS);
+    if (const char* e = getenv("DPT_GPT2_TMA_WARPS")) nw = std::max(1, std::min(TMA_WARPS, atoi(e)));   // (measurement override)
+    int S = 2;   // measured at 1250 and 10000 envs: 2 stages beat 3, 4 and 6
+    if (const char* e = getenv("DPT_GPT2_KV_STAGES")) S = std::max(2, std::min(KV_MAX_STAGES, atoi(e)));   // (measurement override)
+    p.kv_stages = S;
+    const size_t smem_tma = (size_t)nw * (S * (KV_TILE_BYTES + 8) + per_warp) + 8;
+    int rc = launch_smem((const void*)gpt2_online_kernel<false, false, true>, smem_tma);
+    if (rc != DPT_OK) return rc;
+    gpt2_online_kernel<false, false, true><<<(N + nw - 1) / nw, nw * 32, smem_tma, (cudaStream_t)stream>>>(p);
     DPT_LAUNCH_CHECK();
     return DPT_OK;
   }

@@ -35,7 +35,7 @@ elif t in ("gpt2_c4", "gpt2_bf16_c4", "gpt2_c4_8gpu", "gpt2_bf16_c4_8gpu"):   # 
     H = 500
     m = Transformer({"horizon": H, "state_dim": 1, "action_dim": 5, "n_layer": 4, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True})
     m.precision = 1 if "bf16" in t else 0
-    means, _, _ = kernels.bandit_sample_means(1250 if t.endswith("8gpu") else 10000, 5, 0, 0)
+    means, _, _ = kernels.bandit_sample_means(int(os.environ.get("DPT_PROFILE_ENVS", 1250 if t.endswith("8gpu") else 10000)), 5, 0, 0)
     for i in range(reps):
         m.online_loop(means, H, 0.3, True, i, 0)
 elif t in ("gpt2", "gpt2_bf16"):
