@@ -505,8 +505,16 @@ def main():
            "host_bytes_written_per_step": N * H * BYTES_PER_STEP,
            "api": "dpt_bandit_rollin_host (pinned host buffers, chunked H2D/kernel/D2H pipeline, hybrid DMA / host expansion)"}
     try:    # the host side of the e2e path is a pure memory-write stream: report it against the box's measured store peak
-        hp = kernels.host_write_peak()
+        # (non-temporal stores of this rank's share of the host cores into the SAME pinned output array, all ranks at once)
+        n_thr = max(1, len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+        barrier()
+        hp = kernels.host_write_peak(buf=host_out["context_actions"], n_threads=n_thr)
+        t = torch.tensor([hp], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t)
+        hp = float(t[0])
         e2e["host_write_peak_gbs"] = hp
+        e2e["host_write_peak_note"] = "sum over ranks of dpt_host_write_peak into the pinned actions array, %d threads per rank, all ranks concurrently" % n_thr
         e2e["frac_of_host_peak"] = world * N * H * BYTES_PER_STEP * e2e_steps / (e2e_ms * 1e-3) / 1e9 / hp
     except Exception as e:   # noqa: BLE001
         e2e["host_write_peak_gbs"] = None

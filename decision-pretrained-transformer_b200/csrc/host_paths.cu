@@ -8,7 +8,9 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -60,7 +62,7 @@ extern "C" uint64_t dpt_bandit_rollin_host_scratch_bytes(int N, int H, int d) {
 // next_states region of the caller's buffer, so no extra pinned memory is needed.  Both kinds of chunks give
 // bit-identical results (the same Philox counters; tests/test_rollout_gpu.py::test_bandit_rollin_host_path).
 namespace {
-constexpr int HOST_PARTS = 8;   // host jobs per chunk and phase
+constexpr int HOST_PARTS = 16;  // host jobs per chunk and phase
 
 // DPT_HOST_COMPACT: "auto" (default: a chunk goes compact whenever the host workers are about to run dry, otherwise by
 // DMA -- self-balancing between PCIe and the host cores), "0" (all chunks by DMA) or "1" (all compact).
@@ -80,7 +82,36 @@ void fill_ones_nt(float* lo, float* hi) {
   while (lo < hi) *lo++ = 1.0f;
 }
 
-// one-hot rows [lo, hi) of width d from arm indices; 4 rows = d aligned 16 B vectors when lo % 4 == 0
+// one-hot rows [lo, hi) of width d from arm indices; 4 rows = d aligned 16 B vectors when lo % 4 == 0.
+// d <= 5: the 4 d floats of a row quad come from a table indexed by the four arm indices (d^4 <= 625 entries x 16 d
+// bytes <= 50 KB, L2-resident): ~5 instructions per row instead of ~30, so the expansion is bound by the memory system,
+// not by the cores (measured: 66 -> see DESIGN.md GB/s of host stores on 16 cores).
+struct OnehotLut {
+  int d = 0;
+  float* tab = nullptr;      // [d^4][4 d] floats, 16 B aligned
+  int mul[4] = {0, 0, 0, 0};
+};
+static const OnehotLut* onehot_lut(int d) {
+  static OnehotLut luts[6];
+  static std::once_flag once[6];
+  if (d < 1 || d > 5) return nullptr;
+  std::call_once(once[d], [d] {
+    OnehotLut& L = luts[d];
+    int n = d * d * d * d;
+    void* mem = nullptr;
+    if (posix_memalign(&mem, 64, (size_t)n * 4 * d * sizeof(float)) != 0) return;
+    float* t = reinterpret_cast<float*>(mem);
+    for (int i = 0; i < n; ++i) {
+      int a[4] = {i % d, (i / d) % d, (i / (d * d)) % d, i / (d * d * d)};
+      for (int r = 0; r < 4; ++r)
+        for (int j = 0; j < d; ++j) t[(size_t)i * 4 * d + r * d + j] = (j == a[r]) ? 1.0f : 0.0f;
+    }
+    L.mul[0] = 1, L.mul[1] = d, L.mul[2] = d * d, L.mul[3] = d * d * d;
+    L.tab = t, L.d = d;
+  });
+  return luts[d].tab ? &luts[d] : nullptr;
+}
+
 void expand_onehot_nt(float* a, const uint8_t* acts, size_t lo, size_t hi, int d) {
   auto scalar = [&](size_t row) {
     float* o = a + row * d;
@@ -92,12 +123,21 @@ void expand_onehot_nt(float* a, const uint8_t* acts, size_t lo, size_t hi, int d
     return;
   }
   while (lo < hi && (lo & 3)) scalar(lo++);
-  alignas(16) float tmp[4 * 64];
-  for (; lo + 4 <= hi; lo += 4) {
-    for (int j = 0; j < 4 * d; ++j) tmp[j] = 0.0f;
-    tmp[acts[lo]] = 1.0f, tmp[d + acts[lo + 1]] = 1.0f, tmp[2 * d + acts[lo + 2]] = 1.0f, tmp[3 * d + acts[lo + 3]] = 1.0f;
-    float* o = a + lo * d;
-    for (int v = 0; v < d; ++v) _mm_stream_ps(o + 4 * v, _mm_load_ps(tmp + 4 * v));
+  if (const OnehotLut* L = onehot_lut(d)) {
+    const int m1 = L->mul[1], m2 = L->mul[2], m3 = L->mul[3];
+    for (; lo + 4 <= hi; lo += 4) {
+      const float* src = L->tab + (size_t)(acts[lo] + m1 * acts[lo + 1] + m2 * acts[lo + 2] + m3 * acts[lo + 3]) * 4 * d;
+      float* o = a + lo * d;
+      for (int v = 0; v < d; ++v) _mm_stream_ps(o + 4 * v, _mm_load_ps(src + 4 * v));
+    }
+  } else {
+    alignas(16) float tmp[4 * 64];
+    for (; lo + 4 <= hi; lo += 4) {
+      for (int j = 0; j < 4 * d; ++j) tmp[j] = 0.0f;
+      tmp[acts[lo]] = 1.0f, tmp[d + acts[lo + 1]] = 1.0f, tmp[2 * d + acts[lo + 2]] = 1.0f, tmp[3 * d + acts[lo + 3]] = 1.0f;
+      float* o = a + lo * d;
+      for (int v = 0; v < d; ++v) _mm_stream_ps(o + 4 * v, _mm_load_ps(tmp + 4 * v));
+    }
   }
   while (lo < hi) scalar(lo++);
 }
@@ -212,6 +252,91 @@ extern "C" double dpt_host_write_peak(void* dst, uint64_t bytes, int n_threads) 
   return best;
 }
 
+// ---- persistent host worker pool ---------------------------------------------------------------------------
+// The host half of the pipeline (constant columns, expansion of compact chunks) runs on worker threads that live for
+// the process: created on first use, one per core of THIS rank's share of the cores the process may run on
+// (sched_getaffinity, split by LOCAL_RANK / LOCAL_WORLD_SIZE under torchrun) and pinned there, so that the ranks of a
+// node do not migrate onto each other's cores.  One core of the share is left to the calling thread.
+namespace {
+std::vector<int> rank_cpus() {
+  std::vector<int> all;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof(set), &set) == 0)
+    for (int c = 0; c < CPU_SETSIZE; ++c)
+      if (CPU_ISSET(c, &set)) all.push_back(c);
+  if (all.empty())
+    for (unsigned c = 0; c < std::max(1u, std::thread::hardware_concurrency()); ++c) all.push_back((int)c);
+  int w = 1, r = 0;
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) w = std::max(1, atoi(e));
+  if (const char* e = getenv("LOCAL_RANK")) r = std::max(0, atoi(e));
+  if (w > 1 && (int)all.size() >= w) {
+    const size_t k = all.size() / w, lo = (size_t)(r % w) * k;
+    return std::vector<int>(all.begin() + lo, all.begin() + lo + k);
+  }
+  return all;
+}
+
+struct HostPool {
+  std::mutex m;
+  std::condition_variable cv_go, cv_done;
+  HostJobs* jobs = nullptr;
+  uint64_t epoch = 0;
+  int want = 0, active = 0;
+  std::vector<std::thread> threads;
+  std::vector<int> cpus;
+
+  static HostPool& get() {
+    static HostPool* p = new HostPool();   // never destroyed: the threads sleep on cv_go until the process exits
+    return *p;
+  }
+  int capacity() {
+    std::lock_guard<std::mutex> g(m);
+    if (cpus.empty()) cpus = rank_cpus();
+    int n = (int)cpus.size() - 1;          // one core for the thread that drives the GPU pipeline
+    if (const char* e = getenv("DPT_HOST_WORKERS")) n = atoi(e);
+    return std::max(1, std::min(64, n));
+  }
+  void loop(int idx) {
+    uint64_t seen = 0;
+    for (;;) {
+      HostJobs* j;
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cv_go.wait(lk, [&] { return epoch != seen && idx < want; });
+        seen = epoch;
+        j = jobs;
+      }
+      j->run_worker();
+      {
+        std::lock_guard<std::mutex> g(m);
+        if (--active == 0) cv_done.notify_all();
+      }
+    }
+  }
+  void start(HostJobs* j, int n) {
+    std::lock_guard<std::mutex> g(m);
+    while ((int)threads.size() < n) {
+      const int idx = (int)threads.size();
+      threads.emplace_back([this, idx] { loop(idx); });
+      if (cpus.size() > 1) {   // worker idx -> core idx + 1 of the rank's share (core 0 of the share: the caller)
+        cpu_set_t one;
+        CPU_ZERO(&one);
+        CPU_SET(cpus[(size_t)(idx + 1) % cpus.size()], &one);
+        pthread_setaffinity_np(threads.back().native_handle(), sizeof(one), &one);
+      }
+      threads.back().detach();
+    }
+    jobs = j, want = n, active = n, ++epoch;
+    cv_go.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    cv_done.wait(lk, [&] { return active == 0; });
+  }
+};
+}  // namespace
+
 extern "C" int dpt_bandit_rollin_host(const float* means_host, float var, uint64_t seed, uint64_t env_id0, int N,
                                       int H, int d, float* ctx_states_host, float* ctx_actions_host,
                                       float* ctx_next_states_host, float* ctx_rewards_host, void* scratch,
@@ -226,13 +351,28 @@ extern "C" int dpt_bandit_rollin_host(const float* means_host, float var, uint64
   const int C = N < host_chunk_envs() ? N : host_chunk_envs();
   const ChunkLayout L = chunk_layout(C, H, d);
   cudaStream_t cs = (cudaStream_t)stream;
-  cudaStream_t copy;  // D2H stream, so chunk k's copies overlap chunk k+1's kernel
-  DPT_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
-  cudaEvent_t done[2], freed[2];
+  struct Res {   // the pipeline's own stream and events: released on every return path
+    cudaStream_t copy = nullptr;   // D2H stream, so chunk k's copies overlap chunk k+1's kernel
+    cudaEvent_t done[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> d2h;
+    ~Res() {
+      for (int i = 0; i < 2; ++i) {
+        if (done[i]) cudaEventDestroy(done[i]);
+        if (freed[i]) cudaEventDestroy(freed[i]);
+      }
+      for (auto& ev : d2h)
+        if (ev) cudaEventDestroy(ev);
+      if (copy) cudaStreamDestroy(copy);
+    }
+  } res;
+  DPT_CUDA(cudaStreamCreateWithFlags(&res.copy, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
-    DPT_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-    DPT_CUDA(cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming));
+    DPT_CUDA(cudaEventCreateWithFlags(&res.done[i], cudaEventDisableTiming));
+    DPT_CUDA(cudaEventCreateWithFlags(&res.freed[i], cudaEventDisableTiming));
   }
+  cudaStream_t copy = res.copy;
+  cudaEvent_t* done = res.done;
+  cudaEvent_t* freed = res.freed;
   // The bandit state is the constant [1] (envs/bandit_env.py:38): context_states / context_next_states never cross
   // PCIe, host threads write them (and expand the compact chunks) while the GPU pipeline runs.
   HostJobs jobs;
@@ -247,16 +387,17 @@ extern "C" int dpt_bandit_rollin_host(const float* means_host, float var, uint64
     jobs.enqueued[kk].store(0);
     jobs.phase1_left[kk].store(HOST_PARTS);
   }
-  jobs.d2h_done.resize(jobs.K);
-  for (int kk = 0; kk < jobs.K; ++kk) DPT_CUDA(cudaEventCreateWithFlags(&jobs.d2h_done[kk], cudaEventDisableTiming));
-  // one process per GPU shares the host cores: torchrun exports LOCAL_WORLD_SIZE
-  unsigned procs = 1;
-  if (const char* lw = getenv("LOCAL_WORLD_SIZE")) procs = (unsigned)std::max(1, atoi(lw));
-  const unsigned hw = std::max(2u, std::thread::hardware_concurrency() / procs);
+  res.d2h.assign(jobs.K, nullptr);
+  for (int kk = 0; kk < jobs.K; ++kk) DPT_CUDA(cudaEventCreateWithFlags(&res.d2h[kk], cudaEventDisableTiming));
+  jobs.d2h_done = res.d2h;
   const size_t total_rows = (size_t)N * H;
-  const int n_workers = (int)std::min<size_t>(std::min(16u, hw), std::max<size_t>(1, total_rows >> 18));
-  std::vector<std::thread> fillers;
-  for (int t = 0; t < n_workers; ++t) fillers.emplace_back([&jobs] { jobs.run_worker(); });
+  HostPool& pool = HostPool::get();
+  const int n_workers = (int)std::min<size_t>((size_t)pool.capacity(), std::max<size_t>(1, total_rows >> 18));
+  pool.start(&jobs, n_workers);
+  static const int backlog = [] {
+    const char* e = getenv("DPT_HOST_BACKLOG");
+    return std::max(1, e ? atoi(e) : 4);   // measured on a 16-core host: 1: 2.8, 2: 3.4, 3: 4.4, 4: 4.9, 6: 5.0 G env-steps/s
+  }();
   int rc = DPT_OK;
   int k = 0;
   uint64_t d2h_bytes = 0;
@@ -264,42 +405,52 @@ extern "C" int dpt_bandit_rollin_host(const float* means_host, float var, uint64
     const int n = (N - e0) < C ? (N - e0) : C;
     const int b = k & 1;
     float* buf = reinterpret_cast<float*>(scratch) + (size_t)b * L.total;
-    if (k >= 2) cudaEventSynchronize(freed[b]);        // buffer b's previous D2H has drained (host-side pacing)
+    cudaError_t ce = cudaSuccess;
+    auto ck = [&](cudaError_t e) {
+      if (ce == cudaSuccess) ce = e;
+    };
+    if (k >= 2) ck(cudaEventSynchronize(freed[b]));    // buffer b's previous D2H has drained (host-side pacing)
     // kind of this chunk: compact when the host workers would otherwise run out of expansion work
-    jobs.compact[k] = policy < 0 ? (jobs.compact_parts_pending.load() <= n_workers) : (char)policy;
+    // auto: the host cores expand compact chunks (5 B per step over PCIe) as fast as they can -- with the table-driven
+    // expansion that alone reaches the host's measured store bandwidth on a 16-core box -- and a chunk goes by DMA
+    // (24 B per step over PCIe, 8 B per step of host work) only while more than `backlog` compact chunks are queued
+    // for the host, i.e. when the cores, not PCIe, are what the pipeline waits for (few cores per rank at 8 GPUs)
+    jobs.compact[k] = policy < 0 ? (jobs.compact_parts_pending.load() < backlog * HOST_PARTS) : (char)policy;
     if (jobs.compact[k]) jobs.compact_parts_pending.fetch_add(HOST_PARTS);
-    cudaMemcpyAsync(buf + L.means, means_host + (size_t)e0 * d, sizeof(float) * n * d, cudaMemcpyHostToDevice, cs);
+    ck(cudaMemcpyAsync(buf + L.means, means_host + (size_t)e0 * d, sizeof(float) * n * d, cudaMemcpyHostToDevice, cs));
     const size_t row = (size_t)e0 * H, nrow = (size_t)n * H;
     if (jobs.compact[k]) {
       uint8_t* acts_dev = reinterpret_cast<uint8_t*>(buf + L.a);
       rc = bandit_rollin_compact(buf + L.means, var, seed, env_id0 + (uint64_t)e0, n, H, d, acts_dev, buf + L.r, cs);
       if (rc != DPT_OK) break;
-      cudaEventRecord(done[b], cs);
-      cudaStreamWaitEvent(copy, done[b], 0);
-      cudaMemcpyAsync(ctx_next_states_host + row, acts_dev, nrow, cudaMemcpyDeviceToHost, copy);   // staged arm indices
-      cudaMemcpyAsync(ctx_rewards_host + row, buf + L.r, sizeof(float) * nrow, cudaMemcpyDeviceToHost, copy);
+      ck(cudaEventRecord(done[b], cs));
+      ck(cudaStreamWaitEvent(copy, done[b], 0));
+      ck(cudaMemcpyAsync(ctx_next_states_host + row, acts_dev, nrow, cudaMemcpyDeviceToHost, copy));   // staged arm indices
+      ck(cudaMemcpyAsync(ctx_rewards_host + row, buf + L.r, sizeof(float) * nrow, cudaMemcpyDeviceToHost, copy));
     } else {
       rc = dpt_bandit_rollin(buf + L.means, var, DPT_REWARD_GAUSSIAN, seed, env_id0 + (uint64_t)e0, n, H, d, buf + L.s, buf + L.a,
                              buf + L.ns, buf + L.r, nullptr, nullptr, nullptr, cs);
       if (rc != DPT_OK) break;
-      cudaEventRecord(done[b], cs);
-      cudaStreamWaitEvent(copy, done[b], 0);
-      cudaMemcpyAsync(ctx_actions_host + row * d, buf + L.a, sizeof(float) * nrow * d, cudaMemcpyDeviceToHost, copy);
-      cudaMemcpyAsync(ctx_rewards_host + row, buf + L.r, sizeof(float) * nrow, cudaMemcpyDeviceToHost, copy);
+      ck(cudaEventRecord(done[b], cs));
+      ck(cudaStreamWaitEvent(copy, done[b], 0));
+      ck(cudaMemcpyAsync(ctx_actions_host + row * d, buf + L.a, sizeof(float) * nrow * d, cudaMemcpyDeviceToHost, copy));
+      ck(cudaMemcpyAsync(ctx_rewards_host + row, buf + L.r, sizeof(float) * nrow, cudaMemcpyDeviceToHost, copy));
     }
     d2h_bytes += jobs.compact[k] ? nrow * 5 : nrow * 4 * (uint64_t)(d + 1);
-    cudaEventRecord(freed[b], copy);
-    cudaEventRecord(jobs.d2h_done[k], copy);
+    ck(cudaEventRecord(freed[b], copy));
+    ck(cudaEventRecord(jobs.d2h_done[k], copy));
+    if (ce != cudaSuccess) {   // a failed enqueue: stop here, release the workers (they see `failed`), report below
+      set_error("dpt_bandit_rollin_host: %s while enqueueing chunk %d", cudaGetErrorString(ce), k);
+      rc = DPT_ERR_CUDA;
+      break;
+    }
     jobs.enqueued[k].store(1, std::memory_order_release);
   }
   if (rc != DPT_OK) jobs.failed.store(true);
   t_last_d2h_bytes = d2h_bytes;
-  for (auto& th : fillers) th.join();
+  pool.wait();
   cudaError_t e1 = cudaStreamSynchronize(copy);
   cudaError_t e2 = cudaStreamSynchronize(cs);
-  for (int i = 0; i < 2; ++i) cudaEventDestroy(done[i]), cudaEventDestroy(freed[i]);
-  for (auto& ev : jobs.d2h_done) cudaEventDestroy(ev);
-  cudaStreamDestroy(copy);
   if (jobs.failed.load() && rc == DPT_OK) {
     set_error("dpt_bandit_rollin_host: a host worker failed while waiting for its chunk");
     return DPT_ERR_CUDA;
