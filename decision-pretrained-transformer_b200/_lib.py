@@ -69,6 +69,8 @@ PROTOTYPES = {
     "dpt_bandit_opt_action": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dpt_bandit_rollin": (c_int, [c_void_p, c_float, c_int, c_uint64, c_uint64, c_int, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, POINTER(BanditInject), POINTER(BanditDump), c_void_p]),
+    "dpt_bandit_rollin_host_f64": (c_int, [c_void_p, c_float, c_uint64, c_uint64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_uint64, c_void_p]),
     "dpt_bandit_rollin_host_last_d2h_bytes": (c_uint64, []),
     "dpt_host_write_peak": (c_double, [c_void_p, c_uint64, c_int]),
     "dpt_bandit_rollin_p2p": (c_int, [c_void_p, c_float, c_uint64, c_uint64, c_int, c_int, c_int, c_void_p, c_void_p,

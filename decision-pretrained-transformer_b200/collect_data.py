@@ -98,18 +98,35 @@ def generate_bandit_histories_from_envs(envs, n_hists, n_samples, cov, type):
     return trajs
 
 
+def _bandit_trajs_host(host, means64, opt64, n_samples):
+    """Traj dicts over views of the host arrays (no per-env copies)."""
+    cs, ca, cns, cr = host["context_states"], host["context_actions"], host["context_next_states"], host["context_rewards"]
+    q = np.array([1])
+    trajs = []
+    for i in range(cs.shape[0]):
+        for _ in range(n_samples):
+            trajs.append({"query_state": q, "optimal_action": opt64[i], "context_states": cs[i], "context_actions": ca[i],
+                          "context_next_states": cns[i], "context_rewards": cr[i], "means": means64[i]})
+    return trajs
+
+
 def generate_bandit_histories(n_envs, dim, horizon, var, **kwargs):
-    """collect_data.py:221-225.  Task draw and rollouts happen on the device."""
+    """collect_data.py:221-225.  Task draw and rollouts happen on the device; the histories come back in the reference's
+    own dtypes (int64 states, float64 one-hot actions / rewards) through dpt_bandit_rollin_host_f64: 5 B per env-step
+    over PCIe, expanded by the host cores straight into the returned arrays; the traj dicts hold views of them."""
     n_hists, n_samples = kwargs.get("n_hists", 1), kwargs.get("n_samples", 1)
     # the reference draws its envs with bandit_env.sample(dim, horizon, var) -- always type 'uniform' -- and never
     # reads kwargs['type'] (collect_data.py:158-182, 221-225); so do we
     key = rng.next_key()
     means, opt_idx, opt_a = kernels.bandit_sample_means(n_envs, dim, key, 0)
-    per_hist = []
+    means_host = means.cpu()
+    means64, opt64 = means_host.numpy().astype(np.float64), opt_a.cpu().numpy().astype(np.float64)
+    per_hist, scratch = [], None
     for j in range(n_hists):
-        b = kernels.bandit_rollin(means, horizon, float(var), rng.key_for(key, j + 1), 0)
-        b.update(means=means, optimal_actions=opt_a)
-        per_hist.append(_bandit_trajs(b, n_samples))
+        host = kernels.bandit_rollin_host_ref(means_host, horizon, float(var), rng.key_for(key, j + 1), 0)
+        per_hist.append(_bandit_trajs_host(host, means64, opt64, n_samples))
+    if n_hists == 1:
+        return per_hist[0]
     trajs = []
     for i in range(n_envs):
         for j in range(n_hists):

@@ -142,6 +142,57 @@ void expand_onehot_nt(float* a, const uint8_t* acts, size_t lo, size_t hi, int d
   while (lo < hi) scalar(lo++);
 }
 
+// ---- the reference's own dtypes (collect_data.py:23-53 returns int64 states, float64 one-hot actions / rewards) ----
+void fill_ones_i64_nt(int64_t* lo, int64_t* hi) {
+  while (lo < hi && (reinterpret_cast<uintptr_t>(lo) & 15)) *lo++ = 1;
+  const __m128i one = _mm_set1_epi64x(1);
+  for (; lo + 2 <= hi; lo += 2) _mm_stream_si128(reinterpret_cast<__m128i*>(lo), one);
+  while (lo < hi) *lo++ = 1;
+}
+void cvt_f32_f64_nt(double* dst, const float* src, size_t lo, size_t hi) {
+  while (lo < hi && ((reinterpret_cast<uintptr_t>(dst + lo) & 15) || (lo & 1))) dst[lo] = (double)src[lo], ++lo;
+  for (; lo + 2 <= hi; lo += 2) _mm_stream_pd(dst + lo, _mm_cvtps_pd(_mm_castsi128_ps(_mm_loadl_epi64(reinterpret_cast<const __m128i*>(src + lo)))));
+  while (lo < hi) dst[lo] = (double)src[lo], ++lo;
+}
+static const double* onehot_lut_f64(int d) {   // [d^4][4 d] doubles (d <= 5: <= 100 KB, L2-resident)
+  static double* tabs[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  static std::once_flag once[6];
+  if (d < 1 || d > 5) return nullptr;
+  std::call_once(once[d], [d] {
+    const int n = d * d * d * d;
+    void* mem = nullptr;
+    if (posix_memalign(&mem, 64, (size_t)n * 4 * d * sizeof(double)) != 0) return;
+    double* t = reinterpret_cast<double*>(mem);
+    for (int i = 0; i < n; ++i) {
+      const int a[4] = {i % d, (i / d) % d, (i / (d * d)) % d, i / (d * d * d)};
+      for (int r = 0; r < 4; ++r)
+        for (int j = 0; j < d; ++j) t[(size_t)i * 4 * d + r * d + j] = (j == a[r]) ? 1.0 : 0.0;
+    }
+    tabs[d] = t;
+  });
+  return tabs[d];
+}
+void expand_onehot_f64_nt(double* a, const uint8_t* acts, size_t lo, size_t hi, int d) {
+  auto scalar = [&](size_t row) {
+    double* o = a + row * d;
+    const int arm = acts[row];
+    for (int j = 0; j < d; ++j) o[j] = (j == arm) ? 1.0 : 0.0;
+  };
+  const double* tab = (reinterpret_cast<uintptr_t>(a) & 15) ? nullptr : onehot_lut_f64(d);
+  if (!tab) {
+    for (size_t row = lo; row < hi; ++row) scalar(row);
+    return;
+  }
+  while (lo < hi && (lo & 3)) scalar(lo++);
+  const int m1 = d, m2 = d * d, m3 = d * d * d;
+  for (; lo + 4 <= hi; lo += 4) {   // 4 rows = 4 d doubles = 2 d aligned 16 B vectors
+    const double* src = tab + (size_t)(acts[lo] + m1 * acts[lo + 1] + m2 * acts[lo + 2] + m3 * acts[lo + 3]) * 4 * d;
+    double* o = a + lo * d;
+    for (int v = 0; v < 2 * d; ++v) _mm_stream_pd(o + 2 * v, _mm_load_pd(src + 2 * v));
+  }
+  while (lo < hi) scalar(lo++);
+}
+
 struct HostJobs {
   int K, C, N, H, d, device;
   std::vector<char> compact;                 // per chunk
@@ -150,6 +201,9 @@ struct HostJobs {
   std::atomic<int> next{0}, compact_parts_pending{0};
   std::atomic<bool> failed{false};
   float *s, *a, *ns, *r;
+  bool wide = false;                         // reference dtypes: every chunk compact, expanded to int64 / float64
+  int64_t *s64 = nullptr, *ns64 = nullptr;
+  double *a64 = nullptr, *r64 = nullptr;
 
   void rows_of(int k, int part, size_t& lo, size_t& hi) const {
     const int e0 = k * C, n = std::min(C, N - e0);
@@ -170,6 +224,31 @@ struct HostJobs {
       while (!enqueued[k].load(std::memory_order_acquire) && !failed.load()) std::this_thread::yield();   // kind decided
       if (failed.load()) {
         if (!phase2) phase1_left[k].fetch_sub(1);
+        continue;
+      }
+      if (wide) {
+        // staged by DMA at the start of the chunk's own output regions: arm indices (1 B per row) in next_states,
+        // fp32 rewards in states; phase 1 expands actions + rewards, phase 2 overwrites the staging areas with ones
+        const size_t row0 = (size_t)k * C * H;
+        if (!phase2) {
+          if (cudaEventSynchronize(d2h_done[k]) != cudaSuccess) {
+            failed.store(true);
+            phase1_left[k].fetch_sub(1);
+            compact_parts_pending.fetch_sub(1);
+            continue;
+          }
+          const uint8_t* acts = reinterpret_cast<const uint8_t*>(ns64 + row0) - row0;
+          const float* rew = reinterpret_cast<const float*>(s64 + row0) - row0;
+          expand_onehot_f64_nt(a64, acts, lo, hi, d);
+          cvt_f32_f64_nt(r64, rew, lo, hi);
+          _mm_sfence();
+          phase1_left[k].fetch_sub(1, std::memory_order_release);
+          compact_parts_pending.fetch_sub(1);
+        } else {
+          while (phase1_left[k].load(std::memory_order_acquire) > 0) std::this_thread::yield();
+          fill_ones_i64_nt(s64 + lo, s64 + hi);
+          fill_ones_i64_nt(ns64 + lo, ns64 + hi);
+        }
         continue;
       }
       if (!compact[k]) {                      // DMA chunk: only the constant state columns are host work
@@ -337,14 +416,16 @@ struct HostPool {
 };
 }  // namespace
 
-extern "C" int dpt_bandit_rollin_host(const float* means_host, float var, uint64_t seed, uint64_t env_id0, int N,
-                                      int H, int d, float* ctx_states_host, float* ctx_actions_host,
-                                      float* ctx_next_states_host, float* ctx_rewards_host, void* scratch,
-                                      uint64_t scratch_bytes, void* stream) {
+static int rollin_host_impl(const float* means_host, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
+                            float* ctx_states_host, float* ctx_actions_host, float* ctx_next_states_host,
+                            float* ctx_rewards_host, int64_t* s64, double* a64, int64_t* ns64, double* r64, void* scratch,
+                            uint64_t scratch_bytes, void* stream) {
+  const bool wide = a64 != nullptr;
   DPT_CHECK_ARG(N >= 0 && H >= 0 && d >= 1, "dpt_bandit_rollin_host: bad sizes N=%d H=%d d=%d", N, H, d);
   if (N == 0 || H == 0) return DPT_OK;
-  DPT_CHECK_ARG(means_host && ctx_states_host && ctx_actions_host && ctx_next_states_host && ctx_rewards_host,
+  DPT_CHECK_ARG(means_host && (wide ? (s64 && ns64 && r64) : (ctx_states_host && ctx_actions_host && ctx_next_states_host && ctx_rewards_host)),
                 "dpt_bandit_rollin_host: null host pointer");
+  DPT_CHECK_ARG(!wide || d <= 255, "dpt_bandit_rollin_host_f64: d=%d > 255", d);
   DPT_CHECK_ARG(scratch && scratch_bytes >= dpt_bandit_rollin_host_scratch_bytes(N, H, d),
                 "dpt_bandit_rollin_host: scratch too small (%llu < %llu bytes)", (unsigned long long)scratch_bytes,
                 (unsigned long long)dpt_bandit_rollin_host_scratch_bytes(N, H, d));
@@ -379,10 +460,11 @@ extern "C" int dpt_bandit_rollin_host(const float* means_host, float var, uint64
   jobs.K = (N + C - 1) / C, jobs.C = C, jobs.N = N, jobs.H = H, jobs.d = d;
   DPT_CUDA(cudaGetDevice(&jobs.device));
   jobs.s = ctx_states_host, jobs.a = ctx_actions_host, jobs.ns = ctx_next_states_host, jobs.r = ctx_rewards_host;
+  jobs.wide = wide, jobs.s64 = s64, jobs.a64 = a64, jobs.ns64 = ns64, jobs.r64 = r64;
   jobs.compact.assign(jobs.K, 0);
   jobs.enqueued.reset(new std::atomic<int>[jobs.K]);
   jobs.phase1_left.reset(new std::atomic<int>[jobs.K]);
-  const int policy = (jobs.K >= 4 && d <= 255) ? compact_policy() : 0;
+  const int policy = wide ? 1 : ((jobs.K >= 4 && d <= 255) ? compact_policy() : 0);
   for (int kk = 0; kk < jobs.K; ++kk) {
     jobs.enqueued[kk].store(0);
     jobs.phase1_left[kk].store(HOST_PARTS);
@@ -425,8 +507,13 @@ extern "C" int dpt_bandit_rollin_host(const float* means_host, float var, uint64
       if (rc != DPT_OK) break;
       ck(cudaEventRecord(done[b], cs));
       ck(cudaStreamWaitEvent(copy, done[b], 0));
-      ck(cudaMemcpyAsync(ctx_next_states_host + row, acts_dev, nrow, cudaMemcpyDeviceToHost, copy));   // staged arm indices
-      ck(cudaMemcpyAsync(ctx_rewards_host + row, buf + L.r, sizeof(float) * nrow, cudaMemcpyDeviceToHost, copy));
+      if (wide) {   // staged arm indices / fp32 rewards at the start of the chunk's next_states / states regions
+        ck(cudaMemcpyAsync(ns64 + row, acts_dev, nrow, cudaMemcpyDeviceToHost, copy));
+        ck(cudaMemcpyAsync(s64 + row, buf + L.r, sizeof(float) * nrow, cudaMemcpyDeviceToHost, copy));
+      } else {
+        ck(cudaMemcpyAsync(ctx_next_states_host + row, acts_dev, nrow, cudaMemcpyDeviceToHost, copy));   // staged arm indices
+        ck(cudaMemcpyAsync(ctx_rewards_host + row, buf + L.r, sizeof(float) * nrow, cudaMemcpyDeviceToHost, copy));
+      }
     } else {
       rc = dpt_bandit_rollin(buf + L.means, var, DPT_REWARD_GAUSSIAN, seed, env_id0 + (uint64_t)e0, n, H, d, buf + L.s, buf + L.a,
                              buf + L.ns, buf + L.r, nullptr, nullptr, nullptr, cs);
@@ -461,4 +548,20 @@ extern "C" int dpt_bandit_rollin_host(const float* means_host, float var, uint64
     return DPT_ERR_CUDA;
   }
   return DPT_OK;
+}
+
+extern "C" int dpt_bandit_rollin_host(const float* means_host, float var, uint64_t seed, uint64_t env_id0, int N,
+                                      int H, int d, float* ctx_states_host, float* ctx_actions_host,
+                                      float* ctx_next_states_host, float* ctx_rewards_host, void* scratch,
+                                      uint64_t scratch_bytes, void* stream) {
+  return rollin_host_impl(means_host, var, seed, env_id0, N, H, d, ctx_states_host, ctx_actions_host, ctx_next_states_host,
+                          ctx_rewards_host, nullptr, nullptr, nullptr, nullptr, scratch, scratch_bytes, stream);
+}
+
+extern "C" int dpt_bandit_rollin_host_f64(const float* means_host, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
+                                          int64_t* ctx_states_host, double* ctx_actions_host, int64_t* ctx_next_states_host,
+                                          double* ctx_rewards_host, void* scratch, uint64_t scratch_bytes, void* stream) {
+  DPT_CHECK_ARG(ctx_actions_host, "dpt_bandit_rollin_host_f64: null host pointer");
+  return rollin_host_impl(means_host, var, seed, env_id0, N, H, d, nullptr, nullptr, nullptr, nullptr, ctx_states_host,
+                          ctx_actions_host, ctx_next_states_host, ctx_rewards_host, scratch, scratch_bytes, stream);
 }

@@ -134,6 +134,27 @@ def bandit_rollin_host(means_host, H, var, seed, env_id0=0, out=None, scratch=No
     return out, scratch
 
 
+def bandit_rollin_host_ref(means_host, H, var, seed, env_id0=0, scratch=None):
+    """The collection in the REFERENCE's host dtypes (collect_data.py:23-53): returns numpy arrays context_states
+    [N,H,1] int64, context_actions [N,H,d] float64, context_next_states [N,H,1] int64, context_rewards [N,H] float64.
+    Only arm index + fp32 reward cross PCIe; host threads expand them (dpt_bandit_rollin_host_f64)."""
+    import numpy as np
+    dev = _dev()
+    means_host = means_host.contiguous()
+    assert means_host.dtype == F32 and not means_host.is_cuda
+    N, d = means_host.shape
+    out = {"context_states": np.empty((N, H, 1), dtype=np.int64), "context_actions": np.empty((N, H, d), dtype=np.float64),
+           "context_next_states": np.empty((N, H, 1), dtype=np.int64), "context_rewards": np.empty((N, H), dtype=np.float64)}
+    nbytes = lib().dpt_bandit_rollin_host_scratch_bytes(N, H, d)
+    if scratch is None or scratch.numel() < nbytes:
+        scratch = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)
+    check(lib().dpt_bandit_rollin_host_f64(ptr(means_host), var, seed, env_id0, N, H, d, out["context_states"].ctypes.data,
+                                           out["context_actions"].ctypes.data, out["context_next_states"].ctypes.data,
+                                           out["context_rewards"].ctypes.data, ptr(scratch), scratch.numel(), stream_ptr()),
+          "dpt_bandit_rollin_host_f64")
+    return out
+
+
 def host_write_peak(buf=None, nbytes=1 << 30, n_threads=0):
     """GB/s the host cores reach with non-temporal stores (dpt_host_write_peak): into ``buf`` (a CPU tensor, e.g. the
     pinned output arrays of the e2e path) or an internal buffer.  Needs no GPU."""

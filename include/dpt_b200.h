@@ -124,6 +124,13 @@ uint64_t dpt_bandit_rollin_host_scratch_bytes(int N, int H, int d);
 int dpt_bandit_rollin_host(const float* means_host, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
                            float* ctx_states_host, float* ctx_actions_host, float* ctx_next_states_host,
                            float* ctx_rewards_host, void* scratch, uint64_t scratch_bytes, void* stream);
+/* The same collection in the reference's OWN host dtypes (collect_data.py:23-53: states / next_states int64, one-hot
+ * actions and rewards float64; [N,H,1], [N,H,d], [N,H,1], [N,H] row-major) -- what collect_data.generate_bandit_histories
+ * hands to its callers.  Only 5 B per env-step cross PCIe (arm index + fp32 reward, staged inside the output arrays);
+ * the host cores expand them (64 B per env-step of stores).  The arrays may be pageable. */
+int dpt_bandit_rollin_host_f64(const float* means_host, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
+                               int64_t* ctx_states_host, double* ctx_actions_host, int64_t* ctx_next_states_host,
+                               double* ctx_rewards_host, void* scratch, uint64_t scratch_bytes, void* stream);
 /* Bytes that crossed PCIe device->host in this thread's last dpt_bandit_rollin_host call (the pipeline returns a
  * self-balancing share of the chunks as arm index + reward, 5 B per step, and expands them on the host cores). */
 uint64_t dpt_bandit_rollin_host_last_d2h_bytes(void);

@@ -371,6 +371,21 @@ def test_bandit_env_classes(dpt):
     assert np.allclose(le.means, arms @ np.array([0.3, -0.2])) and le.opt_a[le.opt_a_index] == 1
 
 
+def test_bandit_rollin_host_reference_dtypes(dpt):
+    """dpt_bandit_rollin_host_f64 (the reference's own host dtypes, collect_data.py:23-53) == the device path, value for
+    value, at ragged sizes (partial chunks, d with and without the lookup table)."""
+    for N, H, d in ((1, 1, 5), (37, 23, 5), (9000, 40, 5), (300, 64, 3), (50, 31, 7), (20000, 8, 2)):
+        means, _, _ = dpt.kernels.bandit_sample_means(N, d, 17, 3)
+        dev = dpt.kernels.bandit_rollin(means, H, 0.3, 99, 3)
+        host = dpt.kernels.bandit_rollin_host_ref(means.cpu(), H, 0.3, 99, 3)
+        assert host["context_states"].dtype == np.int64 and host["context_actions"].dtype == np.float64
+        assert host["context_next_states"].dtype == np.int64 and host["context_rewards"].dtype == np.float64
+        assert host["context_rewards"].shape == (N, H) and host["context_states"].shape == (N, H, 1)
+        assert np.array_equal(host["context_actions"], dev["context_actions"].cpu().numpy().astype(np.float64))
+        assert np.array_equal(host["context_rewards"], dev["context_rewards"][:, :, 0].cpu().numpy().astype(np.float64))
+        assert np.all(host["context_states"] == 1) and np.all(host["context_next_states"] == 1)
+
+
 def test_collect_data_dropin_api(dpt):
     from dpt_b200 import collect_data
     from dpt_b200.envs.bandit_env import BanditEnv
