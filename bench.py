@@ -157,7 +157,8 @@ def cpu_other_legs(pool):
             ("config3_linear_thompson_collect_H200_d10", "lin_thomp", 60, 200, dict(dim=10, lin_d=2, var=VAR)),
             ("config3_linucb_online_H200_d10", "lin_ucb", 60, 200, dict(dim=10, lin_d=2, var=VAR)),
             ("config4_emp_online_H500_d5", "emp", 40, H, dict(dim=DIM, var=VAR)),
-            ("config4_thompson_online_H500_d5", "thompson", 20, H, dict(dim=DIM, var=VAR))):
+            ("config4_thompson_online_H500_d5", "thompson", 20, H, dict(dim=DIM, var=VAR)),
+            ("darkroom_online_eval_dim10_H100_Heps4", "darkroom_online", 4, 100, dict(dim=10, horizon=100, Heps=4))):
         r = pool.run(wl, n, hh, seed0=400, **extra)
         out[name] = {"env_steps_per_s": _rate(r), "trajs_per_s": _rate(r, "trajs"), "cores": r["cores"], "kind": "reference",
                      "sample": "%d cores x %d envs x H=%d (%.2f s wall)" % (r["cores"], n, hh, r["wall"])}
@@ -240,6 +241,30 @@ def other_workloads(kernels, torch):
         ms = t(lambda: kernels.online_loop(kind, means5, 500, 0.3, 1, 0, **kw))
         out["config4_%s_online_100k_envs_H500_d5" % kind] = {"ms": ms, "env_steps_per_s": 5e7 / (ms * 1e-3), "trajs_per_s": 1e5 / (ms * 1e-3),
                                                              "frac_of_hbm_peak": 5e7 * 36 / (ms * 1e-3) / 1e9 / peak}
+    # darkroom online evaluation (evals/eval_darkroom.py:20-84), the reference's shape: 100 envs x 40 episodes
+    # of 100 steps on a 10 x 10 grid, context H = 100, GPT-2 embd 32 / 4 layers: per episode ONE dense forward over the 100
+    # query states of every env (fp32 CUDA-core kernel, or tcgen05 with precision 1) + ONE rollout launch
+    try:
+        from dpt_b200.ctrls.ctrl_darkroom import DarkroomTransformerController
+        from dpt_b200.envs.darkroom_env import DarkroomEnv, DarkroomEnvVec
+        from dpt_b200.evals import eval_darkroom
+        from dpt_b200.models.net import Transformer
+        torch.manual_seed(0)
+        dm = Transformer({"horizon": 100, "state_dim": 2, "action_dim": 5, "n_layer": 4, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True})
+        vec = DarkroomEnvVec([DarkroomEnv(10, (i % 10, (3 * i + 1) % 10), 100) for i in range(100)])
+        for prec, name in ((0, "fp32"), (1, "tcgen05_bf16")):
+            dm.precision = prec
+            ctrl = DarkroomTransformerController(dm, batch_size=100, sample=True)
+            eval_darkroom.deploy_online_vec(vec, ctrl, 2, 100, 100)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            eval_darkroom.deploy_online_vec(vec, ctrl, 40, 100, 100)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            out["darkroom_online_eval_100_envs_40_episodes_" + name] = {"ms": 1e3 * dt, "env_steps_per_s": 100 * 40 * 100 / dt, "trajs_per_s": 100 / dt,
+                                                                        "timing": "wall clock around evals.eval_darkroom.deploy_online_vec (returns on the host)"}
+    except Exception as e:   # noqa: BLE001
+        out["darkroom_online_eval"] = "failed: %s" % str(e)[:120]
     return out
 
 
@@ -507,12 +532,15 @@ def main():
     try:    # the host side of the e2e path is a pure memory-write stream: report it against the box's measured store peak
         # (non-temporal stores of this rank's share of the host cores into the SAME pinned output array, all ranks at once)
         n_thr = max(1, len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
-        barrier()
-        hp = kernels.host_write_peak(buf=host_out["context_actions"], n_threads=n_thr)
-        t = torch.tensor([hp], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t)
-        hp = float(t[0])
+        hps = []
+        for _ in range(3):      # three barrier-synchronised measurements (all ranks write at once); median of the sums
+            barrier()
+            t = torch.tensor([kernels.host_write_peak(buf=host_out["context_actions"], n_threads=n_thr)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t)
+            hps.append(float(t[0]))
+        hp = statistics.median(hps)
+        e2e["host_write_peak_samples_gbs"] = hps
         e2e["host_write_peak_gbs"] = hp
         e2e["host_write_peak_note"] = "sum over ranks of dpt_host_write_peak into the pinned actions array, %d threads per rank, all ranks concurrently" % n_thr
         e2e["frac_of_host_peak"] = world * N * H * BYTES_PER_STEP * e2e_steps / (e2e_ms * 1e-3) / 1e9 / hp

@@ -32,6 +32,15 @@ namespace dpt {
 #ifndef DPT_WS_WT10
 #define DPT_WS_WT10 16
 #endif
+#ifndef DPT_WS_STAGGER
+#define DPT_WS_STAGGER 0   // measured: no gain (opt 0.668 -> 0.673 ms, Thompson 0.79 -> 1.01 ms)
+#endif
+#ifndef DPT_WS_FILL_TILE
+#define DPT_WS_FILL_TILE 0
+#endif
+#ifndef DPT_WS_SKIP
+#define DPT_WS_SKIP 0   // measurement builds: 1 = no one-hot stores, 2 = no constant-column fill, 4 = no reward stores
+#endif
 #ifndef DPT_WS_NCONS
 #define DPT_WS_NCONS 4
 #endif
@@ -87,7 +96,8 @@ struct WsKernel {
                                                bool bits_ok, bool vec_r, int lane) {
     const int H = p.H, d = p.d;
     // rewards: T * 4 B per env and tile
-    if (vec_r) {
+    if (DPT_WS_SKIP & 4) {
+    } else if (vec_r) {
 #pragma unroll
       for (int it = 0; it < WQ; ++it) {
         const int e = it * (32 / WQ) + lane / WQ, q = lane % WQ;
@@ -105,6 +115,7 @@ struct WsKernel {
       }
     }
     // one-hot rows
+    if (DPT_WS_SKIP & 1) return;   // (measurement builds only)
     if (bits_ok) {   // d == DMAX and T % 4 == 0: float4 g of an env's run of T*d floats is nibble g % DMAX of step quad g / DMAX
       // lane = (env of a group of 4, 8 consecutive float4): every store covers whole 128 B lines of 4 envs
       const int nbn = (T >> 2) * DMAX;                 // float4 per env in this tile
@@ -300,18 +311,21 @@ struct WsKernel {
     S.untried = (d >= 32) ? 0xffffffffu : ((1u << d) - 1u);
     S.s00 = 1.0, S.s01 = 0.0, S.s11 = 1.0, S.b0 = 0.0, S.b1 = 0.0;
     const double sigma2tc0 = p.p0 * p.p0 * p.p1;                  // Thompson: std^2 (ctrls/ctrl_bandit.py:126) * prior_mean
-    const int ntiles = (H + WT - 1) / WT;
     float* cmp = p.cum_means + env;       // (never NULL here: online_ws_supported)
     const int env0 = env - lane, nl = min(32, N - env0);
     const bool bits_ok = p.vec && d == DMAX && (H % 4 == 0);
     const bool vec_r = (H % 4 == 0) && (reinterpret_cast<uintptr_t>(p.ctx_r) & 15) == 0;
-    if (stage) {   // constant states (bandit dx = 1): this warp's envs are one contiguous run
+    if (stage && !DPT_WS_FILL_TILE && !(DPT_WS_SKIP & 2)) {   // constant states (bandit dx = 1): this warp's envs are one contiguous run
       fill_range(p.ctx_s, (size_t)env0 * H, (size_t)(env0 + nl) * H, 1.0f, lane, 32);
       fill_range(p.ctx_ns, (size_t)env0 * H, (size_t)(env0 + nl) * H, 1.0f, lane, 32);
     }
     Tile& tl = cs.tile;
-    for (int i = 0; i < ntiles; ++i) {
-      const int h0 = i * WT, T = min(WT, H - h0);
+    // Warps start with first tiles of different lengths (WT/4 .. WT steps by warp index), so that the warps of an SM
+    // are in different phases: while some drain a tile (store bursts) the others run their controllers
+    int T = WT;
+    if (DPT_WS_STAGGER) T = (((env0 >> 5) & 3) + 1) * (WT / 4);
+    for (int h0 = 0; h0 < H; h0 += T, T = WT) {
+      T = min(T, H - h0);
       const int nq = T >> 2;
 #pragma unroll 1
       for (int q = 0; q < nq; ++q)
@@ -320,6 +334,13 @@ struct WsKernel {
       if (stage) {
         __syncwarp();
         flush(p, tl, s_nib, env0, nl, h0, T, bits_ok, vec_r, lane);
+        if (DPT_WS_FILL_TILE) {   // the constant state columns of this tile: T * 4 B per env and array
+          for (int i = lane; i < nl * T; i += 32) {
+            const int e = i / T, t = i - e * T;
+            st_stream(p.ctx_s + (size_t)(env0 + e) * H + h0 + t, 1.0f);
+            st_stream(p.ctx_ns + (size_t)(env0 + e) * H + h0 + t, 1.0f);
+          }
+        }
         __syncwarp();
       }
     }

@@ -14,6 +14,7 @@ the only way to use a whole host with it is one process per core -- BASELINE.md 
     gpt2_online evals.eval_bandit.deploy_online_vec + BanditTransformerController
                                                                   (eval_bandit.py:56-103, ctrl_bandit.py:383-444) config 4
     emp/ucb/thompson online: same loop with the classical controllers (ctrl_bandit.py:91,351,232)
+    darkroom_online evals.eval_darkroom.deploy_online_vec + DarkroomTransformerController (eval_darkroom.py:20-84)    §8 (f)1
 * ``kind = "port"``: the numpy restatement in ``oracle/dpt_oracle.py`` (bit-identical outputs from the
   same np.random stream; faster per core than the reference because it builds the categorical cdf once
   per env instead of letting np.random.choice re-validate ``p`` at every draw).
@@ -94,6 +95,19 @@ def _work_impl(args):
             chk = float(np.sum(cum))
         dt = time.perf_counter() - t0
         return n * H, n, dt, chk
+    if workload == "darkroom_online":   # evals/eval_darkroom.py:20-84 + ctrls/ctrl_darkroom.py:23-66
+        import torch
+        dim, horizon, Heps = extra["dim"], extra["horizon"], extra["Heps"]
+        torch.manual_seed(0)
+        cfg = {"horizon": H, "state_dim": 2, "action_dim": 5, "n_layer": extra.get("n_layer", 4), "n_embd": 32, "n_head": 1,
+               "dropout": 0.0, "test": True}
+        model = ref.net.Transformer(cfg).to(ref.net.device).eval()
+        envs = [ref.darkroom_env.DarkroomEnv(dim, ((seed + i) % dim, (3 * i + 1) % dim), horizon) for i in range(n)]
+        ctrl = ref.ctrl_darkroom.DarkroomTransformerController(model, batch_size=n, sample=True)
+        t0 = time.perf_counter()
+        ret = ref.eval_darkroom.deploy_online_vec(ref.darkroom_env.DarkroomEnvVec(envs), ctrl, Heps, H, horizon)
+        dt = time.perf_counter() - t0
+        return n * Heps * horizon, n, dt, float(np.sum(ret))
     # online loops on the plain bandit (config 4 and its classical controllers)
     d = extra["dim"]
     means = np.random.uniform(0, 1, (n, d))
