@@ -425,7 +425,7 @@ def main():
             if gather_mode != "p2p":
                 raise RuntimeError("NCCL gather requested")
             peer = ddist.PeerGather(n_slots)
-            gather_how = "fused in-kernel all-gather of return stats over NVLink peer memory (CUDA IPC), no collective launch"
+            gather_how = "all-gather of return stats over NVLink peer memory (CUDA IPC): a one-warp kernel behind each rollin launch stores the totals into every rank's buffer; no collective launch, no host sync"
         except Exception as e:   # noqa: BLE001
             peer = None
             gather_how = "NCCL all-gather of return stats every step (async) [p2p unavailable: %s]" % str(e)[:80]

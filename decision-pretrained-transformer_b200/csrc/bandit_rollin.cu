@@ -43,9 +43,6 @@ struct RollinParams {
   // fused all-gather over NVLink peer memory (nullable): when the LAST CTA of the launch has seen every
   // CTA's contribution, it stores this rank's three totals into slot `peer_slot` of every rank's gather
   // buffer (peer pointers are CUDA-IPC mappings; plain system-scope stores, no collective launch)
-  double* peer_dst[DPT_MAX_PEERS];
-  int n_peers;
-  unsigned int* done_counter;
   dpt_bandit_inject_t in;
   dpt_bandit_dump_t out;
 };
@@ -137,7 +134,6 @@ __device__ __forceinline__ void rollin_setup_env(const RollinParams& p, int env,
 __device__ __forceinline__ void reduce_stats(const RollinParams& p, float sr, float sr2, float nopt) {
   double* stats = p.stats;
   __shared__ float s_part[3][RB_WARPS];
-  __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -150,21 +146,24 @@ __device__ __forceinline__ void reduce_stats(const RollinParams& p, float sr, fl
   if (threadIdx.x < 3) {
     double acc = 0.0;
     for (int w = 0; w < RB_WARPS; ++w) acc += (double)s_part[threadIdx.x][w];
-    atomicAdd(stats + threadIdx.x, acc);
-    __threadfence();
+    atomicAdd(stats + threadIdx.x, acc);   // fire-and-forget: the kernel boundary orders it before any reader
   }
-  if (p.n_peers > 0) {   // uniform over the grid
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(p.done_counter, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (s_last && threadIdx.x < 3) {
-      __threadfence();
-      const double total = *reinterpret_cast<volatile double*>(stats + threadIdx.x);
-      for (int r = 0; r < p.n_peers; ++r)
-        asm volatile("st.global.release.sys.f64 [%0], %1;" ::"l"(p.peer_dst[r] + threadIdx.x), "d"(total) : "memory");
-      if (threadIdx.x == 0) *p.done_counter = 0u;   // ready for the next launch
-    }
-  }
+}
+
+// Multi-GPU form: a one-warp kernel behind the rollin launch stores the rank's three totals into slot `rank` of every
+// rank's gather buffer over NVLink (plain system-visible stores through the CUDA-IPC mappings, one thread per (peer,
+// statistic): all n_peers * 3 stores are in flight together; the kernel boundary makes them visible, readers order
+// themselves with stream sync + barrier).  Round 1 did this inside the rollin kernel ("last CTA" pattern) with
+// `st.global.release.sys` issued one after the other: every release store waited for the previous one to become
+// visible system-wide, ~1.5 us per peer -- the whole 1 -> 8 GPU efficiency loss (launch 0.3105 ms with the statistics
+// off, 0.3206 / 0.3241 / 0.3296 ms at 2 / 4 / 8 GPUs, linear in the number of peers; profiles/r02_scale_n8_*.json).
+struct PeerPublish {
+  double* dst[DPT_MAX_PEERS];
+  int n;
+};
+__global__ void peer_publish_kernel(const double* __restrict__ stats, const PeerPublish pp) {
+  const int r = threadIdx.x / 3, t = threadIdx.x - 3 * r;
+  if (r < pp.n) asm volatile("st.global.relaxed.sys.f64 [%0], %1;" ::"l"(pp.dst[r] + t), "d"(stats[t]) : "memory");
 }
 
 // packed fp32 pair arithmetic (sm_100: FADD2 / FFMA2, one issue slot for two lanes of work)
@@ -465,13 +464,9 @@ static int bandit_rollin_impl(const float* means, float var, int reward_type, ui
   p.N = N, p.H = H, p.d = d;
   p.ctx_s = ctx_states, p.ctx_a = ctx_actions, p.ctx_ns = ctx_next_states, p.ctx_r = ctx_rewards;
   p.stats = return_stats;
-  if (n_peers > 0) {
-    DPT_CHECK_ARG(n_peers <= DPT_MAX_PEERS && peer_dst && done_counter && return_stats,
-                  "dpt_bandit_rollin_p2p: needs return_stats, a done counter and 1..%d peer pointers", DPT_MAX_PEERS);
-    for (int r = 0; r < n_peers; ++r) p.peer_dst[r] = peer_dst[r];
-    p.n_peers = n_peers;
-    p.done_counter = done_counter;
-  }
+  if (n_peers > 0)
+    DPT_CHECK_ARG(n_peers <= DPT_MAX_PEERS && peer_dst && return_stats,
+                  "dpt_bandit_rollin_p2p: needs return_stats and 1..%d peer pointers", DPT_MAX_PEERS);
   int mode = MODE_PHILOX;
   if (inject) {
     DPT_CHECK_ARG(!dump, "dpt_bandit_rollin: inject and dump are mutually exclusive");
@@ -494,6 +489,14 @@ static int bandit_rollin_impl(const float* means, float var, int reward_type, ui
   else
     launch_mode<MODE_INJECT>(p, fast, st);
   DPT_LAUNCH_CHECK();
+  if (n_peers > 0) {
+    PeerPublish pp{};
+    for (int r = 0; r < n_peers; ++r) pp.dst[r] = peer_dst[r];
+    pp.n = n_peers;
+    peer_publish_kernel<<<1, 3 * DPT_MAX_PEERS <= 32 ? 32 : 3 * DPT_MAX_PEERS, 0, st>>>(return_stats, pp);
+    DPT_LAUNCH_CHECK();
+  }
+  (void)done_counter;   // kept in the ABI (round 1's in-kernel protocol used it); unused
   return DPT_OK;
 }
 

@@ -335,7 +335,7 @@ extern "C" double dpt_host_write_peak(void* dst, uint64_t bytes, int n_threads) 
 // The host half of the pipeline (constant columns, expansion of compact chunks) runs on worker threads that live for
 // the process: created on first use, one per core of THIS rank's share of the cores the process may run on
 // (sched_getaffinity, split by LOCAL_RANK / LOCAL_WORLD_SIZE under torchrun) and pinned there, so that the ranks of a
-// node do not migrate onto each other's cores.  One core of the share is left to the calling thread.
+// node do not migrate onto each other's cores.
 namespace {
 std::vector<int> rank_cpus() {
   std::vector<int> all;
@@ -372,7 +372,7 @@ struct HostPool {
   int capacity() {
     std::lock_guard<std::mutex> g(m);
     if (cpus.empty()) cpus = rank_cpus();
-    int n = (int)cpus.size() - 1;          // one core for the thread that drives the GPU pipeline
+    int n = (int)cpus.size();              // the thread that drives the GPU pipeline sleeps in its waits
     if (const char* e = getenv("DPT_HOST_WORKERS")) n = atoi(e);
     return std::max(1, std::min(64, n));
   }
@@ -398,10 +398,10 @@ struct HostPool {
     while ((int)threads.size() < n) {
       const int idx = (int)threads.size();
       threads.emplace_back([this, idx] { loop(idx); });
-      if (cpus.size() > 1) {   // worker idx -> core idx + 1 of the rank's share (core 0 of the share: the caller)
+      if (cpus.size() > 1) {   // worker idx -> core idx of the rank's share
         cpu_set_t one;
         CPU_ZERO(&one);
-        CPU_SET(cpus[(size_t)(idx + 1) % cpus.size()], &one);
+        CPU_SET(cpus[(size_t)idx % cpus.size()], &one);
         pthread_setaffinity_np(threads.back().native_handle(), sizeof(one), &one);
       }
       threads.back().detach();
@@ -449,7 +449,9 @@ static int rollin_host_impl(const float* means_host, float var, uint64_t seed, u
   DPT_CUDA(cudaStreamCreateWithFlags(&res.copy, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
     DPT_CUDA(cudaEventCreateWithFlags(&res.done[i], cudaEventDisableTiming));
-    DPT_CUDA(cudaEventCreateWithFlags(&res.freed[i], cudaEventDisableTiming));
+    // (blocking sync: the thread that drives the pipeline sleeps in its pacing waits instead of spinning on a core
+    //  the workers can use -- 4 cores per rank at 8 GPUs)
+    DPT_CUDA(cudaEventCreateWithFlags(&res.freed[i], cudaEventDisableTiming | cudaEventBlockingSync));
   }
   cudaStream_t copy = res.copy;
   cudaEvent_t* done = res.done;

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(OL_THREADS) online_loop_kernel(const OnlinePar
         for (int q = lane; q < nq; q += 32) {
           const int t0 = (d == 1) ? 4 * q : (int)__umulhi((uint32_t)(4 * q), p.magic_d);
           const int r0 = 4 * q - t0 * d;
-          const int t1 = min(t0 + 1, OL_T - 1), t2 = min(t0 + 2, OL_T - 1), t3 = min(t0 + 3, OL_T - 1);
+          const int t1 = min(t0 + 1, T - 1), t2 = min(t0 + 2, T - 1), t3 = min(t0 + 3, T - 1);   // never read a step this tile did not write
           float4* dst = dst0 + q;
           for (int e = 0; e < nl; ++e, dst += estride) {
             mask_t M = ((mask_t)1 << tile.acts[e][t0]) | ((mask_t)1 << (d + tile.acts[e][t1]));

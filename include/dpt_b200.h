@@ -88,13 +88,12 @@ int dpt_bandit_rollin(const float* means, float var, int reward_type, uint64_t s
                       double* return_stats, const dpt_bandit_inject_t* inject, const dpt_bandit_dump_t* dump,
                       void* stream);
 
-/* Multi-GPU form: the same launch, plus a fused all-gather of the three return statistics over NVLink peer
- * memory.  return_stats must be zero before the launch (it holds this launch's totals only).  When the last
- * CTA has seen every CTA's contribution it stores the three totals to peer_dst[r][0..2] for r < n_peers
- * (peer_dst: HOST array of device pointers, normally slot `rank` of every rank's gather buffer, opened with
- * dpt_peer_buffer_open; one of them may be this rank's own buffer).  done_counter: device uint32, zero
- * before the first launch, reset by the kernel.  No collective launch, no host synchronisation; readers
- * must order themselves after all ranks' launches (stream sync + barrier). */
+/* Multi-GPU form: the same launch, plus an all-gather of the three return statistics over NVLink peer memory without a
+ * collective: a one-warp kernel enqueued behind the rollin launch stores return_stats[0..2] to peer_dst[r][0..2] for
+ * r < n_peers with system-scope stores (peer_dst: HOST array of device pointers, normally slot `rank` of every rank's
+ * gather buffer, opened with dpt_peer_buffer_open; one of them may be this rank's own buffer).  return_stats must be zero
+ * before the launch (it holds this launch's totals only).  done_counter: unused (round 1's in-kernel protocol), may be
+ * NULL.  No host synchronisation; readers must order themselves after all ranks' launches (stream sync + barrier). */
 int dpt_bandit_rollin_p2p(const float* means, float var, uint64_t seed, uint64_t env_id0, int N, int H, int d,
                           float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
                           double* return_stats, double* const* peer_dst, int n_peers, unsigned int* done_counter,
@@ -108,8 +107,6 @@ int dpt_peer_buffer_read(const void* dev_ptr, void* host_dst, uint64_t bytes, vo
 int dpt_peer_buffer_zero(void* dev_ptr, uint64_t bytes, void* stream);  /* cudaMemsetAsync through a (peer) mapping:
                                                                          * what a rank with an empty env shard publishes */
 /* Protocol notes for dpt_bandit_rollin_p2p / the peer buffers (reference: none -- the reference is single-process):
- *  - the done-counter is reset by the launch that drains it, so all launches that share one counter must be issued
- *    on ONE stream (stream order is what separates consecutive launches' counts);
  *  - a slot may be re-used only after every rank has read it: order readers with stream-sync + barrier BEFORE the
  *    read and a second barrier AFTER it (dist.collect_bandit_sharded does both). */
 

@@ -1,26 +1,20 @@
 #!/bin/bash
 mkdir -p gpurun_out
-V=decision-pretrained-transformer_b200/variants
-cat > /tmp/o.py <<'PY'
-import sys, torch
-sys.path.insert(0,'.')
-import dpt_b200
-from dpt_b200 import kernels
-for N in (20000, 40000):
-  means,_,_ = kernels.bandit_sample_means(N,5,0,0)
-  for kind,par in (("opt",{}),("emp",dict(p0=1.0))):
-    for mat in (True, False):
-        f=lambda: kernels.online_loop(kind, means, 512, 0.3, 2, 0, materialise=mat, regret=False, **par)
-        for _ in range(3): f()
-        torch.cuda.synchronize()
-        e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10): f()
-        e1.record(); torch.cuda.synchronize()
-        ms=e0.elapsed_time(e1)/10
-        print("N=%d H=512"%N, kind, "mat" if mat else "no-mat", "%.3f ms"%ms, "%.0f GB/s"%(N*512*36/ms/1e6) if mat else "", flush=True)
-PY
-for v in wt16 default wt64 wt128; do
-  if [ $v = default ]; then unset DPT_B200_LIB; else export DPT_B200_LIB=$PWD/$V/libdpt_b200_$v.so; fi
-  echo "--- $v"; python /tmp/o.py
-done
+N=$(nvidia-smi -L | wc -l)
+echo "gpus: $N  cores: $(nproc)"
+timeout 900 python -m pytest tests/test_multi_gpu.py tests/test_rollout_gpu.py -m gpu -x -q 2>&1 | tail -3
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 50 --warmup 5 > gpurun_out/bench_n${N}.json 2> gpurun_out/bench_n${N}.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_n${N}.err | cut -c1-300
+python -c "
+import json,sys; l=json.loads([x for x in open('gpurun_out/bench_n${N}.json') if x.startswith('{')][-1])
+print('N=$N: value %.1f G frac %.3f e2e %.2f G (host peak %.0f frac %.2f) d2h/step %.1f'%(l['value']/1e9, l['roofline']['frac'], l['e2e']['value']/1e9, l['e2e'].get('host_write_peak_gbs') or 0, l['e2e'].get('frac_of_host_peak') or 0, l['e2e']['d2h_bytes_per_step']/62.5e6))
+print('per-rank launch ms', ['%.4f'%x for x in l['roofline']['launch_ms_mean_per_rank']])
+if 'online_eval' in l:
+  for sc,r in l['online_eval']['runs'].items():
+    if isinstance(r,dict):
+      for k,v in r.items(): print(sc, k, '%.1f k trajs/s frac %.3f envs/gpu %d'%(v['value']/1e3, v['roofline']['frac'], v['envs_per_gpu']))
+"
+if [ $N -gt 1 ]; then
+timeout 600 python bench.py --no-cpu-baseline --no-other --no-online-eval --steps 50 > gpurun_out/bench_n1_same_box.json 2>/dev/null
+python -c "
+import json; l=json.load(open('gpurun_out/bench_n1_same_box.json')); print('N=1 same box: value %.1f G ms %.4f e2e %.2f G'%(l['value']/1e9, l['ms_per_step'], l['e2e']['value']/1e9))"
+fi
