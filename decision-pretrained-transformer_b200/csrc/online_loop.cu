@@ -355,15 +355,15 @@ __global__ void __launch_bounds__(256) arm_stats_kernel(const float* __restrict_
   }
 }
 
-// The regret scratch comes from the device's default stream-ordered pool; let the pool keep up to 64 MB
-// across synchronisations so that repeated calls do not go back to the driver for it.
-static void keep_pool_memory() {
+// The scratch (regret replicas; split pipeline: the arms words, 1 B per env-step) comes from the device's default
+// stream-ordered pool; let the pool keep up to 256 MB across synchronisations so that repeated calls do not go back to the driver.
+void keep_pool_memory() {
   static thread_local int done_dev = -1;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev == done_dev) return;
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-    uint64_t cur = 0, want = 64ull << 20;
+    uint64_t cur = 0, want = 256ull << 20;
     if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) == cudaSuccess && cur < want)
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &want);
   }
@@ -469,7 +469,8 @@ extern "C" int dpt_online_loop(int ctrl_kind, double p0, double p1, double p2, c
   cudaStream_t st = (cudaStream_t)stream;
   // Every warp adds its 32 envs' partial sums to the same [H,4] block, tile by tile and nearly in lockstep:
   // spread them over replicated accumulators (stream-ordered scratch, <= 4 MB) and fold the replicas afterwards.
-  // DPT_OL_IMPL: 0 / unset = warp-specialised kernel where it applies (d <= 10, lin_d == 2), 1 = always the general kernel
+  // DPT_OL_IMPL: 0 / unset = split pipeline (online_loop_ws.cu) where it applies (d <= 10, lin_d == 2), 2 = its single fused
+  // kernel, 1 = always the general kernel
   static const int impl = [] {
     const char* s = getenv("DPT_OL_IMPL");
     return s ? atoi(s) : 0;
@@ -498,7 +499,7 @@ extern "C" int dpt_online_loop(int ctrl_kind, double p0, double p1, double p2, c
     if (reps_bytes) reps = reinterpret_cast<double*>(scratch), p.regret = reps, p.regret_reps = r;
   }
   if (ws)
-    e = launch_online_ws(ctrl_kind, p, reinterpret_cast<double*>(scratch + reps_bytes), regret_sums, st);
+    e = launch_online_ws(ctrl_kind, p, reinterpret_cast<double*>(scratch + reps_bytes), regret_sums, st, impl == 2);
   else if (d <= 5)
     e = launch_online_kind<5>(ctrl_kind, p, st);
   else if (d <= 10)

@@ -97,7 +97,8 @@ __device__ __forceinline__ void reward_noise4(Key key, uint64_t gid, uint32_t k,
 // online_loop_ws.cu: returns cudaErrorNotSupported when the shape is outside what the warp-specialised kernel
 // handles (the caller then launches the general kernel); tab = [2][H + 1] doubles of count-indexed terms
 // regret_out: the caller's [H,4] sums (+=) or NULL; p.regret then is zeroed scratch of at least regret_reps * H * 3 doubles
-cudaError_t launch_online_ws(int kind, const OnlineParams& p, double* tab, double* regret_out, cudaStream_t st);
+cudaError_t launch_online_ws(int kind, const OnlineParams& p, double* tab, double* regret_out, cudaStream_t st, bool fused);
 bool online_ws_supported(int kind, const OnlineParams& p);
+void keep_pool_memory();
 
 }  // namespace dpt

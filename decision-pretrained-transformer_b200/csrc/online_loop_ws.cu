@@ -22,6 +22,10 @@
 // per step for its three controllers and becomes the bottleneck (controllers stalled 12 % of their time on the
 // "tile drained" barrier); letting every warp drain its own tile has no hand-over and the same instruction count.
 // HBM traffic per env-step: 4 (2 + d + 1) B of context rows + 4 B of cum_means (36 B at d = 5).
+#include <stdlib.h>
+
+#include <mutex>
+
 #include "online_loop.cuh"
 
 namespace dpt {
@@ -60,9 +64,36 @@ struct alignas(16) WsTile {
                              // float4 q DMAX + f of the env's run of T d floats
 };
 
-template <int DMAX, bool STATS>
+// Measurement builds (-DDPT_TIMELINE): first-CTA-start / last-CTA-end of every kernel of a pass on the GPU's global timer,
+// the stand-in for a timeline profiler on a box without nsys (scripts/ol_timeline.py)
+#ifdef DPT_TIMELINE
+__device__ unsigned long long g_tl[64][2];
+struct TlScope {
+  int id;
+  static __device__ __forceinline__ unsigned long long now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+  }
+  __device__ __forceinline__ explicit TlScope(int i) : id(i) {
+    if (threadIdx.x == 0) atomicMin(&g_tl[id][0], now());
+  }
+  __device__ __forceinline__ ~TlScope() {
+    if (threadIdx.x == 0) atomicMax(&g_tl[id][1], now());
+  }
+};
+#define DPT_TL(id) TlScope tl_scope_(id)
+#else
+#define DPT_TL(id)
+#endif
+
+struct WsNoTile {};
+
+// SPLIT: the controller kernel of the split pipeline (below) stages nothing -- it emits the pulled arms as one coalesced
+// 4-byte word per env and step quad and leaves the context rows to online_expand_kernel
+template <int DMAX, bool STATS, bool SPLIT>
 struct alignas(16) WsCons {
-  WsTile<DMAX> tile;
+  std::conditional_t<SPLIT, WsNoTile, WsTile<DMAX>> tile;
   float means[32][DMAX];
   double sum[STATS ? DMAX : 1][32];   // reward sum per arm   (only the pulled arm is touched in a step)
   int cnt[STATS ? DMAX : 1][32];      // pull count per arm
@@ -82,10 +113,25 @@ __device__ __forceinline__ double div_by_count(double a, int n, double rc) {
   return q;
 }
 
-template <int DMAX, int KIND, bool IO>
+// the env step's reward in float64, as the reference forms it; shared by the controller (statistics) and the expander (context rows)
+__device__ __forceinline__ double reward_f64(float ma, float z, double var, int rtype) {
+  return rtype == DPT_REWARD_GAUSSIAN ? (double)ma + (0.0 + var * (double)z)   // envs/bandit_env.py:59
+                                      : (z < ma ? 1.0 : 0.0);                  // :61 Bernoulli(mean)
+}
+
+// what a controller chunk of the split pipeline needs besides OnlineParams
+struct SplitArgs {
+  int h_lo, h_hi;        // steps of this launch (h_lo a multiple of 4)
+  uint32_t* arms4;       // [ceil(H/4)][N]: byte u of word (q, env) = arm pulled at step 4 q + u; NULL = context not materialised
+  double* st_sum;        // [DMAX or 5][N] carried between chunks: reward sums (LinUCB: s00, s01, s11, b0, b1)
+  int* st_cnt;           // [DMAX][N] pull counts
+  int chunk;             // index of the chunk (timeline builds)
+};
+
+template <int DMAX, int KIND, bool IO, bool SPLIT = false>
 struct WsKernel {
   static constexpr bool STATS = (KIND == K_EMP || KIND == K_UCB || KIND == K_THOMPSON);
-  using Cons = WsCons<DMAX, STATS>;
+  using Cons = WsCons<DMAX, STATS, SPLIT>;
   using Tile = WsTile<DMAX>;
   static constexpr int BWQ = Tile::BWQ, WT = Tile::WT, WQ = Tile::WQ;
   static __device__ __forceinline__ int swz(int e) { return swz_t<WQ>(e); }
@@ -158,9 +204,10 @@ struct WsKernel {
 
   // one step quad (4 steps; FULL: all four exist).  Returns nothing; stages rewards / arms / one-hot bits of the quad.
   template <bool FULL>
-  static __device__ __forceinline__ void quad(const OnlineParams& p, Cons& cs, Tile& tl, State& S, const double* s_arms,
+  static __device__ __forceinline__ void quad(const OnlineParams& p, Cons& cs, State& S, const double* s_arms,
                                               const double* __restrict__ tab0, const double* __restrict__ tab1, int h, int nsteps, int q,
-                                              int opt, int env, bool live, uint64_t gid, float*& cmp, double sigma2tc0, bool stage, int lane) {
+                                              int opt, int env, bool live, uint64_t gid, float*& cmp, double sigma2tc0, bool stage, int lane,
+                                              uint32_t* arms4) {
     const int N = p.N, H = p.H, d = p.d;
     // reward noise of the quad: one Philox block + two Box-Muller pairs, off the controller's dependency chain
     float zz[4];
@@ -243,8 +290,7 @@ struct WsKernel {
       // ------------------------------------------------ env step ---------------------------
       const float z = zz[u];
       const float ma = cs.means[lane][a];
-      const double r = p.rtype == DPT_REWARD_GAUSSIAN ? (double)ma + (0.0 + p.var * (double)z)   // envs/bandit_env.py:59
-                                                      : (z < ma ? 1.0 : 0.0);                    // :61 Bernoulli(mean)
+      const double r = reward_f64(ma, z, p.var, p.rtype);
       // ------------------------------------------------ controller statistics --------------
       if (STATS) {
         const double sa = cs.sum[a][lane] + r;
@@ -277,7 +323,10 @@ struct WsKernel {
       aw |= (uint32_t)a << (8 * u);
       bq |= (uint64_t)(1u << a) << (u * DMAX);                          // one-hot row of step u at bit u * DMAX of the quad's string
     }
-    if (stage) {
+    if constexpr (SPLIT) {
+      if (arms4 && live) arms4[(size_t)(h >> 2) * N + env] = aw;   // 128 B per warp and step quad
+    } else if (stage) {
+      Tile& tl = cs.tile;
       tl.rew[lane][q ^ swz(lane)] = make_float4(rr[0], rr[1], rr[2], rr[3]);
       tl.acts[lane][q] = aw;
       tl.bits[lane][q * BWQ] = (uint32_t)bq;
@@ -329,8 +378,8 @@ struct WsKernel {
       const int nq = T >> 2;
 #pragma unroll 1
       for (int q = 0; q < nq; ++q)
-        quad<true>(p, cs, tl, S, s_arms, tab0, tab1, h0 + 4 * q, 4, q, opt, env, live, gid, cmp, sigma2tc0, stage, lane);
-      if (T & 3) quad<false>(p, cs, tl, S, s_arms, tab0, tab1, h0 + 4 * nq, T & 3, nq, opt, env, live, gid, cmp, sigma2tc0, stage, lane);
+        quad<true>(p, cs, S, s_arms, tab0, tab1, h0 + 4 * q, 4, q, opt, env, live, gid, cmp, sigma2tc0, stage, lane, nullptr);
+      if (T & 3) quad<false>(p, cs, S, s_arms, tab0, tab1, h0 + 4 * nq, T & 3, nq, opt, env, live, gid, cmp, sigma2tc0, stage, lane, nullptr);
       if (stage) {
         __syncwarp();
         flush(p, tl, s_nib, env0, nl, h0, T, bits_ok, vec_r, lane);
@@ -342,6 +391,72 @@ struct WsKernel {
           }
         }
         __syncwarp();
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------------------- controller warp, split pipeline
+  // steps [sa.h_lo, sa.h_hi) of the warp's 32 envs; the per-arm (sum, count) -- LinUCB: Sigma and b -- are carried between
+  // the chunks of a pass in global memory ([field][env], coalesced), the cached decision statistics are re-derived from
+  // them with the expressions of the step itself, so a chunked pass is bit-identical to an unchunked one
+  static __device__ __forceinline__ void controller_split(const OnlineParams& p, const SplitArgs& sa, Cons& cs, const double* s_arms,
+                                                          const double* __restrict__ tab0, const double* __restrict__ tab1, int env, bool live,
+                                                          int lane) {
+    const int N = p.N, H = p.H, d = p.d;
+    const uint64_t gid = p.env_id0 + (uint64_t)env;
+    const bool first = sa.h_lo == 0, last = sa.h_hi >= H;
+    const double sigma2tc0 = p.p0 * p.p0 * p.p1;
+    float mmax = -INFINITY;
+    int opt = 0;
+    State S;
+    S.untried = 0u;
+    S.s00 = 1.0, S.s01 = 0.0, S.s11 = 1.0, S.b0 = 0.0, S.b1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j) {
+      const bool real = j < d;         // padding arms (j >= d) carry -inf and can never win an argmax
+      const float mj = (live && real) ? p.means[(size_t)env * d + j] : -INFINITY;
+      if (mj > mmax) mmax = mj, opt = j;
+      cs.means[lane][j] = mj;
+      if (STATS) {
+        double sj = 0.0;
+        int cj = 0;
+        if (!first && live && real) sj = sa.st_sum[(size_t)j * N + env], cj = sa.st_cnt[(size_t)j * N + env];
+        cs.sum[j][lane] = sj, cs.cnt[j][lane] = cj;
+        if (cj == 0) {   // before the first pull: EMP mean 0, UCB 0 + bonus(0) = const, THOMPSON the prior
+          if (real) S.untried |= 1u << j;
+          if (KIND == K_EMP) S.st0[j] = real ? 0.0 : -INFINITY;
+          if (KIND == K_UCB) S.st0[j] = real ? 0.0 + p.p0 : -INFINITY;
+          if (KIND == K_THOMPSON) S.st0[j] = real ? p.p1 : -INFINITY, S.st1[j] = real ? sqrt(p.p2) : 0.0;
+        } else if (KIND == K_THOMPSON) {
+          S.st0[j] = fma(p.p2, sj, sigma2tc0) * __ldg(tab0 + cj);
+          S.st1[j] = __ldg(tab1 + cj);
+        } else {
+          S.st0[j] = div_by_count(sj, cj, __ldg(tab0 + cj));
+          if (KIND == K_UCB) S.st0[j] += __ldg(tab1 + cj);
+        }
+      }
+    }
+    if (KIND == K_LINUCB2 && !first && live) {
+      S.s00 = sa.st_sum[env], S.s01 = sa.st_sum[(size_t)N + env], S.s11 = sa.st_sum[2 * (size_t)N + env];
+      S.b0 = sa.st_sum[3 * (size_t)N + env], S.b1 = sa.st_sum[4 * (size_t)N + env];
+    }
+    __syncwarp();
+    float* cmp = p.cum_means + (size_t)sa.h_lo * N + env;
+    const int h_hi = min(sa.h_hi, H);
+    const int nq = (h_hi - sa.h_lo) >> 2, rem = (h_hi - sa.h_lo) & 3;
+#pragma unroll 1
+    for (int q = 0; q < nq; ++q)
+      quad<true>(p, cs, S, s_arms, tab0, tab1, sa.h_lo + 4 * q, 4, q, opt, env, live, gid, cmp, sigma2tc0, false, lane, sa.arms4);
+    if (rem) quad<false>(p, cs, S, s_arms, tab0, tab1, sa.h_lo + 4 * nq, rem, nq, opt, env, live, gid, cmp, sigma2tc0, false, lane, sa.arms4);
+    if (!last && live) {
+      if (STATS) {
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j)
+          if (j < d) sa.st_sum[(size_t)j * N + env] = cs.sum[j][lane], sa.st_cnt[(size_t)j * N + env] = cs.cnt[j][lane];
+      }
+      if (KIND == K_LINUCB2) {
+        sa.st_sum[env] = S.s00, sa.st_sum[(size_t)N + env] = S.s01, sa.st_sum[2 * (size_t)N + env] = S.s11;
+        sa.st_sum[3 * (size_t)N + env] = S.b0, sa.st_sum[4 * (size_t)N + env] = S.b1;
       }
     }
   }
@@ -370,6 +485,153 @@ __global__ void __launch_bounds__(WS_NCONS * 32, ws_min_blocks<DMAX, KIND>()) on
     K::controller(p, cons[warp], s_arms, s_nib, tab, tab + (p.H + 1), env, env < p.N, lane);
 }
 
+// =============================================================================================
+// Split pipeline (round 2, second half): controller chunks || context expansion || regret pass
+// =============================================================================================
+// The fused kernel above is bound by its context stores: every 32 steps an env's rows leave as 640 B + 128 B pieces scattered over
+// 100k rows, drained by the same warps whose controller chains are the critical path (store-stream elimination in DESIGN.md section 4:
+// 0.10 ms of controller against 0.46 ms of stores at 100k x 500).  Here the sequential part does only what is sequential:
+//   online_ctrl_kernel     lane = env, steps [h_lo, h_hi): arm, reward (for its statistics), cum_means[h, env] and ONE coalesced
+//                          4-byte word of arms per env and step quad into a scratch [H/4][N] (1 B per env-step, stays in L2);
+//   online_expand_kernel   fully parallel over (env, step quad), launched per chunk behind the controller chunk that produced its
+//                          arms: re-derives the rewards from the same Philox block and the same float64 expression and writes the
+//                          one-hot rows and rewards as contiguous 128-step runs (16 B per lane, 512 B per warp and instruction);
+//   ones_fill_kernel       the constant state columns, one streaming fill that runs beside the first controller chunk;
+//   regret_pass_kernel     per chunk, the float64 cumulative regret carried between chunks.
+// The three run on three internal streams forked from / joined to the caller's stream with events (graph-capturable), the
+// controller stream at high priority: HBM-bound expansion and latency-bound control share the SMs.
+#ifndef DPT_CTRL_MINB
+#define DPT_CTRL_MINB (ws_min_blocks<DMAX, KIND>())
+#endif
+#ifndef DPT_EX_MINB
+#define DPT_EX_MINB 12
+#endif
+template <int DMAX, int KIND, bool IO>
+__global__ void __launch_bounds__(WS_NCONS * 32, DPT_CTRL_MINB) online_ctrl_kernel(const OnlineParams p, const double* __restrict__ tab,
+                                                                                                   const SplitArgs sa) {
+  using K = WsKernel<DMAX, KIND, IO, true>;
+  using Cons = typename K::Cons;
+  DPT_TL(1 + sa.chunk);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cons* cons = reinterpret_cast<Cons*>(smem_raw);
+  double* s_arms = reinterpret_cast<double*>(smem_raw + sizeof(Cons) * WS_NCONS);   // [d][2] (LinUCB)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (KIND == K_LINUCB2) {
+    for (int i = tid; i < p.d * 2; i += blockDim.x) s_arms[i] = p.arms[i];
+    __syncthreads();
+  }
+  const int env = (blockIdx.x * WS_NCONS + warp) * 32 + lane;
+  if (env - lane < p.N)            // warp-uniform
+    K::controller_split(p, sa, cons[warp], s_arms, tab, tab + (p.H + 1), env, env < p.N, lane);
+}
+
+constexpr int EX_WARPS = 4;
+constexpr int EX_Q = 32;     // step quads per warp task (lane = quad): 128 steps
+constexpr int EX_TASKS = 8;  // envs per warp
+
+// Fast expander: compile-time d, H % 4 == 0, 16 B-aligned context rows.  A warp task is one env x 32 step quads (lane = quad);
+// a CTA covers 32 consecutive envs, so the 32 lines [quad][env0 .. env0 + 31] of arms words its tasks gather from are fetched once
+// and then hit in L1.  No shared memory, no CTA barrier (the kernel runs in the registers / warp slots the controller kernel
+// leaves free): the env's means sit in lanes 0 .. d - 1 and are picked with a shuffle by the arm; the next task's loads are issued
+// before the current task's stores.
+template <int D, bool INJ>
+__global__ void __launch_bounds__(EX_WARPS * 32, DPT_EX_MINB) online_expand_kernel(const OnlineParams p, const uint32_t* __restrict__ arms4, int q_lo, int q_hi,
+                                                                                   int ngy, int chunk) {
+  DPT_TL(10 + chunk);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = p.N, H = p.H;
+  // CTAs in flight together cover whole rows of consecutive envs (quad group fastest): DRAM sees one compact write window
+  const int bx = blockIdx.x / ngy, by = blockIdx.x - bx * ngy;
+  const int env0 = bx * 32 + warp * EX_TASKS, ne = min(EX_TASKS, N - env0);
+  const int q0 = q_lo + by * EX_Q, nq = min(EX_Q, q_hi - q0);
+  if (ne <= 0) return;
+  const int q = q0 + lane;
+  const bool qv = lane < nq;
+  const uint32_t* asrc = arms4 + (size_t)(qv ? q : q0) * N + env0;
+  const float* msrc = p.means + (size_t)env0 * D + (lane < D ? lane : 0);
+  uint32_t aw_n = __ldg(asrc);
+  float m_n = __ldg(msrc);
+  for (int e = 0; e < ne; ++e) {
+    const int env = env0 + e;
+    const uint32_t aw = aw_n;
+    const float m = m_n;
+    if (e + 1 < ne) aw_n = __ldg(asrc + e + 1), m_n = __ldg(msrc + (e + 1) * D);
+    float zz[4];
+    if (INJ) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) zz[t] = qv ? p.in.reward_z[(size_t)(4 * q + t) * N + env] : 0.f;
+    } else {
+      reward_noise4(p.key, p.env_id0 + (uint64_t)env, (uint32_t)q, p.rtype, zz);
+    }
+    float rr[4];
+    uint64_t bq = 0ull;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int a = qv ? (aw >> (8 * u)) & 255 : 0;
+      rr[u] = (float)reward_f64(__shfl_sync(0xffffffffu, m, a), zz[u], p.var, p.rtype);
+      bq |= (uint64_t)(1u << a) << (u * D);
+    }
+    const size_t row = (size_t)env * H + 4 * (size_t)q0;   // first step of this task
+    st_stream_if(qv, reinterpret_cast<float4*>(p.ctx_r + row) + lane, make_float4(rr[0], rr[1], rr[2], rr[3]));
+    // one-hot rows: the task's 32 quads are 32 D float4; float4 g is nibble g % D of the bit string of quad g / D
+    float4* abase = reinterpret_cast<float4*>(p.ctx_a + row * D);
+    const uint32_t blo = (uint32_t)bq, bhi = (uint32_t)(bq >> 32);
+    const int nvalid = nq * D;
+#pragma unroll
+    for (int it = 0; it < D; ++it) {
+      const int g = it * 32 + lane;
+      const int src = g / D, f = g - src * D;
+      uint32_t w = __shfl_sync(0xffffffffu, blo, src);
+      if (4 * D > 32) {
+        const uint32_t wh = __shfl_sync(0xffffffffu, bhi, src);
+        w = (uint32_t)((((uint64_t)wh << 32) | w) >> (4 * f));
+      } else {
+        w >>= 4 * f;
+      }
+      const float4 v = make_float4((w & 1u) ? 1.f : 0.f, (w & 2u) ? 1.f : 0.f, (w & 4u) ? 1.f : 0.f, (w & 8u) ? 1.f : 0.f);
+      st_stream_if(g < nvalid, abase + g, v);
+    }
+  }
+}
+
+// Generic expander: any d <= 10, any H, any alignment; lane = step quad, scalar stores (odd shapes only)
+__global__ void __launch_bounds__(EX_WARPS * 32) online_expand_generic_kernel(const OnlineParams p, const uint32_t* __restrict__ arms4, int q_lo,
+                                                                              int q_hi) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = p.N, H = p.H, d = p.d;
+  const int env = blockIdx.x * EX_WARPS + warp;
+  if (env >= N) return;
+  const bool inj = p.in.reward_z != nullptr;
+  for (int q = q_lo + lane; q < q_hi; q += 32) {
+    const uint32_t aw = arms4[(size_t)q * N + env];
+    float zz[4];
+    if (inj) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) zz[t] = (4 * q + t < H) ? p.in.reward_z[(size_t)(4 * q + t) * N + env] : 0.f;
+    } else {
+      reward_noise4(p.key, p.env_id0 + (uint64_t)env, (uint32_t)q, p.rtype, zz);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int h = 4 * q + u;
+      if (h >= H) break;
+      const int a = (aw >> (8 * u)) & 255;
+      const size_t row = (size_t)env * H + h;
+      st_stream(p.ctx_r + row, (float)reward_f64(p.means[(size_t)env * d + a], zz[u], p.var, p.rtype));
+      for (int j = 0; j < d; ++j) st_stream(p.ctx_a + row * d + j, j == a ? 1.f : 0.f);
+    }
+  }
+}
+
+// constant states (bandit dx = 1, envs/bandit_env.py:38): context_states = context_next_states = 1
+__global__ void __launch_bounds__(256) ones_fill_kernel(float* __restrict__ a, float* __restrict__ b, size_t n) {
+  DPT_TL(0);
+  const size_t per = ((n + gridDim.x - 1) / gridDim.x + 3) & ~size_t(3);
+  const size_t lo = min(n, per * blockIdx.x), hi = min(n, lo + per);
+  fill_range(a, lo, hi, 1.0f, threadIdx.x, 256);
+  fill_range(b, lo, hi, 1.0f, threadIdx.x, 256);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Regret statistics (evals/eval_bandit.py:169-178) from cum_means [H,N]: sums over envs, per step, of the regret
 // reg = max(means) - cum_means, reg^2, the cumulative regret and its square.  One warp per 32 envs: lane = env for
@@ -379,7 +641,9 @@ __global__ void __launch_bounds__(WS_NCONS * 32, ws_min_blocks<DMAX, KIND>()) on
 constexpr int RP_WARPS = 4;
 constexpr int RP_T = 16;      // steps per tile: 32 envs x 16 steps (6.5 KB of shared memory per warp, so 100k envs are one wave)
 __global__ void __launch_bounds__(RP_WARPS * 32, 6) regret_pass_kernel(const float* __restrict__ cum_means, const float* __restrict__ means, int N,
-                                                                       int H, int d, double* __restrict__ reps, int n_reps) {
+                                                                       int H, int d, double* __restrict__ reps, int n_reps, int h_lo, int h_hi,
+                                                                       double* __restrict__ carry) {
+  DPT_TL(20 + (h_hi - 1) * 8 / H);
   __shared__ float s_cm[RP_WARPS][32][RP_T + 1];
   __shared__ double s_cr[RP_WARPS][32][RP_T + 1];
   __shared__ float s_mx[RP_WARPS][32];
@@ -392,23 +656,24 @@ __global__ void __launch_bounds__(RP_WARPS * 32, 6) regret_pass_kernel(const flo
   if (live)
     for (int j = 0; j < d; ++j) mmax = fmaxf(mmax, means[(size_t)env * d + j]);
   s_mx[warp][lane] = mmax;
-  double creg = 0.0;
+  // steps [h_lo, h_hi) of the pass (split pipeline: one launch per controller chunk, the cumulative regret carried in `carry`)
+  double creg = (h_lo > 0 && live) ? carry[env] : 0.0;
   double* acc = reps + 3 * (size_t)(gw & (n_reps - 1)) * H;    // [n_reps][H][3]: sum reg, sum reg^2, sum creg^2
   const int t = lane & (RP_T - 1), half = lane >> 4;           // sums over envs: lane = (half of the envs, step)
   const float* src = cum_means + env;
   float cm[RP_T], nx[RP_T];
 #pragma unroll
-  for (int k = 0; k < RP_T; ++k) nx[k] = (live && k < H) ? __ldcs(src + (size_t)k * N) : 0.f;
-  for (int h0 = 0; h0 < H; h0 += RP_T) {
-    const int T = min(RP_T, H - h0);
+  for (int k = 0; k < RP_T; ++k) nx[k] = (live && h_lo + k < h_hi) ? __ldcs(src + (size_t)(h_lo + k) * N) : 0.f;
+  for (int h0 = h_lo; h0 < h_hi; h0 += RP_T) {
+    const int T = min(RP_T, h_hi - h0);
 #pragma unroll
     for (int k = 0; k < RP_T; ++k) cm[k] = nx[k];
 #pragma unroll
     for (int k = 0; k < RP_T; ++k)   // next tile's loads are in flight while this one is reduced
-      nx[k] = (live && h0 + RP_T + k < H) ? __ldcs(src + (size_t)(h0 + RP_T + k) * N) : 0.f;
+      nx[k] = (live && h0 + RP_T + k < h_hi) ? __ldcs(src + (size_t)(h0 + RP_T + k) * N) : 0.f;
 #pragma unroll
     for (int k = 0; k < RP_T; ++k) {
-      creg += (double)mmax - (double)cm[k];
+      if (k < T) creg += (double)mmax - (double)cm[k];   // (a carried prefix must not see the padding of a partial tile)
       s_cm[warp][lane][k] = cm[k];
       s_cr[warp][lane][k] = creg;
     }
@@ -427,11 +692,13 @@ __global__ void __launch_bounds__(RP_WARPS * 32, 6) regret_pass_kernel(const flo
     }
     __syncwarp();
   }
+  if (h_hi < H && live) carry[env] = creg;
 }
 
 // regret[h] += (S1, S2, C1, C2)[h]: S1, S2, C2 folded over the replicas in a fixed order; the sum over envs of the cumulative
 // regret is linear in the per-step sums, C1[h] = sum_{h' <= h} S1[h'], so it is a prefix over steps (one block, carry per chunk)
 __global__ void __launch_bounds__(1024) regret_finish_kernel(const double* __restrict__ reps, int n_reps, int H, double* __restrict__ regret) {
+  DPT_TL(30);
   __shared__ double s_warp[32];
   __shared__ double s_carry;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -537,12 +804,177 @@ static cudaError_t launch_ws_kind(int kind, const OnlineParams& p, double* tab, 
   }
 }
 
-cudaError_t launch_online_ws(int kind, const OnlineParams& p, double* tab, double* regret_out, cudaStream_t st) {
+// ------------------------------------------------------------------------------------------- split pipeline, host side
+namespace {
+constexpr int SPLIT_MAX_CHUNKS = 8;
+struct SplitStreams {
+  cudaStream_t ctrl = nullptr, expand = nullptr, regret = nullptr;
+  cudaEvent_t fork = nullptr, chunk[SPLIT_MAX_CHUNKS] = {}, join[3] = {};
+  bool ok = false;
+};
+std::mutex g_split_mu;                 // one pass is enqueued at a time: the internal streams and events are shared per device
+SplitStreams g_split[DPT_MAX_PEERS * 2];
+
+cudaError_t split_streams(SplitStreams** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= (int)(sizeof(g_split) / sizeof(g_split[0]))) return cudaErrorInvalidDevice;
+  SplitStreams& s = g_split[dev];
+  if (!s.ok) {
+    int lo = 0, hi = 0;   // (least, greatest) priority; numerically lower = higher priority
+    if ((e = cudaDeviceGetStreamPriorityRange(&lo, &hi)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithPriority(&s.ctrl, cudaStreamNonBlocking, hi)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithPriority(&s.expand, cudaStreamNonBlocking, lo)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithPriority(&s.regret, cudaStreamNonBlocking, lo)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+    for (auto& ev : s.chunk)
+      if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    for (auto& ev : s.join)
+      if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    s.ok = true;
+  }
+  *out = &s;
+  return cudaSuccess;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+}  // namespace
+
+#define SPLIT_TRY(call)                  \
+  do {                                   \
+    cudaError_t _e = (call);             \
+    if (_e != cudaSuccess) return _e;    \
+  } while (0)
+
+template <int D>
+static void launch_expand_fast(const OnlineParams& p, const uint32_t* arms4, int q_lo, int q_hi, int chunk, cudaStream_t st) {
+  const int ngy = (q_hi - q_lo + EX_Q - 1) / EX_Q;
+  const unsigned grid = (unsigned)((p.N + 31) / 32) * ngy;
+  if (p.in.reward_z)
+    online_expand_kernel<D, true><<<grid, EX_WARPS * 32, 0, st>>>(p, arms4, q_lo, q_hi, ngy, chunk);
+  else
+    online_expand_kernel<D, false><<<grid, EX_WARPS * 32, 0, st>>>(p, arms4, q_lo, q_hi, ngy, chunk);
+}
+
+static void launch_expand(const OnlineParams& p, const uint32_t* arms4, int q_lo, int q_hi, int chunk, cudaStream_t st) {
+  const bool fast = p.vec && p.H % 4 == 0 && aligned16(p.ctx_r);
+  if (fast && p.d == 5) return launch_expand_fast<5>(p, arms4, q_lo, q_hi, chunk, st);
+  if (fast && p.d == 10) return launch_expand_fast<10>(p, arms4, q_lo, q_hi, chunk, st);
+  if (fast && p.d == 2) return launch_expand_fast<2>(p, arms4, q_lo, q_hi, chunk, st);
+  if (fast && p.d == 3) return launch_expand_fast<3>(p, arms4, q_lo, q_hi, chunk, st);
+  if (fast && p.d == 4) return launch_expand_fast<4>(p, arms4, q_lo, q_hi, chunk, st);
+  online_expand_generic_kernel<<<(p.N + EX_WARPS - 1) / EX_WARPS, EX_WARPS * 32, 0, st>>>(p, arms4, q_lo, q_hi);
+}
+
+template <int DMAX, int KIND>
+static cudaError_t launch_split(const OnlineParams& p, double* tab, double* regret_out, cudaStream_t st) {
+  const bool io = p.in.reward_z || p.in.ctrl_z || p.in.first_arm || p.out.reward_z || p.out.ctrl_z || p.out.first_arm;
+  auto kern = io ? online_ctrl_kernel<DMAX, KIND, true> : online_ctrl_kernel<DMAX, KIND, false>;
+  using Cons = typename WsKernel<DMAX, KIND, false, true>::Cons;
+  const size_t smem = sizeof(Cons) * WS_NCONS + (KIND == K_LINUCB2 ? sizeof(double) * 2 * p.d : 0);
+  const int N = p.N, H = p.H;
+  const bool mat = p.ctx_a != nullptr;
+  // chunks of the pass: multiples of 32 steps (step quads; whole regret tiles), DPT_OL_CHUNKS of them (default 4) when the batch is
+  // large enough for the overlap to matter
+  static const int want = env_int("DPT_OL_CHUNKS", 4);
+  int n_chunks = (mat || regret_out) && (size_t)N * H >= (1u << 20) ? min(max(want, 1), SPLIT_MAX_CHUNKS) : 1;
+  int cl = ((H + n_chunks - 1) / n_chunks + 31) & ~31;
+  n_chunks = (H + cl - 1) / cl;
+  const int HQ = (H + 3) / 4;
+  constexpr int NSUM = DMAX > 5 ? DMAX : 5;
+  const size_t b_arms = mat ? (((size_t)HQ * N * 4 + 255) & ~size_t(255)) : 0;
+  const size_t b_sum = n_chunks > 1 ? (((size_t)NSUM * N * 8 + 255) & ~size_t(255)) : 0;
+  const size_t b_cnt = n_chunks > 1 ? (((size_t)DMAX * N * 4 + 255) & ~size_t(255)) : 0;
+  const size_t b_carry = (n_chunks > 1 && regret_out) ? (size_t)N * 8 : 0;
+  unsigned char* scratch = nullptr;
+  if (b_arms + b_sum + b_cnt + b_carry) {
+    keep_pool_memory();
+    SPLIT_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), b_arms + b_sum + b_cnt + b_carry, st));
+  }
+  SplitArgs sa{};
+  sa.arms4 = mat ? reinterpret_cast<uint32_t*>(scratch) : nullptr;
+  sa.st_sum = reinterpret_cast<double*>(scratch + b_arms);
+  sa.st_cnt = reinterpret_cast<int*>(scratch + b_arms + b_sum);
+  double* carry = reinterpret_cast<double*>(scratch + b_arms + b_sum + b_cnt);
+  if (KIND == K_EMP || KIND == K_UCB || KIND == K_THOMPSON)
+    online_ws_table_kernel<<<(H + 1 + 255) / 256, 256, 0, st>>>(KIND, p.p0, p.p2, H, tab);
+  const int warps_total = (N + 31) / 32;
+  const int ctrl_grid = (warps_total + WS_NCONS - 1) / WS_NCONS;
+  const int rp_grid = (warps_total + RP_WARPS - 1) / RP_WARPS;
+  cudaError_t err = cudaSuccess;
+  static const bool serial = env_int("DPT_OL_SERIAL", 0) != 0;   // measurement: everything on the caller's stream, no overlap
+  {
+    std::lock_guard<std::mutex> lock(g_split_mu);
+    SplitStreams* ss = nullptr;
+    SPLIT_TRY(split_streams(&ss));
+    const cudaStream_t s_ctrl = serial ? st : ss->ctrl, s_exp = serial ? st : ss->expand, s_reg = serial ? st : ss->regret;
+    if (!serial) {
+      SPLIT_TRY(cudaEventRecord(ss->fork, st));
+      SPLIT_TRY(cudaStreamWaitEvent(s_ctrl, ss->fork, 0));
+      if (mat) SPLIT_TRY(cudaStreamWaitEvent(s_exp, ss->fork, 0));
+      if (regret_out) SPLIT_TRY(cudaStreamWaitEvent(s_reg, ss->fork, 0));
+    }
+    if (mat) {
+      const size_t n = (size_t)N * H;
+      const size_t fill_want = (n + 16383) / 16384, fill_cap = (size_t)sm_count() * 8;
+      const int fill_grid = (int)(fill_want < fill_cap ? fill_want : fill_cap);
+      ones_fill_kernel<<<max(fill_grid, 1), 256, 0, s_exp>>>(p.ctx_s, p.ctx_ns, n);
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+      sa.h_lo = c * cl, sa.h_hi = min(H, (c + 1) * cl), sa.chunk = c;
+      kern<<<ctrl_grid, WS_NCONS * 32, smem, s_ctrl>>>(p, tab, sa);
+      if (!serial && (mat || regret_out)) SPLIT_TRY(cudaEventRecord(ss->chunk[c], s_ctrl));
+      if (mat) {
+        if (!serial) SPLIT_TRY(cudaStreamWaitEvent(s_exp, ss->chunk[c], 0));
+        launch_expand(p, sa.arms4, sa.h_lo / 4, (sa.h_hi + 3) / 4, c, s_exp);
+      }
+      if (regret_out) {
+        if (!serial) SPLIT_TRY(cudaStreamWaitEvent(s_reg, ss->chunk[c], 0));
+        regret_pass_kernel<<<rp_grid, RP_WARPS * 32, 0, s_reg>>>(p.cum_means, p.means, N, H, p.d, p.regret, p.regret_reps, sa.h_lo, sa.h_hi, carry);
+      }
+    }
+    if (regret_out) regret_finish_kernel<<<1, 1024, 0, s_reg>>>(p.regret, p.regret_reps, H, regret_out);
+    err = cudaGetLastError();
+    if (!serial) {
+      SPLIT_TRY(cudaEventRecord(ss->join[0], s_ctrl));
+      SPLIT_TRY(cudaStreamWaitEvent(st, ss->join[0], 0));
+      if (mat) {
+        SPLIT_TRY(cudaEventRecord(ss->join[1], s_exp));
+        SPLIT_TRY(cudaStreamWaitEvent(st, ss->join[1], 0));
+      }
+      if (regret_out) {
+        SPLIT_TRY(cudaEventRecord(ss->join[2], s_reg));
+        SPLIT_TRY(cudaStreamWaitEvent(st, ss->join[2], 0));
+      }
+    }
+  }
+  if (scratch) SPLIT_TRY(cudaFreeAsync(scratch, st));
+  return err;
+}
+
+template <int DMAX>
+static cudaError_t launch_split_kind(int kind, const OnlineParams& p, double* tab, double* regret_out, cudaStream_t st) {
+  switch (kind) {
+    case K_OPT: return launch_split<DMAX, K_OPT>(p, tab, regret_out, st);
+    case K_EMP: return launch_split<DMAX, K_EMP>(p, tab, regret_out, st);
+    case K_UCB: return launch_split<DMAX, K_UCB>(p, tab, regret_out, st);
+    case K_THOMPSON: return launch_split<DMAX, K_THOMPSON>(p, tab, regret_out, st);
+    default: return launch_split<DMAX, K_LINUCB2>(p, tab, regret_out, st);
+  }
+}
+
+// the split pipeline (default); fused = true: the single fused kernel of this file's first half (DPT_OL_IMPL=2, A/B measurements)
+cudaError_t launch_online_ws(int kind, const OnlineParams& p, double* tab, double* regret_out, cudaStream_t st, bool fused) {
   if (!online_ws_supported(kind, p)) return cudaErrorNotSupported;
+  if (!fused) return p.d <= 5 ? launch_split_kind<5>(kind, p, tab, regret_out, st) : launch_split_kind<10>(kind, p, tab, regret_out, st);
   cudaError_t e = p.d <= 5 ? launch_ws_kind<5>(kind, p, tab, st) : launch_ws_kind<10>(kind, p, tab, st);
   if (e == cudaSuccess && regret_out) {   // [H,4] regret sums from cum_means: p.regret = zeroed [regret_reps][H][3] scratch
     const int ctas = ((p.N + 31) / 32 + RP_WARPS - 1) / RP_WARPS;   // one atomic set per warp (32 envs) and 16-step tile
-    regret_pass_kernel<<<ctas, RP_WARPS * 32, 0, st>>>(p.cum_means, p.means, p.N, p.H, p.d, p.regret, p.regret_reps);
+    regret_pass_kernel<<<ctas, RP_WARPS * 32, 0, st>>>(p.cum_means, p.means, p.N, p.H, p.d, p.regret, p.regret_reps, 0, p.H, nullptr);
     regret_finish_kernel<<<1, 1024, 0, st>>>(p.regret, p.regret_reps, p.H, regret_out);
     e = cudaGetLastError();
   }
@@ -552,6 +984,18 @@ cudaError_t launch_online_ws(int kind, const OnlineParams& p, double* tab, doubl
 }  // namespace dpt
 
 using namespace dpt;
+
+#ifdef DPT_TIMELINE
+// copies the [64][2] stamps to the host (after a device synchronise) and re-arms them
+extern "C" int dpt_debug_timeline(unsigned long long* out) {
+  DPT_CUDA(cudaDeviceSynchronize());
+  DPT_CUDA(cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 128));
+  unsigned long long init[64][2];
+  for (auto& r : init) r[0] = ~0ull, r[1] = 0ull;
+  DPT_CUDA(cudaMemcpyToSymbol(g_tl, init, sizeof(init)));
+  return DPT_OK;
+}
+#endif
 
 extern "C" int dpt_selftest_div(const double* a, const int* n, int count, int* mismatches, void* stream) {
   DPT_CHECK_ARG(a && n && mismatches && count >= 0, "dpt_selftest_div: bad arguments");
