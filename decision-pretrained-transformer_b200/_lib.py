@@ -92,6 +92,7 @@ PROTOTYPES = {
     "dpt_gpu_bandit_step": (c_int, [c_void_p, c_void_p, c_float, c_int, c_uint64, c_uint64, c_int64, c_int, c_int,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "dpt_selftest_div": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "dpt_debug_online_impl": (c_int, [c_int]),
     "dpt_arm_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dpt_online_loop": (c_int, [c_int, c_double, c_double, c_double, c_void_p, c_void_p, c_int, c_double, c_int, c_uint64,
                                 c_uint64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -18,6 +18,8 @@
 // (32 steps * d * 4 B per env).
 #include <cstdlib>
 
+#include <atomic>
+
 #include "online_loop.cuh"
 
 namespace dpt {
@@ -432,6 +434,9 @@ static cudaError_t launch_online_kind(int kind, const OnlineParams& p, cudaStrea
 
 using namespace dpt;
 
+static std::atomic<int> g_online_impl{-1};
+extern "C" int dpt_debug_online_impl(int impl) { return g_online_impl.exchange(impl < -1 || impl > 3 ? -1 : impl); }
+
 extern "C" int dpt_online_loop(int ctrl_kind, double p0, double p1, double p2, const float* means, const double* arms,
                                int lin_d, double var, int reward_type, uint64_t seed, uint64_t env_id0, int N, int H, int d,
                                float* ctx_states, float* ctx_actions, float* ctx_next_states, float* ctx_rewards,
@@ -469,12 +474,16 @@ extern "C" int dpt_online_loop(int ctrl_kind, double p0, double p1, double p2, c
   cudaStream_t st = (cudaStream_t)stream;
   // Every warp adds its 32 envs' partial sums to the same [H,4] block, tile by tile and nearly in lockstep:
   // spread them over replicated accumulators (stream-ordered scratch, <= 4 MB) and fold the replicas afterwards.
-  // DPT_OL_IMPL: 0 / unset = split pipeline (online_loop_ws.cu) where it applies (d <= 10, lin_d == 2), 2 = its single fused
-  // kernel, 1 = always the general kernel
-  static const int impl = [] {
+  // DPT_OL_IMPL: 0 / unset = online_loop_ws.cu where it applies (d <= 10, lin_d == 2): the split pipeline (controller kernel, then
+  // context expansion) for Opt / EmpMean / UCB and for small batches, the single fused kernel for Thompson / LinUCB at large batches
+  // (their controller chains are long enough to hide the fused kernel's scattered stores: 100k x 200, d = 10: 0.50 / 0.65 ms fused
+  // against 0.56 / 0.71 ms split); 2 = always fused, 3 = always split, 1 = always the general kernel
+  static const int env_impl = [] {
     const char* s = getenv("DPT_OL_IMPL");
     return s ? atoi(s) : 0;
   }();
+  const int ovr = g_online_impl.load(std::memory_order_relaxed);
+  const int impl = ovr >= 0 ? ovr : env_impl;
   const bool ws = impl != 1 && online_ws_supported(ctrl_kind, p);
   double* reps = nullptr;
   unsigned char* scratch = nullptr;
@@ -499,7 +508,8 @@ extern "C" int dpt_online_loop(int ctrl_kind, double p0, double p1, double p2, c
     if (reps_bytes) reps = reinterpret_cast<double*>(scratch), p.regret = reps, p.regret_reps = r;
   }
   if (ws)
-    e = launch_online_ws(ctrl_kind, p, reinterpret_cast<double*>(scratch + reps_bytes), regret_sums, st, impl == 2);
+    e = launch_online_ws(ctrl_kind, p, reinterpret_cast<double*>(scratch + reps_bytes), regret_sums, st,
+                         impl == 2 || (impl != 3 && (ctrl_kind == K_THOMPSON || ctrl_kind == K_LINUCB) && N > 32768));
   else if (d <= 5)
     e = launch_online_kind<5>(ctrl_kind, p, st);
   else if (d <= 10)

@@ -24,8 +24,6 @@
 // HBM traffic per env-step: 4 (2 + d + 1) B of context rows + 4 B of cum_means (36 B at d = 5).
 #include <stdlib.h>
 
-#include <mutex>
-
 #include "online_loop.cuh"
 
 namespace dpt {
@@ -119,13 +117,22 @@ __device__ __forceinline__ double reward_f64(float ma, float z, double var, int 
                                       : (z < ma ? 1.0 : 0.0);                  // :61 Bernoulli(mean)
 }
 
-// what a controller chunk of the split pipeline needs besides OnlineParams
+// what the controller kernel of the split pipeline needs besides OnlineParams
 struct SplitArgs {
-  int h_lo, h_hi;        // steps of this launch (h_lo a multiple of 4)
   uint32_t* arms4;       // [ceil(H/4)][N]: byte u of word (q, env) = arm pulled at step 4 q + u; NULL = context not materialised
-  double* st_sum;        // [DMAX or 5][N] carried between chunks: reward sums (LinUCB: s00, s01, s11, b0, b1)
-  int* st_cnt;           // [DMAX][N] pull counts
-  int chunk;             // index of the chunk (timeline builds)
+  double* creg;          // [ceil(H/128) + 1][N]: cumulative regret of the env before step 128 k (float64), last row: max(means);
+                         // NULL = the expander does not accumulate the regret sums
+  bool fill;             // the controller warps also write the constant state columns (H % 4 == 0, 16 B-aligned arrays)
+};
+
+// per-lane state of the split controller besides the controller's own (quad() takes it by reference)
+struct SplitLane {
+  uint32_t* arms4;     // this env's word of the current step quad
+  double* creg_out;    // this env's carry slot of the current 128-step range
+  double sum_ma, mmax; // sum of the pulled arms' means so far; max(means)
+  float4* fill_p;      // next float4 of the constant-column fill (context_states; context_next_states = + fill_off bytes)
+  ptrdiff_t fill_off;
+  int fill_n;          // step quads in which this lane still has a float4 to write
 };
 
 template <int DMAX, int KIND, bool IO, bool SPLIT = false>
@@ -207,7 +214,7 @@ struct WsKernel {
   static __device__ __forceinline__ void quad(const OnlineParams& p, Cons& cs, State& S, const double* s_arms,
                                               const double* __restrict__ tab0, const double* __restrict__ tab1, int h, int nsteps, int q,
                                               int opt, int env, bool live, uint64_t gid, float*& cmp, double sigma2tc0, bool stage, int lane,
-                                              uint32_t* arms4) {
+                                              SplitLane& sl) {
     const int N = p.N, H = p.H, d = p.d;
     // reward noise of the quad: one Philox block + two Box-Muller pairs, off the controller's dependency chain
     float zz[4];
@@ -225,6 +232,20 @@ struct WsKernel {
     float rr[4] = {0.f, 0.f, 0.f, 0.f};
     uint32_t aw = 0u;
     uint64_t bq = 0ull;
+    if (SPLIT && sl.creg_out && (h & 127) == 0) {   // regret carry for the expander: cumulative regret before every 128th step
+      if (live) *sl.creg_out = fma((double)h, sl.mmax, -sl.sum_ma);   // = sum over h' < h of (max(means) - means[arm_h'])
+      sl.creg_out += N;
+    }
+    if (SPLIT && FULL && sl.fill_n > 0) {
+      // constant states (bandit dx = 1, envs/bandit_env.py:38): the warp's 32 envs are one contiguous run of 32 H floats per array,
+      // written 128 floats per step quad and array -- HBM-only work spread over the controller's (latency-bound) lifetime
+      const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (q < sl.fill_n) {
+        st_stream(sl.fill_p, one4);
+        st_stream(reinterpret_cast<float4*>(reinterpret_cast<char*>(sl.fill_p) + sl.fill_off), one4);
+      }
+      sl.fill_p += 32;
+    }
     float zc[KIND == K_THOMPSON ? 2 * DMAX : 1];                  // control normals of the current step pair
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -307,9 +328,10 @@ struct WsKernel {
         }
 #pragma unroll
         for (int j = 0; j < DMAX; ++j) {
-          const bool hit = (j == a);
-          S.st0[j] = hit ? n0 : S.st0[j];
-          if (KIND == K_THOMPSON) S.st1[j] = hit ? n1 : S.st1[j];
+          if (j == a) {
+            S.st0[j] = n0;
+            if (KIND == K_THOMPSON) S.st1[j] = n1;
+          }
         }
       } else if (KIND == K_LINUCB2) {
         const double x0 = s_arms[2 * a], x1 = s_arms[2 * a + 1];
@@ -319,12 +341,16 @@ struct WsKernel {
       // ------------------------------------------------ outputs ----------------------------
       if (live) st_stream(cmp, ma);                                     // get_arm_value :151-153 -> cum_means[hh, env]
       cmp += N;
+      if (SPLIT && sl.creg_out) sl.sum_ma += (double)ma;
       rr[u] = (float)r;
       aw |= (uint32_t)a << (8 * u);
       bq |= (uint64_t)(1u << a) << (u * DMAX);                          // one-hot row of step u at bit u * DMAX of the quad's string
     }
     if constexpr (SPLIT) {
-      if (arms4 && live) arms4[(size_t)(h >> 2) * N + env] = aw;   // 128 B per warp and step quad
+      if (sl.arms4) {
+        if (live) *sl.arms4 = aw;   // 128 B per warp and step quad
+        sl.arms4 += N;
+      }
     } else if (stage) {
       Tile& tl = cs.tile;
       tl.rew[lane][q ^ swz(lane)] = make_float4(rr[0], rr[1], rr[2], rr[3]);
@@ -369,6 +395,7 @@ struct WsKernel {
       fill_range(p.ctx_ns, (size_t)env0 * H, (size_t)(env0 + nl) * H, 1.0f, lane, 32);
     }
     Tile& tl = cs.tile;
+    SplitLane sl{};   // (unused by the fused kernel)
     // Warps start with first tiles of different lengths (WT/4 .. WT steps by warp index), so that the warps of an SM
     // are in different phases: while some drain a tile (store bursts) the others run their controllers
     int T = WT;
@@ -378,8 +405,8 @@ struct WsKernel {
       const int nq = T >> 2;
 #pragma unroll 1
       for (int q = 0; q < nq; ++q)
-        quad<true>(p, cs, S, s_arms, tab0, tab1, h0 + 4 * q, 4, q, opt, env, live, gid, cmp, sigma2tc0, stage, lane, nullptr);
-      if (T & 3) quad<false>(p, cs, S, s_arms, tab0, tab1, h0 + 4 * nq, T & 3, nq, opt, env, live, gid, cmp, sigma2tc0, stage, lane, nullptr);
+        quad<true>(p, cs, S, s_arms, tab0, tab1, h0 + 4 * q, 4, q, opt, env, live, gid, cmp, sigma2tc0, stage, lane, sl);
+      if (T & 3) quad<false>(p, cs, S, s_arms, tab0, tab1, h0 + 4 * nq, T & 3, nq, opt, env, live, gid, cmp, sigma2tc0, stage, lane, sl);
       if (stage) {
         __syncwarp();
         flush(p, tl, s_nib, env0, nl, h0, T, bits_ok, vec_r, lane);
@@ -396,69 +423,44 @@ struct WsKernel {
   }
 
   // ------------------------------------------------------------------------------- controller warp, split pipeline
-  // steps [sa.h_lo, sa.h_hi) of the warp's 32 envs; the per-arm (sum, count) -- LinUCB: Sigma and b -- are carried between
-  // the chunks of a pass in global memory ([field][env], coalesced), the cached decision statistics are re-derived from
-  // them with the expressions of the step itself, so a chunked pass is bit-identical to an unchunked one
   static __device__ __forceinline__ void controller_split(const OnlineParams& p, const SplitArgs& sa, Cons& cs, const double* s_arms,
                                                           const double* __restrict__ tab0, const double* __restrict__ tab1, int env, bool live,
                                                           int lane) {
-    const int N = p.N, H = p.H, d = p.d;
+    const int H = p.H, d = p.d;
     const uint64_t gid = p.env_id0 + (uint64_t)env;
-    const bool first = sa.h_lo == 0, last = sa.h_hi >= H;
     const double sigma2tc0 = p.p0 * p.p0 * p.p1;
     float mmax = -INFINITY;
     int opt = 0;
     State S;
-    S.untried = 0u;
-    S.s00 = 1.0, S.s01 = 0.0, S.s11 = 1.0, S.b0 = 0.0, S.b1 = 0.0;
 #pragma unroll
     for (int j = 0; j < DMAX; ++j) {
       const bool real = j < d;         // padding arms (j >= d) carry -inf and can never win an argmax
       const float mj = (live && real) ? p.means[(size_t)env * d + j] : -INFINITY;
       if (mj > mmax) mmax = mj, opt = j;
       cs.means[lane][j] = mj;
-      if (STATS) {
-        double sj = 0.0;
-        int cj = 0;
-        if (!first && live && real) sj = sa.st_sum[(size_t)j * N + env], cj = sa.st_cnt[(size_t)j * N + env];
-        cs.sum[j][lane] = sj, cs.cnt[j][lane] = cj;
-        if (cj == 0) {   // before the first pull: EMP mean 0, UCB 0 + bonus(0) = const, THOMPSON the prior
-          if (real) S.untried |= 1u << j;
-          if (KIND == K_EMP) S.st0[j] = real ? 0.0 : -INFINITY;
-          if (KIND == K_UCB) S.st0[j] = real ? 0.0 + p.p0 : -INFINITY;
-          if (KIND == K_THOMPSON) S.st0[j] = real ? p.p1 : -INFINITY, S.st1[j] = real ? sqrt(p.p2) : 0.0;
-        } else if (KIND == K_THOMPSON) {
-          S.st0[j] = fma(p.p2, sj, sigma2tc0) * __ldg(tab0 + cj);
-          S.st1[j] = __ldg(tab1 + cj);
-        } else {
-          S.st0[j] = div_by_count(sj, cj, __ldg(tab0 + cj));
-          if (KIND == K_UCB) S.st0[j] += __ldg(tab1 + cj);
-        }
-      }
+      if (STATS) cs.sum[j][lane] = 0.0, cs.cnt[j][lane] = 0;
+      if (KIND == K_EMP) S.st0[j] = real ? 0.0 : -INFINITY;
+      if (KIND == K_UCB) S.st0[j] = real ? 0.0 + p.p0 : -INFINITY;
+      if (KIND == K_THOMPSON) S.st0[j] = real ? p.p1 : -INFINITY, S.st1[j] = real ? sqrt(p.p2) : 0.0;
     }
-    if (KIND == K_LINUCB2 && !first && live) {
-      S.s00 = sa.st_sum[env], S.s01 = sa.st_sum[(size_t)N + env], S.s11 = sa.st_sum[2 * (size_t)N + env];
-      S.b0 = sa.st_sum[3 * (size_t)N + env], S.b1 = sa.st_sum[4 * (size_t)N + env];
-    }
+    S.untried = (1u << d) - 1u;
+    S.s00 = 1.0, S.s01 = 0.0, S.s11 = 1.0, S.b0 = 0.0, S.b1 = 0.0;
     __syncwarp();
-    float* cmp = p.cum_means + (size_t)sa.h_lo * N + env;
-    const int h_hi = min(sa.h_hi, H);
-    const int nq = (h_hi - sa.h_lo) >> 2, rem = (h_hi - sa.h_lo) & 3;
-#pragma unroll 1
-    for (int q = 0; q < nq; ++q)
-      quad<true>(p, cs, S, s_arms, tab0, tab1, sa.h_lo + 4 * q, 4, q, opt, env, live, gid, cmp, sigma2tc0, false, lane, sa.arms4);
-    if (rem) quad<false>(p, cs, S, s_arms, tab0, tab1, sa.h_lo + 4 * nq, rem, nq, opt, env, live, gid, cmp, sigma2tc0, false, lane, sa.arms4);
-    if (!last && live) {
-      if (STATS) {
-#pragma unroll
-        for (int j = 0; j < DMAX; ++j)
-          if (j < d) sa.st_sum[(size_t)j * N + env] = cs.sum[j][lane], sa.st_cnt[(size_t)j * N + env] = cs.cnt[j][lane];
-      }
-      if (KIND == K_LINUCB2) {
-        sa.st_sum[env] = S.s00, sa.st_sum[(size_t)N + env] = S.s01, sa.st_sum[2 * (size_t)N + env] = S.s11;
-        sa.st_sum[3 * (size_t)N + env] = S.b0, sa.st_sum[4 * (size_t)N + env] = S.b1;
-      }
+    float* cmp = p.cum_means + env;
+    SplitLane sl{};
+    sl.arms4 = sa.arms4 ? sa.arms4 + env : nullptr, sl.creg_out = sa.creg ? sa.creg + env : nullptr, sl.mmax = (double)mmax;
+    if (sa.creg && live) sa.creg[(size_t)((H + 127) >> 7) * p.N + env] = (double)mmax;   // row ceil(H / 128): max(means), for the expander
+    if (sa.fill) {   // this lane's float4 of every 128-float piece of the warp's run of min(32, N - env0) * H floats
+      const int env0 = env - lane;
+      const long long run = (long long)min(32, p.N - env0) * H - 4 * lane;
+      sl.fill_n = run > 0 ? (int)((run + 127) >> 7) : 0;
+      sl.fill_p = reinterpret_cast<float4*>(p.ctx_s + (size_t)env0 * H) + lane;
+      sl.fill_off = reinterpret_cast<char*>(p.ctx_ns) - reinterpret_cast<char*>(p.ctx_s);
     }
+    const int nq = H >> 2, rem = H & 3;
+#pragma unroll 1
+    for (int q = 0; q < nq; ++q) quad<true>(p, cs, S, s_arms, tab0, tab1, 4 * q, 4, q, opt, env, live, gid, cmp, sigma2tc0, false, lane, sl);
+    if (rem) quad<false>(p, cs, S, s_arms, tab0, tab1, 4 * nq, rem, nq, opt, env, live, gid, cmp, sigma2tc0, false, lane, sl);
   }
 };
 
@@ -500,18 +502,22 @@ __global__ void __launch_bounds__(WS_NCONS * 32, ws_min_blocks<DMAX, KIND>()) on
 //   regret_pass_kernel     per chunk, the float64 cumulative regret carried between chunks.
 // The three run on three internal streams forked from / joined to the caller's stream with events (graph-capturable), the
 // controller stream at high priority: HBM-bound expansion and latency-bound control share the SMs.
+// resident CTAs per SM the controller kernel is compiled for: 6 (80 registers, no spills; 100k envs = 5.3 CTAs per SM are still one
+// wave), Thompson at d = 10 (40 float64 statistics in registers) 4
+template <int DMAX, int KIND>
+constexpr int ctrl_min_blocks() { return (DMAX > 5 && KIND == K_THOMPSON) ? 4 : 6; }
 #ifndef DPT_CTRL_MINB
-#define DPT_CTRL_MINB (ws_min_blocks<DMAX, KIND>())
+#define DPT_CTRL_MINB (ctrl_min_blocks<DMAX, KIND>())
 #endif
 #ifndef DPT_EX_MINB
-#define DPT_EX_MINB 12
+#define DPT_EX_MINB (REG ? (D > 5 ? 5 : 6) : 8)   // the 12 float64 accumulators of REG need 80 registers (96 at d = 10)
 #endif
 template <int DMAX, int KIND, bool IO>
 __global__ void __launch_bounds__(WS_NCONS * 32, DPT_CTRL_MINB) online_ctrl_kernel(const OnlineParams p, const double* __restrict__ tab,
                                                                                                    const SplitArgs sa) {
   using K = WsKernel<DMAX, KIND, IO, true>;
   using Cons = typename K::Cons;
-  DPT_TL(1 + sa.chunk);
+  DPT_TL(1);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cons* cons = reinterpret_cast<Cons*>(smem_raw);
   double* s_arms = reinterpret_cast<double*>(smem_raw + sizeof(Cons) * WS_NCONS);   // [d][2] (LinUCB)
@@ -526,36 +532,64 @@ __global__ void __launch_bounds__(WS_NCONS * 32, DPT_CTRL_MINB) online_ctrl_kern
 }
 
 constexpr int EX_WARPS = 4;
-constexpr int EX_Q = 32;     // step quads per warp task (lane = quad): 128 steps
-constexpr int EX_TASKS = 8;  // envs per warp
+constexpr int EX_Q = 32;      // step quads per warp task (lane = quad): 128 steps
+constexpr int EX_TASKS = 32;  // envs per warp: the 32 arms words a lane gathers are one 128 B line
 
-// Fast expander: compile-time d, H % 4 == 0, 16 B-aligned context rows.  A warp task is one env x 32 step quads (lane = quad);
-// a CTA covers 32 consecutive envs, so the 32 lines [quad][env0 .. env0 + 31] of arms words its tasks gather from are fetched once
-// and then hit in L1.  No shared memory, no CTA barrier (the kernel runs in the registers / warp slots the controller kernel
-// leaves free): the env's means sit in lanes 0 .. d - 1 and are picked with a shuffle by the arm; the next task's loads are issued
-// before the current task's stores.
-template <int D, bool INJ>
-__global__ void __launch_bounds__(EX_WARPS * 32, DPT_EX_MINB) online_expand_kernel(const OnlineParams p, const uint32_t* __restrict__ arms4, int q_lo, int q_hi,
-                                                                                   int ngy, int chunk) {
-  DPT_TL(10 + chunk);
+// Fast expander: compile-time d, H % 4 == 0, 16 B-aligned context rows.  A warp task is one env x 32 step quads (lane = quad); a
+// warp walks 32 consecutive envs at a fixed 128-step range, so the arms words a lane gathers ([quad][env .. env + 31]) are one
+// line, fetched once and then hit in L1.  No shared memory, no CTA barrier: the env's means sit in lanes 0 .. d - 1 and are picked
+// with a shuffle by the arm; the next task's loads are issued before the current task's stores.  CTAs in flight together cover
+// whole rows of consecutive envs (range index fastest), so DRAM sees one compact write window (x-major order: 4.2 TB/s, this:
+// 5.5 TB/s).
+// REG: the per-step regret sums [H,3] (evals/eval_bandit.py:169-178: sum over envs of reg = max(means) - means[arm], reg^2 and the
+// squared cumulative regret) are accumulated here instead of by a pass over cum_means: a lane owns the same 4 steps for all of its
+// warp's envs, so the sums over envs are thread-local float64 accumulators; the cumulative regret of a step is the carry the
+// controller left for this 128-step range + a warp scan over the quads + the prefix inside the quad.
+template <int D, bool INJ, bool REG>
+__global__ void __launch_bounds__(EX_WARPS * 32, DPT_EX_MINB) online_expand_kernel(const OnlineParams p, const uint32_t* __restrict__ arms4,
+                                                                                   const double* __restrict__ creg_in, int nqt, int ngy) {
+  DPT_TL(10);
+  __shared__ float4 s_nib[16];   // 4-bit pattern -> four 0/1 floats
+  __shared__ uint32_t s_arm[EX_WARPS][EX_Q][33];   // per warp: arms words [quad][env], read back by lane = quad (conflict-free)
+  if (threadIdx.x < 16) {
+    const int t = threadIdx.x;
+    s_nib[t] = make_float4((t & 1) ? 1.f : 0.f, (t & 2) ? 1.f : 0.f, (t & 4) ? 1.f : 0.f, (t & 8) ? 1.f : 0.f);
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int N = p.N, H = p.H;
-  // CTAs in flight together cover whole rows of consecutive envs (quad group fastest): DRAM sees one compact write window
-  const int bx = blockIdx.x / ngy, by = blockIdx.x - bx * ngy;
-  const int env0 = bx * 32 + warp * EX_TASKS, ne = min(EX_TASKS, N - env0);
-  const int q0 = q_lo + by * EX_Q, nq = min(EX_Q, q_hi - q0);
+  // warp slot W = (env block of 32, 128-step range), range fastest: the warps of a CTA write the ranges of the SAME envs' rows at
+  // the same time, env after env -- one contiguous burst per row, like a sequential stream
+  const int W = blockIdx.x * EX_WARPS + warp;
+  const int bx = W / ngy, by = W - bx * ngy;
+  const int env0 = bx * EX_TASKS, ne = min(EX_TASKS, N - env0);
+  const int q0 = by * EX_Q, nq = min(EX_Q, nqt - q0);
   if (ne <= 0) return;
   const int q = q0 + lane;
   const bool qv = lane < nq;
-  const uint32_t* asrc = arms4 + (size_t)(qv ? q : q0) * N + env0;
+  // the warp's arms words: 32 coalesced row loads (one 128 B line each; a lane-per-quad gather would cost 32 LSU wavefronts per
+  // task -- ncu showed the LSU data pipe at 59 %), transposed through shared memory
+#pragma unroll 8
+  for (int k = 0; k < nq; ++k) s_arm[warp][k][lane] = lane < ne ? __ldcs(arms4 + (size_t)(q0 + k) * N + env0 + lane) : 0u;
+  __syncwarp();
   const float* msrc = p.means + (size_t)env0 * D + (lane < D ? lane : 0);
-  uint32_t aw_n = __ldg(asrc);
+  const double* csrc = creg_in + (size_t)by * N + env0;      // (REG only) range `by` starts at step 128 by
   float m_n = __ldg(msrc);
+  const double* xsrc = creg_in + (size_t)ngy * N + env0;     // (REG only) row ngy: max(means) of the env
+  double c_n = REG ? __ldg(csrc) : 0.0, x_n = REG ? __ldg(xsrc) : 0.0;
+  double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0}, c2[4] = {0.0, 0.0, 0.0, 0.0};
   for (int e = 0; e < ne; ++e) {
+#ifdef DPT_EX_SYNC
+    if (ngy == EX_WARPS) __syncthreads();   // (measurement) the CTA's warps = the ranges of one env block: write each row together
+#endif
     const int env = env0 + e;
-    const uint32_t aw = aw_n;
+    const uint32_t aw = qv ? s_arm[warp][lane][e] : 0u;
     const float m = m_n;
-    if (e + 1 < ne) aw_n = __ldg(asrc + e + 1), m_n = __ldg(msrc + (e + 1) * D);
+    const double carry = c_n, mmax = x_n;
+    if (e + 1 < ne) {
+      m_n = __ldg(msrc + (e + 1) * D);
+      if (REG) c_n = __ldg(csrc + e + 1), x_n = __ldg(xsrc + e + 1);
+    }
     float zz[4];
     if (INJ) {
 #pragma unroll
@@ -563,16 +597,29 @@ __global__ void __launch_bounds__(EX_WARPS * 32, DPT_EX_MINB) online_expand_kern
     } else {
       reward_noise4(p.key, p.env_id0 + (uint64_t)env, (uint32_t)q, p.rtype, zz);
     }
-    float rr[4];
+    float rr[4], ma[4];
     uint64_t bq = 0ull;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int a = qv ? (aw >> (8 * u)) & 255 : 0;
-      rr[u] = (float)reward_f64(__shfl_sync(0xffffffffu, m, a), zz[u], p.var, p.rtype);
+      ma[u] = __shfl_sync(0xffffffffu, m, a);
+      rr[u] = (float)reward_f64(ma[u], zz[u], p.var, p.rtype);
       bq |= (uint64_t)(1u << a) << (u * D);
     }
     const size_t row = (size_t)env * H + 4 * (size_t)q0;   // first step of this task
     st_stream_if(qv, reinterpret_cast<float4*>(p.ctx_r + row) + lane, make_float4(rr[0], rr[1], rr[2], rr[3]));
+    // regret of the quad's steps and their prefix; the inclusive scan of the quad totals over the lanes (5 dependent shuffle
+    // rounds) is interleaved with the one-hot stores below, which do not depend on it
+    double reg[4], sc = 0.0;
+    if (REG) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) reg[u] = qv ? mmax - (double)ma[u] : 0.0;
+      sc = ((reg[0] + reg[1]) + reg[2]) + reg[3];
+    }
+    auto scan_round = [&](int o) {
+      const double v = __shfl_up_sync(0xffffffffu, sc, o);
+      if (lane >= o) sc += v;
+    };
     // one-hot rows: the task's 32 quads are 32 D float4; float4 g is nibble g % D of the bit string of quad g / D
     float4* abase = reinterpret_cast<float4*>(p.ctx_a + row * D);
     const uint32_t blo = (uint32_t)bq, bhi = (uint32_t)(bq >> 32);
@@ -588,15 +635,31 @@ __global__ void __launch_bounds__(EX_WARPS * 32, DPT_EX_MINB) online_expand_kern
       } else {
         w >>= 4 * f;
       }
-      const float4 v = make_float4((w & 1u) ? 1.f : 0.f, (w & 2u) ? 1.f : 0.f, (w & 4u) ? 1.f : 0.f, (w & 8u) ? 1.f : 0.f);
-      st_stream_if(g < nvalid, abase + g, v);
+      st_stream_if(g < nvalid, abase + g, s_nib[w & 15u]);
+      if (REG && it < 5) scan_round(1 << it);
     }
+    if (REG) {
+#pragma unroll
+      for (int it = D; it < 5; ++it) scan_round(1 << it);
+      double cr = carry + (sc - (((reg[0] + reg[1]) + reg[2]) + reg[3]));   // cumulative regret before this quad
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        cr += reg[u];                                                       // (lanes past the range: reg = 0, sums land nowhere)
+        s1[u] += reg[u], s2[u] = fma(reg[u], reg[u], s2[u]), c2[u] = fma(cr, cr, c2[u]);
+      }
+    }
+  }
+  if (REG && qv) {
+    double* acc = p.regret + 3 * ((size_t)(bx & (p.regret_reps - 1)) * H + 4 * (size_t)q);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) atomicAdd(acc + 3 * u, s1[u]), atomicAdd(acc + 3 * u + 1, s2[u]), atomicAdd(acc + 3 * u + 2, c2[u]);
   }
 }
 
 // Generic expander: any d <= 10, any H, any alignment; lane = step quad, scalar stores (odd shapes only)
 __global__ void __launch_bounds__(EX_WARPS * 32) online_expand_generic_kernel(const OnlineParams p, const uint32_t* __restrict__ arms4, int q_lo,
                                                                               int q_hi) {
+  DPT_TL(10);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int N = p.N, H = p.H, d = p.d;
   const int env = blockIdx.x * EX_WARPS + warp;
@@ -806,42 +869,12 @@ static cudaError_t launch_ws_kind(int kind, const OnlineParams& p, double* tab, 
 
 // ------------------------------------------------------------------------------------------- split pipeline, host side
 namespace {
-constexpr int SPLIT_MAX_CHUNKS = 8;
-struct SplitStreams {
-  cudaStream_t ctrl = nullptr, expand = nullptr, regret = nullptr;
-  cudaEvent_t fork = nullptr, chunk[SPLIT_MAX_CHUNKS] = {}, join[3] = {};
-  bool ok = false;
-};
-std::mutex g_split_mu;                 // one pass is enqueued at a time: the internal streams and events are shared per device
-SplitStreams g_split[DPT_MAX_PEERS * 2];
-
-cudaError_t split_streams(SplitStreams** out) {
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= (int)(sizeof(g_split) / sizeof(g_split[0]))) return cudaErrorInvalidDevice;
-  SplitStreams& s = g_split[dev];
-  if (!s.ok) {
-    int lo = 0, hi = 0;   // (least, greatest) priority; numerically lower = higher priority
-    if ((e = cudaDeviceGetStreamPriorityRange(&lo, &hi)) != cudaSuccess) return e;
-    if ((e = cudaStreamCreateWithPriority(&s.ctrl, cudaStreamNonBlocking, hi)) != cudaSuccess) return e;
-    if ((e = cudaStreamCreateWithPriority(&s.expand, cudaStreamNonBlocking, lo)) != cudaSuccess) return e;
-    if ((e = cudaStreamCreateWithPriority(&s.regret, cudaStreamNonBlocking, lo)) != cudaSuccess) return e;
-    if ((e = cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming)) != cudaSuccess) return e;
-    for (auto& ev : s.chunk)
-      if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
-    for (auto& ev : s.join)
-      if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
-    s.ok = true;
-  }
-  *out = &s;
-  return cudaSuccess;
+int fill_grid(size_t n, int per_sm) {
+  const size_t want = (n + 16383) / 16384, cap = (size_t)sm_count() * per_sm;
+  const size_t g = want < cap ? want : cap;
+  return g ? (int)g : 1;
 }
 
-int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
 }  // namespace
 
 #define SPLIT_TRY(call)                  \
@@ -850,26 +883,35 @@ int env_int(const char* name, int dflt) {
     if (_e != cudaSuccess) return _e;    \
   } while (0)
 
+static bool expand_is_fast(const OnlineParams& p) {
+  return p.vec && p.H % 4 == 0 && aligned16(p.ctx_r) && (p.d == 10 || (p.d >= 2 && p.d <= 5));
+}
+
 template <int D>
-static void launch_expand_fast(const OnlineParams& p, const uint32_t* arms4, int q_lo, int q_hi, int chunk, cudaStream_t st) {
-  const int ngy = (q_hi - q_lo + EX_Q - 1) / EX_Q;
-  const unsigned grid = (unsigned)((p.N + 31) / 32) * ngy;
-  if (p.in.reward_z)
-    online_expand_kernel<D, true><<<grid, EX_WARPS * 32, 0, st>>>(p, arms4, q_lo, q_hi, ngy, chunk);
-  else
-    online_expand_kernel<D, false><<<grid, EX_WARPS * 32, 0, st>>>(p, arms4, q_lo, q_hi, ngy, chunk);
+static void launch_expand_fast(const OnlineParams& p, const uint32_t* arms4, const double* creg, cudaStream_t st) {
+  const int nqt = p.H / 4, ngy = (nqt + EX_Q - 1) / EX_Q;
+  const unsigned slots = (unsigned)((p.N + EX_TASKS - 1) / EX_TASKS) * ngy, grid = (slots + EX_WARPS - 1) / EX_WARPS;
+  const bool inj = p.in.reward_z != nullptr, reg = creg != nullptr;
+  auto kern = inj ? (reg ? online_expand_kernel<D, true, true> : online_expand_kernel<D, true, false>)
+                  : (reg ? online_expand_kernel<D, false, true> : online_expand_kernel<D, false, false>);
+  kern<<<grid, EX_WARPS * 32, 0, st>>>(p, arms4, creg, nqt, ngy);
 }
 
-static void launch_expand(const OnlineParams& p, const uint32_t* arms4, int q_lo, int q_hi, int chunk, cudaStream_t st) {
-  const bool fast = p.vec && p.H % 4 == 0 && aligned16(p.ctx_r);
-  if (fast && p.d == 5) return launch_expand_fast<5>(p, arms4, q_lo, q_hi, chunk, st);
-  if (fast && p.d == 10) return launch_expand_fast<10>(p, arms4, q_lo, q_hi, chunk, st);
-  if (fast && p.d == 2) return launch_expand_fast<2>(p, arms4, q_lo, q_hi, chunk, st);
-  if (fast && p.d == 3) return launch_expand_fast<3>(p, arms4, q_lo, q_hi, chunk, st);
-  if (fast && p.d == 4) return launch_expand_fast<4>(p, arms4, q_lo, q_hi, chunk, st);
-  online_expand_generic_kernel<<<(p.N + EX_WARPS - 1) / EX_WARPS, EX_WARPS * 32, 0, st>>>(p, arms4, q_lo, q_hi);
+static void launch_expand(const OnlineParams& p, const uint32_t* arms4, const double* creg, cudaStream_t st) {
+  if (expand_is_fast(p)) {
+    switch (p.d) {
+      case 2: return launch_expand_fast<2>(p, arms4, creg, st);
+      case 3: return launch_expand_fast<3>(p, arms4, creg, st);
+      case 4: return launch_expand_fast<4>(p, arms4, creg, st);
+      case 5: return launch_expand_fast<5>(p, arms4, creg, st);
+      default: return launch_expand_fast<10>(p, arms4, creg, st);
+    }
+  }
+  online_expand_generic_kernel<<<(p.N + EX_WARPS - 1) / EX_WARPS, EX_WARPS * 32, 0, st>>>(p, arms4, 0, (p.H + 3) / 4);
 }
 
+// One pass, all on the caller's stream: count tables -> controller (+ constant-column fill) -> expansion (+ regret sums) ->
+// regret_finish.
 template <int DMAX, int KIND>
 static cudaError_t launch_split(const OnlineParams& p, double* tab, double* regret_out, cudaStream_t st) {
   const bool io = p.in.reward_z || p.in.ctrl_z || p.in.first_arm || p.out.reward_z || p.out.ctrl_z || p.out.first_arm;
@@ -878,80 +920,33 @@ static cudaError_t launch_split(const OnlineParams& p, double* tab, double* regr
   const size_t smem = sizeof(Cons) * WS_NCONS + (KIND == K_LINUCB2 ? sizeof(double) * 2 * p.d : 0);
   const int N = p.N, H = p.H;
   const bool mat = p.ctx_a != nullptr;
-  // chunks of the pass: multiples of 32 steps (step quads; whole regret tiles), DPT_OL_CHUNKS of them (default 4) when the batch is
-  // large enough for the overlap to matter
-  static const int want = env_int("DPT_OL_CHUNKS", 4);
-  int n_chunks = (mat || regret_out) && (size_t)N * H >= (1u << 20) ? min(max(want, 1), SPLIT_MAX_CHUNKS) : 1;
-  int cl = ((H + n_chunks - 1) / n_chunks + 31) & ~31;
-  n_chunks = (H + cl - 1) / cl;
-  const int HQ = (H + 3) / 4;
-  constexpr int NSUM = DMAX > 5 ? DMAX : 5;
+  const bool reg_fused = mat && regret_out && expand_is_fast(p);   // regret sums in the expander; otherwise a pass over cum_means
+  const int HQ = (H + 3) / 4, HC = (H + 127) / 128;
   const size_t b_arms = mat ? (((size_t)HQ * N * 4 + 255) & ~size_t(255)) : 0;
-  const size_t b_sum = n_chunks > 1 ? (((size_t)NSUM * N * 8 + 255) & ~size_t(255)) : 0;
-  const size_t b_cnt = n_chunks > 1 ? (((size_t)DMAX * N * 4 + 255) & ~size_t(255)) : 0;
-  const size_t b_carry = (n_chunks > 1 && regret_out) ? (size_t)N * 8 : 0;
+  const size_t b_creg = reg_fused ? (size_t)(HC + 1) * N * 8 : 0;
   unsigned char* scratch = nullptr;
-  if (b_arms + b_sum + b_cnt + b_carry) {
+  if (b_arms + b_creg) {
     keep_pool_memory();
-    SPLIT_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), b_arms + b_sum + b_cnt + b_carry, st));
+    SPLIT_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), b_arms + b_creg, st));
   }
   SplitArgs sa{};
   sa.arms4 = mat ? reinterpret_cast<uint32_t*>(scratch) : nullptr;
-  sa.st_sum = reinterpret_cast<double*>(scratch + b_arms);
-  sa.st_cnt = reinterpret_cast<int*>(scratch + b_arms + b_sum);
-  double* carry = reinterpret_cast<double*>(scratch + b_arms + b_sum + b_cnt);
+  sa.creg = reg_fused ? reinterpret_cast<double*>(scratch + b_arms) : nullptr;
   if (KIND == K_EMP || KIND == K_UCB || KIND == K_THOMPSON)
     online_ws_table_kernel<<<(H + 1 + 255) / 256, 256, 0, st>>>(KIND, p.p0, p.p2, H, tab);
   const int warps_total = (N + 31) / 32;
   const int ctrl_grid = (warps_total + WS_NCONS - 1) / WS_NCONS;
-  const int rp_grid = (warps_total + RP_WARPS - 1) / RP_WARPS;
-  cudaError_t err = cudaSuccess;
-  static const bool serial = env_int("DPT_OL_SERIAL", 0) != 0;   // measurement: everything on the caller's stream, no overlap
-  {
-    std::lock_guard<std::mutex> lock(g_split_mu);
-    SplitStreams* ss = nullptr;
-    SPLIT_TRY(split_streams(&ss));
-    const cudaStream_t s_ctrl = serial ? st : ss->ctrl, s_exp = serial ? st : ss->expand, s_reg = serial ? st : ss->regret;
-    if (!serial) {
-      SPLIT_TRY(cudaEventRecord(ss->fork, st));
-      SPLIT_TRY(cudaStreamWaitEvent(s_ctrl, ss->fork, 0));
-      if (mat) SPLIT_TRY(cudaStreamWaitEvent(s_exp, ss->fork, 0));
-      if (regret_out) SPLIT_TRY(cudaStreamWaitEvent(s_reg, ss->fork, 0));
-    }
-    if (mat) {
-      const size_t n = (size_t)N * H;
-      const size_t fill_want = (n + 16383) / 16384, fill_cap = (size_t)sm_count() * 8;
-      const int fill_grid = (int)(fill_want < fill_cap ? fill_want : fill_cap);
-      ones_fill_kernel<<<max(fill_grid, 1), 256, 0, s_exp>>>(p.ctx_s, p.ctx_ns, n);
-    }
-    for (int c = 0; c < n_chunks; ++c) {
-      sa.h_lo = c * cl, sa.h_hi = min(H, (c + 1) * cl), sa.chunk = c;
-      kern<<<ctrl_grid, WS_NCONS * 32, smem, s_ctrl>>>(p, tab, sa);
-      if (!serial && (mat || regret_out)) SPLIT_TRY(cudaEventRecord(ss->chunk[c], s_ctrl));
-      if (mat) {
-        if (!serial) SPLIT_TRY(cudaStreamWaitEvent(s_exp, ss->chunk[c], 0));
-        launch_expand(p, sa.arms4, sa.h_lo / 4, (sa.h_hi + 3) / 4, c, s_exp);
-      }
-      if (regret_out) {
-        if (!serial) SPLIT_TRY(cudaStreamWaitEvent(s_reg, ss->chunk[c], 0));
-        regret_pass_kernel<<<rp_grid, RP_WARPS * 32, 0, s_reg>>>(p.cum_means, p.means, N, H, p.d, p.regret, p.regret_reps, sa.h_lo, sa.h_hi, carry);
-      }
-    }
-    if (regret_out) regret_finish_kernel<<<1, 1024, 0, s_reg>>>(p.regret, p.regret_reps, H, regret_out);
-    err = cudaGetLastError();
-    if (!serial) {
-      SPLIT_TRY(cudaEventRecord(ss->join[0], s_ctrl));
-      SPLIT_TRY(cudaStreamWaitEvent(st, ss->join[0], 0));
-      if (mat) {
-        SPLIT_TRY(cudaEventRecord(ss->join[1], s_exp));
-        SPLIT_TRY(cudaStreamWaitEvent(st, ss->join[1], 0));
-      }
-      if (regret_out) {
-        SPLIT_TRY(cudaEventRecord(ss->join[2], s_reg));
-        SPLIT_TRY(cudaStreamWaitEvent(st, ss->join[2], 0));
-      }
-    }
+  sa.fill = mat && H % 4 == 0 && aligned16(p.ctx_s) && aligned16(p.ctx_ns);
+  kern<<<ctrl_grid, WS_NCONS * 32, smem, st>>>(p, tab, sa);
+  if (mat && !sa.fill) ones_fill_kernel<<<fill_grid((size_t)N * H, 8), 256, 0, st>>>(p.ctx_s, p.ctx_ns, (size_t)N * H);
+  if (mat) launch_expand(p, sa.arms4, sa.creg, st);
+  if (regret_out) {
+    if (!reg_fused)
+      regret_pass_kernel<<<(warps_total + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, st>>>(p.cum_means, p.means, N, H, p.d, p.regret, p.regret_reps, 0, H,
+                                                                                          nullptr);
+    regret_finish_kernel<<<1, 1024, 0, st>>>(p.regret, p.regret_reps, H, regret_out);
   }
+  const cudaError_t err = cudaGetLastError();
   if (scratch) SPLIT_TRY(cudaFreeAsync(scratch, st));
   return err;
 }

@@ -197,6 +197,12 @@ int dpt_arm_stats(const float* ctx_actions, const float* ctx_rewards, int N, int
  * (a[i], n[i] >= 1) give a / n != the table-reciprocal + two-FMA-correction quotient the fused loop uses in place of
  * the reference's `b / np.maximum(1, counts)` (ctrls/ctrl_bandit.py:105).  Must be 0. */
 int dpt_selftest_div(const double* a, const int32_t* n, int count, int32_t* mismatches, void* stream);
+/* Which implementation dpt_online_loop uses for shapes the fast kernels cover (d <= 10; LinUCB: lin_d == 2), for A/B
+ * measurements and for the parity test that runs every implementation on the same inputs (no reference counterpart):
+ * 0 = automatic (the default: split pipeline -- controller kernel, then context expansion -- or the single fused kernel,
+ * by controller kind and batch size), 1 = general kernel, 2 = fused kernel, 3 = split pipeline; -1 = back to the
+ * DPT_OL_IMPL environment variable (what a fresh process uses).  Returns the previous setting. */
+int dpt_debug_online_impl(int impl);
 
 /* ---------------------------------------------------------------- L1: deploy_online_vec ----
  * evals/eval_bandit.py:56-103 fused with BanditEnvVec.deploy/step (envs/bandit_env.py:98-149) and

@@ -43,6 +43,9 @@ def main():
             if k in h:
                 i = h.index(k)
                 lines.append("%-78s %s %s" % (k, r[i], units[i]))
+        for i, k in enumerate(h):   # every stall reason the capture holds (cycles per issued instruction)
+            if "issue_stalled" in k and k.endswith("per_issue_active.ratio") and k not in KEYS:
+                lines.append("%-78s %s %s" % (k, r[i], units[i]))
         lines.append("")
     open(out, "w").write("\n".join(lines))
     print("\n".join(lines[:60]))

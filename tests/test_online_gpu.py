@@ -375,6 +375,47 @@ def test_deploy_online_single_env(dpt):
     assert eval_linear_bandit.deploy_online is eval_bandit.deploy_online
 
 
+@pytest.fixture
+def online_impl(dpt):
+    """Selects the dpt_online_loop implementation for one test (dpt_debug_online_impl) and restores the default."""
+    lib = dpt._lib.lib()
+    yield lambda impl: lib.dpt_debug_online_impl(int(impl))
+    lib.dpt_debug_online_impl(-1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,par,d,H,N", [("opt", {}, 5, 500, 4099), ("emp", dict(p0=1.0), 5, 500, 4099), ("ucb", dict(p0=1.0), 5, 260, 2050),
+                                            ("thompson", dict(p0=0.3, p1=0.5, p2=1 / 12.0), 5, 500, 3000),
+                                            ("thompson", dict(p0=0.3, p1=0.0, p2=1.0), 10, 200, 3000), ("linucb", dict(p0=1.0), 10, 200, 3000),
+                                            ("emp", dict(p0=1.0), 3, 64, 777), ("ucb", dict(p0=1.0), 7, 33, 500)])
+@pytest.mark.parametrize("reward_type", ["uniform", "bernoulli"])
+def test_online_impls_agree(dpt, online_impl, kind, par, d, H, N, reward_type):
+    """General kernel (1), fused kernel (2) and split pipeline (3) are three implementations of one contract and one Philox
+    stream: identical context tensors and cum_means bit for bit; regret sums: fused vs split to 1e-9 (float64, different summation
+    orders), the general kernel to 1e-6 (it stages the cumulative regret as fp32)."""
+    par = dict(par)
+    if kind == "linucb":
+        par["arms"] = np.random.RandomState(5).normal(size=(d, 2)) / np.sqrt(2)
+    means, _, _ = dpt.kernels.bandit_sample_means(N, d, 17, 0)
+    outs = {}
+    # (Thompson: the general kernel draws its control normals per step, the fast kernels per step pair -- different Philox
+    # counters, same distribution -- so only the two fast implementations are comparable there)
+    impls = (2, 3) if kind == "thompson" else (1, 2, 3)
+    for impl in impls:
+        online_impl(impl)
+        outs[impl] = dpt.kernels.online_loop(kind, means, H, 0.3, 23, 5, reward_type=reward_type, **par)
+    for impl in impls[1:]:
+        for k in ("context_states", "context_actions", "context_next_states", "context_rewards", "cum_means"):
+            assert torch.equal(outs[impl][k], outs[impls[0]][k]), (impl, k)
+        assert torch.allclose(outs[impl]["regret_sums"], outs[impls[0]]["regret_sums"], rtol=1e-6, atol=1e-9), impl
+    assert torch.allclose(outs[3]["regret_sums"], outs[2]["regret_sums"], rtol=1e-9, atol=1e-9)
+    # without the context tensors (the regret sums then come from the pass over cum_means)
+    online_impl(3)
+    lean = dpt.kernels.online_loop(kind, means, H, 0.3, 23, 5, reward_type=reward_type, materialise=False, **par)
+    assert torch.equal(lean["cum_means"], outs[2]["cum_means"])
+    assert torch.allclose(lean["regret_sums"], outs[2]["regret_sums"], rtol=1e-9, atol=1e-9)
+
+
 @pytest.mark.gpu
 def test_count_division_is_exact(dpt):
     """The warp-specialised loop replaces the reference's float64 ``b / max(1, counts)`` (ctrls/ctrl_bandit.py:105) by
@@ -393,11 +434,14 @@ def test_count_division_is_exact(dpt):
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,par", [("opt", {}), ("emp", dict(p0=1.0)), ("emp", dict(p0=0.0)), ("ucb", dict(p0=1.0)),
                                       ("thompson", dict(p0=0.3, p1=0.5, p2=1 / 12.0))])
-@pytest.mark.parametrize("d,H,N", [(5, 500, 997), (5, 37, 65), (3, 50, 33), (10, 200, 300), (7, 19, 100), (1, 9, 40)])
-def test_ws_kernel_matches_oracle_ragged(dpt, kind, par, d, H, N):
-    """The warp-specialised kernel and the general one-warp kernel are two implementations of one contract: on the same
-    injected noise they must agree on every arm bit for bit, on rewards / cum_means exactly and on the regret sums."""
-    import subprocess, sys, json, tempfile
+@pytest.mark.parametrize("d,H,N", [(5, 500, 997), (5, 37, 65), (3, 50, 33), (10, 200, 300), (7, 19, 100), (1, 9, 40), (5, 132, 130), (4, 260, 70)])
+@pytest.mark.parametrize("impl", [3])   # (fused kernel == split pipeline bit for bit: test_online_impls_agree)
+def test_ws_kernel_matches_oracle_ragged(dpt, kind, par, d, H, N, impl, online_impl):
+    """The fast kernels (impl 2: single fused kernel; impl 3: split pipeline = controller kernel + context expansion with the
+    regret sums) against the oracle's recount-from-context controllers on the same injected noise: every arm bit for bit,
+    rewards to 1e-5, cum_means exactly, the regret sums to 1e-6 -- at ragged sizes (partial warps, partial step quads,
+    partial 128-step ranges, d below / at the compiled widths)."""
+    online_impl(impl)
     rs = np.random.RandomState(d * 1000 + H)
     means = torch.tensor(rs.uniform(0, 1, (N, d)).astype(np.float32), device="cuda")
     inj = {"reward_z": rs.normal(0, 1, (H, N)).astype(np.float32)}
