@@ -536,11 +536,14 @@ constexpr int EX_Q = 32;      // step quads per warp task (lane = quad): 128 ste
 constexpr int EX_TASKS = 32;  // envs per warp: the 32 arms words a lane gathers are one 128 B line
 
 // Fast expander: compile-time d, H % 4 == 0, 16 B-aligned context rows.  A warp task is one env x 32 step quads (lane = quad); a
-// warp walks 32 consecutive envs at a fixed 128-step range, so the arms words a lane gathers ([quad][env .. env + 31]) are one
-// line, fetched once and then hit in L1.  No shared memory, no CTA barrier: the env's means sit in lanes 0 .. d - 1 and are picked
-// with a shuffle by the arm; the next task's loads are issued before the current task's stores.  CTAs in flight together cover
-// whole rows of consecutive envs (range index fastest), so DRAM sees one compact write window (x-major order: 4.2 TB/s, this:
-// 5.5 TB/s).
+// warp walks up to 32 consecutive envs at a fixed 128-step range.  Its arms words arrive as coalesced [quad][env] rows (one line
+// each) and are transposed through a per-warp shared-memory tile -- a lane-per-quad gather costs 32 LSU wavefronts per task (ncu:
+// LSU data pipe at 59 %).  Rewards are re-derived from the same Philox block and float64 expression as in the controller (letting
+// the controller store them in place, 16 B per lane at a row stride, cost it 258 -> 402 us).  The env's means sit in lanes
+// 0 .. d - 1 and are picked with a shuffle by the arm.  One-hot rows: the task's 32 D float4 are re-tiled across the warp by
+// shuffling the quads' bit strings; a float4 is one nibble = one 16-entry table lookup.  Warp slots are enumerated range-fastest,
+// so CTAs in flight together cover whole rows of consecutive envs and DRAM sees one compact write window (env-block-fastest
+// order: 4.2 TB/s, this order: 5.5 TB/s).
 // REG: the per-step regret sums [H,3] (evals/eval_bandit.py:169-178: sum over envs of reg = max(means) - means[arm], reg^2 and the
 // squared cumulative regret) are accumulated here instead of by a pass over cum_means: a lane owns the same 4 steps for all of its
 // warp's envs, so the sums over envs are thread-local float64 accumulators; the cumulative regret of a step is the carry the
@@ -579,9 +582,6 @@ __global__ void __launch_bounds__(EX_WARPS * 32, DPT_EX_MINB) online_expand_kern
   double c_n = REG ? __ldg(csrc) : 0.0, x_n = REG ? __ldg(xsrc) : 0.0;
   double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0}, c2[4] = {0.0, 0.0, 0.0, 0.0};
   for (int e = 0; e < ne; ++e) {
-#ifdef DPT_EX_SYNC
-    if (ngy == EX_WARPS) __syncthreads();   // (measurement) the CTA's warps = the ranges of one env block: write each row together
-#endif
     const int env = env0 + e;
     const uint32_t aw = qv ? s_arm[warp][lane][e] : 0u;
     const float m = m_n;
