@@ -25,6 +25,8 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -198,7 +200,13 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
       const float4* K4 = reinterpret_cast<const float4*>(K) + b8;   // row stride = 8 float4
       const float4* V4 = reinterpret_cast<const float4*>(V) + b8;
       __syncwarp();
-      for (int k0 = 0; k0 < pos; k0 += 32) {  // cached keys 0..pos-1, 32 per iteration: 8 row loads in flight per lane
+      // cached keys 0..pos-1, 32 per tile: 8 row loads in flight per lane.  TAIL = the last, partial tile: load instruction i
+      // covers keys k0 + 4 i .. k0 + 4 i + 3 of all key groups, so instructions past the last key are skipped with a
+      // WARP-UNIFORM predicate (round 2: the padded rows of the last tile were 4.7 % of the kernel's DRAM traffic; per-lane
+      // predication of every tile, DPT_GPT2_KPRED, cost more issue than the bytes saved)
+      auto k_tile = [&](const int k0, auto tail_tag) {
+        constexpr bool TAIL = decltype(tail_tag)::value;
+        const int r = pos - k0;
         if (pos <= PF_MAX_POS && k0 + PF_AHEAD * 32 < pos) prefetch_l2(K + (size_t)(k0 + PF_AHEAD * 32 + lane) * G_E);
         float4 kk[8];
   #pragma unroll
@@ -206,7 +214,7 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
 #if DPT_GPT2_KPRED   // rows >= pos are not read (3-5 % of the K/V traffic at H = 500)
           kk[i] = (k0 + 4 * i + g < pos) ? __ldcg(K4 + (size_t)(k0 + 4 * i + g) * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
 #else
-          kk[i] = __ldcg(K4 + (size_t)(k0 + 4 * i + g) * 8);   // in bounds (Tpad % 32 == 0)
+          kk[i] = (!TAIL || 4 * i < r) ? __ldcg(K4 + (size_t)(k0 + 4 * i + g) * 8) : make_float4(0.f, 0.f, 0.f, 0.f);   // in bounds (Tpad % 32 == 0)
 #endif
         }
         float pv[8];
@@ -227,10 +235,15 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
         }
         const float sc = (u1 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, u1 ? w2[0] : w2[1], 1);
         const int key = k0 + 4 * b8 + g;
-        if (key < pos) {
+        if (!TAIL || key < pos) {
           ssc[key] = sc;
           lmax = fmaxf(lmax, sc);
         }
+      };
+      {
+        int k0 = 0;
+        for (; k0 + 32 <= pos; k0 += 32) k_tile(k0, std::false_type{});
+        if (k0 < pos) k_tile(k0, std::true_type{});
       }
       s_self = warp_sum(q * k);  // the token attends to itself (causal mask keeps keys <= pos)
       lmax = fmaxf(warp_max(lmax), s_self);
@@ -245,14 +258,15 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
       inv = 1.0f / (warp_sum(lsum) + p_self);
       __syncwarp();
       float4 oa = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int k0 = 0; k0 < pos; k0 += 32) {
+      auto v_tile = [&](const int k0, auto tail_tag) {
+        constexpr bool TAIL = decltype(tail_tag)::value;
         if (pos <= PF_MAX_POS && k0 + PF_AHEAD * 32 < pos) prefetch_l2(V + (size_t)(k0 + PF_AHEAD * 32 + lane) * G_E);
         float4 vv[8];
         float pr[8];
   #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int key = k0 + 4 * i + g;
-          const bool ok = key < pos;                 // rows >= pos are uninitialised: never touch them
+          const bool ok = !TAIL || key < pos;        // rows >= pos are uninitialised: never touch them
           vv[i] = ok ? __ldcg(V4 + (size_t)key * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
           pr[i] = ok ? ssc[key] : 0.f;
         }
@@ -263,6 +277,11 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
           oa.z = fmaf(pr[i], vv[i].z, oa.z);
           oa.w = fmaf(pr[i], vv[i].w, oa.w);
         }
+      };
+      {
+        int k0 = 0;
+        for (; k0 + 32 <= pos; k0 += 32) v_tile(k0, std::false_type{});
+        if (k0 < pos) v_tile(k0, std::true_type{});
       }
       // sum the 4 key groups (lanes with equal b8), then hand channel `lane` its value
   #pragma unroll
@@ -313,14 +332,18 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
       }
       const uint4* K8 = reinterpret_cast<const uint4*>(K) + c;   // row stride = 4 uint4
       __syncwarp();
-      for (int k0 = 0; k0 < pos; k0 += 64) {
+      // 64 keys per tile; TAIL = the last, partial tile: load instruction i covers keys k0 + 8 i .. k0 + 8 i + 7, instructions
+      // past the last key are skipped with a warp-uniform predicate (the padded rows were 6.2 % of the DRAM traffic)
+      auto k_tile = [&](const int k0, auto tail_tag) {
+        constexpr bool TAIL = decltype(tail_tag)::value;
+        const int r = pos - k0;
         uint4 kk[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
 #if DPT_GPT2_KPRED   // rows >= pos are not read (~6 % of the K/V traffic at H = 500)
           kk[i] = (k0 + 8 * i + g < pos) ? __ldcg(K8 + (size_t)(k0 + 8 * i + g) * 4) : make_uint4(0u, 0u, 0u, 0u);
 #else
-          kk[i] = __ldcg(K8 + (size_t)(k0 + 8 * i + g) * 4);   // in bounds (Tpad % 64 == 0)
+          kk[i] = (!TAIL || 8 * i < r) ? __ldcg(K8 + (size_t)(k0 + 8 * i + g) * 4) : make_uint4(0u, 0u, 0u, 0u);   // in bounds (Tpad % 64 == 0)
 #endif
         }
         // the V blocks of the same 64 keys (4 KB = one 128 B line per lane) start their trip from HBM to L2 now; the
@@ -330,15 +353,21 @@ __device__ __forceinline__ float token_forward(const Gpt2Dev& m, float x, int po
         // scores^T = K q^T: 16 keys are the rows of the A tile (octets 2m and 2m + 1), q is column 0 of B
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
+          if (TAIL && 16 * mt >= r) break;        // (warp-uniform)
           float d[4] = {0.f, 0.f, 0.f, 0.f};
           mma_bf16_16816(d, kk[2 * mt].x, kk[2 * mt + 1].x, kk[2 * mt].y, kk[2 * mt + 1].y, qa0, qa1);
           mma_bf16_16816(d, kk[2 * mt].z, kk[2 * mt + 1].z, kk[2 * mt].w, kk[2 * mt + 1].w, qa2, qa3);
           const int key = k0 + 16 * mt + g;       // column 0 of the tile: lanes with c == 0 hold keys g and g + 8
           if (c == 0) {
-            if (key < pos) ssc[key] = d[0], lmax = fmaxf(lmax, d[0]);
-            if (key + 8 < pos) ssc[key + 8] = d[2], lmax = fmaxf(lmax, d[2]);
+            if (!TAIL || key < pos) ssc[key] = d[0], lmax = fmaxf(lmax, d[0]);
+            if (!TAIL || key + 8 < pos) ssc[key + 8] = d[2], lmax = fmaxf(lmax, d[2]);
           }
         }
+      };
+      {
+        int k0 = 0;
+        for (; k0 + 64 <= pos; k0 += 64) k_tile(k0, std::false_type{});
+        if (k0 < pos) k_tile(k0, std::true_type{});
       }
       s_self = warp_sum(q * k);
       lmax = fmaxf(warp_max(lmax), s_self);
