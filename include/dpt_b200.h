@@ -206,7 +206,11 @@ int dpt_debug_online_impl(int impl);
 
 /* ---------------------------------------------------------------- L1: deploy_online_vec ----
  * evals/eval_bandit.py:56-103 fused with BanditEnvVec.deploy/step (envs/bandit_env.py:98-149) and
- * the controller's set_batch_numpy_vec/act_numpy_vec, all H steps in ONE launch.
+ * the controller's set_batch_numpy_vec/act_numpy_vec: all H steps in one call and no host synchronisation.  d <= 10 (LinUCB:
+ * lin_d == 2) runs either as ONE fused kernel or as a controller kernel followed by a context-expansion kernel (chosen by
+ * controller kind and batch size; results are bit-identical), other shapes as one general kernel; every launch goes to `stream`
+ * (graph-capturable); scratch (1 B per env-step of arm indices, a few [N] / [H] float64 arrays) is stream-ordered
+ * (cudaMallocAsync / cudaFreeAsync on `stream`).
  * ctrl kinds and the reference classes they replace (ctrls/ctrl_bandit.py):
  *   0 OptPolicy :22-38 | 1 EmpMeanPolicy :57-118 (p0 = online flag) | 2 UCBPolicy :318-380 (p0 = const)
  *   3 ThompsonSamplingPolicy sample=True :122-251 (p0 = std, p1 = prior_mean, p2 = prior_var)

@@ -518,6 +518,7 @@ def test_entry_points_are_graph_capturable(dpt):
     with torch.cuda.stream(s):
         dpt.kernels.bandit_rollin(means, H, 0.3, 11, 0, out=out)       # warm-up outside capture (occupancy queries)
         dpt.kernels.gpu_bandit_step(means, acts, 0.3, 0, 5, 0, 7, out=r)
+        ol_ref = dpt.kernels.online_loop("ucb", means, H, 0.3, 5, 0, p0=1.0)   # split pipeline: 4 launches + stream-ordered scratch
     torch.cuda.current_stream().wait_stream(s)
     for v in out.values():
         v.zero_()
@@ -526,12 +527,16 @@ def test_entry_points_are_graph_capturable(dpt):
     with torch.cuda.graph(g):
         dpt.kernels.bandit_rollin(means, H, 0.3, 11, 0, out=out)
         dpt.kernels.gpu_bandit_step(means, acts, 0.3, 0, 5, 0, 7, out=r)
+        ol = dpt.kernels.online_loop("ucb", means, H, 0.3, 5, 0, p0=1.0)
     assert float(out["context_actions"].abs().sum()) == 0.0            # captured, not executed
     g.replay()
     torch.cuda.synchronize()
     for k in ref:
         assert torch.equal(out[k], ref[k]), k
     assert torch.equal(r, r_ref)
+    for k in ("context_actions", "context_rewards", "context_states", "cum_means"):
+        assert torch.equal(ol[k], ol_ref[k]), k
+    assert torch.allclose(ol["regret_sums"], ol_ref["regret_sums"], rtol=1e-12)
 
 
 def test_build_datasets_files(dpt, tmp_path):
