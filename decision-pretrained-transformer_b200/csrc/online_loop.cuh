@@ -31,6 +31,7 @@ struct OnlineParams {
   dpt_online_inject_t in;
   dpt_online_dump_t out;
   bool vec;  // float4 flush allowed
+  double* creg_carry;  // fused fast kernel: [ceil(H/128)][N] cumulative regret before every 128th step (NULL: not wanted)
 };
 
 struct WarpTile {

@@ -232,7 +232,7 @@ struct WsKernel {
     float rr[4] = {0.f, 0.f, 0.f, 0.f};
     uint32_t aw = 0u;
     uint64_t bq = 0ull;
-    if (SPLIT && sl.creg_out && (h & 127) == 0) {   // regret carry for the expander: cumulative regret before every 128th step
+    if (sl.creg_out && (h & 127) == 0) {   // regret carry (expander / regret pass): cumulative regret before every 128th step
       if (live) *sl.creg_out = fma((double)h, sl.mmax, -sl.sum_ma);   // = sum over h' < h of (max(means) - means[arm_h'])
       sl.creg_out += N;
     }
@@ -341,7 +341,7 @@ struct WsKernel {
       // ------------------------------------------------ outputs ----------------------------
       if (live) st_stream(cmp, ma);                                     // get_arm_value :151-153 -> cum_means[hh, env]
       cmp += N;
-      if (SPLIT && sl.creg_out) sl.sum_ma += (double)ma;
+      if (sl.creg_out) sl.sum_ma += (double)ma;
       rr[u] = (float)r;
       aw |= (uint32_t)a << (8 * u);
       bq |= (uint64_t)(1u << a) << (u * DMAX);                          // one-hot row of step u at bit u * DMAX of the quad's string
@@ -395,7 +395,8 @@ struct WsKernel {
       fill_range(p.ctx_ns, (size_t)env0 * H, (size_t)(env0 + nl) * H, 1.0f, lane, 32);
     }
     Tile& tl = cs.tile;
-    SplitLane sl{};   // (unused by the fused kernel)
+    SplitLane sl{};   // (the fused kernel uses the regret carries only)
+    if (p.creg_carry) sl.creg_out = p.creg_carry + env, sl.mmax = (double)mmax;
     // Warps start with first tiles of different lengths (WT/4 .. WT steps by warp index), so that the warps of an SM
     // are in different phases: while some drain a tile (store bursts) the others run their controllers
     int T = WT;
@@ -464,10 +465,10 @@ struct WsKernel {
   }
 };
 
-// threads per SM the kernel is compiled for: 1024 (64 registers) so that 100k envs (21.1 warps per SM) are ONE wave;
-// Thompson at d = 10 keeps 40 float64 statistics in registers and gets 512
+// resident CTAs per SM the kernels are compiled for: 6 (80 registers, no spills; 100k envs = 5.3 CTAs per SM are still ONE wave),
+// Thompson at d = 10 keeps 40 float64 statistics in registers and gets 4 (128 registers)
 template <int DMAX, int KIND>
-constexpr int ws_min_blocks() { return ((DMAX > 5 && KIND == K_THOMPSON) ? 512 : 1024) / (WS_NCONS * 32); }
+constexpr int ws_min_blocks() { return (DMAX > 5 && KIND == K_THOMPSON) ? 4 : 6; }
 
 template <int DMAX, int KIND, bool IO>
 __global__ void __launch_bounds__(WS_NCONS * 32, ws_min_blocks<DMAX, KIND>()) online_loop_ws_kernel(const OnlineParams p, const double* __restrict__ tab) {
@@ -704,9 +705,13 @@ __global__ void __launch_bounds__(256) ones_fill_kernel(float* __restrict__ a, f
 constexpr int RP_WARPS = 4;
 constexpr int RP_T = 16;      // steps per tile: 32 envs x 16 steps (6.5 KB of shared memory per warp, so 100k envs are one wave)
 __global__ void __launch_bounds__(RP_WARPS * 32, 6) regret_pass_kernel(const float* __restrict__ cum_means, const float* __restrict__ means, int N,
-                                                                       int H, int d, double* __restrict__ reps, int n_reps, int h_lo, int h_hi,
-                                                                       double* __restrict__ carry) {
-  DPT_TL(20 + (h_hi - 1) * 8 / H);
+                                                                       int H, int d, double* __restrict__ reps, int n_reps,
+                                                                       const double* __restrict__ creg_in) {
+  DPT_TL(20);
+  // blockIdx.y = a 128-step range; its starting cumulative regret per env is what the loop kernel left in creg_in [range][N].
+  // (Measured, 100k x 500: one warp per 32 envs over all H 0.09 ms; ranges -- 4x the warps -- the same; 4 env blocks per warp
+  // with the sums meeting in shared memory -- 4x fewer atomics -- 0.11 ms: neither parallelism nor the atomics bound it.)
+  const int h_lo = 128 * (int)blockIdx.y, h_hi = min(H, h_lo + 128);
   __shared__ float s_cm[RP_WARPS][32][RP_T + 1];
   __shared__ double s_cr[RP_WARPS][32][RP_T + 1];
   __shared__ float s_mx[RP_WARPS][32];
@@ -719,8 +724,7 @@ __global__ void __launch_bounds__(RP_WARPS * 32, 6) regret_pass_kernel(const flo
   if (live)
     for (int j = 0; j < d; ++j) mmax = fmaxf(mmax, means[(size_t)env * d + j]);
   s_mx[warp][lane] = mmax;
-  // steps [h_lo, h_hi) of the pass (split pipeline: one launch per controller chunk, the cumulative regret carried in `carry`)
-  double creg = (h_lo > 0 && live) ? carry[env] : 0.0;
+  double creg = live ? creg_in[(size_t)blockIdx.y * N + env] : 0.0;
   double* acc = reps + 3 * (size_t)(gw & (n_reps - 1)) * H;    // [n_reps][H][3]: sum reg, sum reg^2, sum creg^2
   const int t = lane & (RP_T - 1), half = lane >> 4;           // sums over envs: lane = (half of the envs, step)
   const float* src = cum_means + env;
@@ -736,7 +740,7 @@ __global__ void __launch_bounds__(RP_WARPS * 32, 6) regret_pass_kernel(const flo
       nx[k] = (live && h0 + RP_T + k < h_hi) ? __ldcs(src + (size_t)(h0 + RP_T + k) * N) : 0.f;
 #pragma unroll
     for (int k = 0; k < RP_T; ++k) {
-      if (k < T) creg += (double)mmax - (double)cm[k];   // (a carried prefix must not see the padding of a partial tile)
+      if (k < T) creg += (double)mmax - (double)cm[k];   // (the prefix must not see the padding of a partial tile)
       s_cm[warp][lane][k] = cm[k];
       s_cr[warp][lane][k] = creg;
     }
@@ -755,7 +759,6 @@ __global__ void __launch_bounds__(RP_WARPS * 32, 6) regret_pass_kernel(const flo
     }
     __syncwarp();
   }
-  if (h_hi < H && live) carry[env] = creg;
 }
 
 // regret[h] += (S1, S2, C1, C2)[h]: S1, S2, C2 folded over the replicas in a fixed order; the sum over envs of the cumulative
@@ -923,7 +926,7 @@ static cudaError_t launch_split(const OnlineParams& p, double* tab, double* regr
   const bool reg_fused = mat && regret_out && expand_is_fast(p);   // regret sums in the expander; otherwise a pass over cum_means
   const int HQ = (H + 3) / 4, HC = (H + 127) / 128;
   const size_t b_arms = mat ? (((size_t)HQ * N * 4 + 255) & ~size_t(255)) : 0;
-  const size_t b_creg = reg_fused ? (size_t)(HC + 1) * N * 8 : 0;
+  const size_t b_creg = regret_out ? (size_t)(HC + 1) * N * 8 : 0;   // regret carries: for the expander, else for the regret pass
   unsigned char* scratch = nullptr;
   if (b_arms + b_creg) {
     keep_pool_memory();
@@ -931,7 +934,7 @@ static cudaError_t launch_split(const OnlineParams& p, double* tab, double* regr
   }
   SplitArgs sa{};
   sa.arms4 = mat ? reinterpret_cast<uint32_t*>(scratch) : nullptr;
-  sa.creg = reg_fused ? reinterpret_cast<double*>(scratch + b_arms) : nullptr;
+  sa.creg = regret_out ? reinterpret_cast<double*>(scratch + b_arms) : nullptr;
   if (KIND == K_EMP || KIND == K_UCB || KIND == K_THOMPSON)
     online_ws_table_kernel<<<(H + 1 + 255) / 256, 256, 0, st>>>(KIND, p.p0, p.p2, H, tab);
   const int warps_total = (N + 31) / 32;
@@ -939,11 +942,11 @@ static cudaError_t launch_split(const OnlineParams& p, double* tab, double* regr
   sa.fill = mat && H % 4 == 0 && aligned16(p.ctx_s) && aligned16(p.ctx_ns);
   kern<<<ctrl_grid, WS_NCONS * 32, smem, st>>>(p, tab, sa);
   if (mat && !sa.fill) ones_fill_kernel<<<fill_grid((size_t)N * H, 8), 256, 0, st>>>(p.ctx_s, p.ctx_ns, (size_t)N * H);
-  if (mat) launch_expand(p, sa.arms4, sa.creg, st);
+  if (mat) launch_expand(p, sa.arms4, reg_fused ? sa.creg : nullptr, st);
   if (regret_out) {
     if (!reg_fused)
-      regret_pass_kernel<<<(warps_total + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, st>>>(p.cum_means, p.means, N, H, p.d, p.regret, p.regret_reps, 0, H,
-                                                                                          nullptr);
+      regret_pass_kernel<<<dim3((warps_total + RP_WARPS - 1) / RP_WARPS, HC), RP_WARPS * 32, 0, st>>>(p.cum_means, p.means, N, H, p.d, p.regret,
+                                                                                                    p.regret_reps, sa.creg);
     regret_finish_kernel<<<1, 1024, 0, st>>>(p.regret, p.regret_reps, H, regret_out);
   }
   const cudaError_t err = cudaGetLastError();
@@ -966,13 +969,20 @@ static cudaError_t launch_split_kind(int kind, const OnlineParams& p, double* ta
 cudaError_t launch_online_ws(int kind, const OnlineParams& p, double* tab, double* regret_out, cudaStream_t st, bool fused) {
   if (!online_ws_supported(kind, p)) return cudaErrorNotSupported;
   if (!fused) return p.d <= 5 ? launch_split_kind<5>(kind, p, tab, regret_out, st) : launch_split_kind<10>(kind, p, tab, regret_out, st);
-  cudaError_t e = p.d <= 5 ? launch_ws_kind<5>(kind, p, tab, st) : launch_ws_kind<10>(kind, p, tab, st);
+  OnlineParams q = p;
+  const int HC = (p.H + 127) / 128;
+  if (regret_out) {   // regret carries [HC][N] for the ranged regret pass
+    keep_pool_memory();
+    SPLIT_TRY(cudaMallocAsync(reinterpret_cast<void**>(&q.creg_carry), (size_t)HC * p.N * sizeof(double), st));
+  }
+  cudaError_t e = p.d <= 5 ? launch_ws_kind<5>(kind, q, tab, st) : launch_ws_kind<10>(kind, q, tab, st);
   if (e == cudaSuccess && regret_out) {   // [H,4] regret sums from cum_means: p.regret = zeroed [regret_reps][H][3] scratch
     const int ctas = ((p.N + 31) / 32 + RP_WARPS - 1) / RP_WARPS;   // one atomic set per warp (32 envs) and 16-step tile
-    regret_pass_kernel<<<ctas, RP_WARPS * 32, 0, st>>>(p.cum_means, p.means, p.N, p.H, p.d, p.regret, p.regret_reps, 0, p.H, nullptr);
+    regret_pass_kernel<<<dim3(ctas, HC), RP_WARPS * 32, 0, st>>>(p.cum_means, p.means, p.N, p.H, p.d, p.regret, p.regret_reps, q.creg_carry);
     regret_finish_kernel<<<1, 1024, 0, st>>>(p.regret, p.regret_reps, p.H, regret_out);
     e = cudaGetLastError();
   }
+  if (q.creg_carry) SPLIT_TRY(cudaFreeAsync(q.creg_carry, st));
   return e;
 }
 
