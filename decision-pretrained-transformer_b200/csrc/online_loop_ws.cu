@@ -111,6 +111,31 @@ __device__ __forceinline__ double div_by_count(double a, int n, double rc) {
   return q;
 }
 
+// LinUCB (lin_d = 2): per-arm row of constants in shared memory -- x0, x1, x0^2, 2 x0 x1, x1^2, pad
+constexpr int LIN_AW = 6;
+__device__ __forceinline__ void lin_arm_row(double* row, double x0, double x1) {
+  row[0] = x0, row[1] = x1, row[2] = x0 * x0, row[3] = 2.0 * (x0 * x1), row[4] = x1 * x1, row[5] = 0.0;
+}
+
+// sqrt of a positive, normal float64 to ~1 ulp without the IEEE routine's special-case branches: hardware reciprocal square
+// root seed (20 bits) + two coupled Newton steps (Goldschmidt); 0 -> 0
+__device__ __forceinline__ double sqrt_nr(double q) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q));
+  double g = q * y, h = 0.5 * y;
+  double r = fma(-h, g, 0.5);
+  g = fma(g, r, g), h = fma(h, r, h);
+  r = fma(-h, g, 0.5);
+  g = fma(g, r, g);
+  return q > 0.0 ? g : 0.0;
+}
+
+__device__ __forceinline__ void lin_arm_load(uint32_t sa, double* A) {   // the row's first five entries
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(A[0]), "=d"(A[1]) : "r"(sa));
+  asm("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(A[2]), "=d"(A[3]) : "r"(sa));
+  asm("ld.shared.f64 %0, [%1+32];" : "=d"(A[4]) : "r"(sa));
+}
+
 // the env step's reward in float64, as the reference forms it; shared by the controller (statistics) and the expander (context rows)
 __device__ __forceinline__ double reward_f64(float ma, float z, double var, int rtype) {
   return rtype == DPT_REWARD_GAUSSIAN ? (double)ma + (0.0 + var * (double)z)   // envs/bandit_env.py:59
@@ -299,12 +324,20 @@ struct WsKernel {
           const double idet = 1.0 / (S.s00 * S.s11 - S.s01 * S.s01);
           const double i00 = S.s11 * idet, i01 = -S.s01 * idet, i11 = S.s00 * idet;
           const double t0 = i00 * S.b0 + i01 * S.b1, t1 = i01 * S.b0 + i11 * S.b1;   // theta = cov_inv @ A^T r  :513
+          // per arm (s_arms row: x0, x1, x0^2, 2 x0 x1, x1^2): arm @ cov_inv @ arm = i00 x0^2 + i01 (2 x0 x1) + i11 x1^2 -- 3 float64
+          // operations on the arm's constant products instead of 6 on (x0, x1); like the reference's LAPACK inverse / BLAS
+          // products this is float64-accurate, not bit-identical, arithmetic: the argmax is what is pinned (goldens)
           double best = -INFINITY;
-          for (int j = 0; j < d; ++j) {
-            const double x0 = s_arms[2 * j], x1 = s_arms[2 * j + 1];
-            const double qf = x0 * (i00 * x0 + i01 * x1) + x1 * (i01 * x0 + i11 * x1);
-            const double v = (t0 * x0 + t1 * x1) + p.p0 * sqrt(qf);                 // :519
-            if (v > best) best = v, a = j;                                           // strict >: first maximum :520
+          const uint32_t arms_sa = (uint32_t)__cvta_generic_to_shared(s_arms);   // (one conversion; per-access generic addressing cost 3 uniform instructions per load)
+#pragma unroll
+          for (int j = 0; j < DMAX; ++j) {
+            if (j < d) {
+              double A[LIN_AW];
+              lin_arm_load(arms_sa + 8 * LIN_AW * j, A);
+              const double qf = fma(i00, A[2], fma(i01, A[3], i11 * A[4]));
+              const double v = fma(p.p0, sqrt_nr(qf), fma(t0, A[0], t1 * A[1]));       // :519
+              if (v > best) best = v, a = j;                                           // strict >: first maximum :520
+            }
           }
         }
       }
@@ -334,9 +367,9 @@ struct WsKernel {
           }
         }
       } else if (KIND == K_LINUCB2) {
-        const double x0 = s_arms[2 * a], x1 = s_arms[2 * a + 1];
-        S.b0 += x0 * r, S.b1 += x1 * r;
-        S.s00 += x0 * x0, S.s01 += x0 * x1, S.s11 += x1 * x1;
+        const double* A = s_arms + LIN_AW * a;
+        S.b0 += A[0] * r, S.b1 += A[1] * r;
+        S.s00 += A[2], S.s01 += 0.5 * A[3], S.s11 += A[4];   // (0.5 * (2 x0 x1) is exact)
       }
       // ------------------------------------------------ outputs ----------------------------
       if (live) st_stream(cmp, ma);                                     // get_arm_value :151-153 -> cum_means[hh, env]
@@ -477,11 +510,11 @@ __global__ void __launch_bounds__(WS_NCONS * 32, ws_min_blocks<DMAX, KIND>()) on
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float4 s_nib[16];   // 4-bit pattern -> four 0/1 floats (one-hot flush)
   Cons* cons = reinterpret_cast<Cons*>(smem_raw);
-  double* s_arms = reinterpret_cast<double*>(smem_raw + sizeof(Cons) * WS_NCONS);   // [d][2] (LinUCB)
+  double* s_arms = reinterpret_cast<double*>(smem_raw + sizeof(Cons) * WS_NCONS);   // [d][LIN_AW] (LinUCB)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < 16) s_nib[tid] = make_float4((tid & 1) ? 1.f : 0.f, (tid & 2) ? 1.f : 0.f, (tid & 4) ? 1.f : 0.f, (tid & 8) ? 1.f : 0.f);
   if (KIND == K_LINUCB2)
-    for (int i = tid; i < p.d * 2; i += blockDim.x) s_arms[i] = p.arms[i];
+    for (int j = tid; j < p.d; j += blockDim.x) lin_arm_row(s_arms + LIN_AW * j, p.arms[2 * j], p.arms[2 * j + 1]);
   __syncthreads();
   const int env = (blockIdx.x * WS_NCONS + warp) * 32 + lane;
   if (env - lane < p.N)            // warp-uniform
@@ -521,10 +554,10 @@ __global__ void __launch_bounds__(WS_NCONS * 32, DPT_CTRL_MINB) online_ctrl_kern
   DPT_TL(1);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cons* cons = reinterpret_cast<Cons*>(smem_raw);
-  double* s_arms = reinterpret_cast<double*>(smem_raw + sizeof(Cons) * WS_NCONS);   // [d][2] (LinUCB)
+  double* s_arms = reinterpret_cast<double*>(smem_raw + sizeof(Cons) * WS_NCONS);   // [d][LIN_AW] (LinUCB)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (KIND == K_LINUCB2) {
-    for (int i = tid; i < p.d * 2; i += blockDim.x) s_arms[i] = p.arms[i];
+    for (int j = tid; j < p.d; j += blockDim.x) lin_arm_row(s_arms + LIN_AW * j, p.arms[2 * j], p.arms[2 * j + 1]);
     __syncthreads();
   }
   const int env = (blockIdx.x * WS_NCONS + warp) * 32 + lane;
@@ -847,7 +880,7 @@ static cudaError_t launch_ws(const OnlineParams& p, double* tab, cudaStream_t st
   const bool io = p.in.reward_z || p.in.ctrl_z || p.in.first_arm || p.out.reward_z || p.out.ctrl_z || p.out.first_arm;
   auto kern = io ? online_loop_ws_kernel<DMAX, KIND, true> : online_loop_ws_kernel<DMAX, KIND, false>;
   using Cons = typename WsKernel<DMAX, KIND, false>::Cons;
-  const size_t smem = sizeof(Cons) * WS_NCONS + (KIND == K_LINUCB2 ? sizeof(double) * 2 * p.d : 0);
+  const size_t smem = sizeof(Cons) * WS_NCONS + (KIND == K_LINUCB2 ? sizeof(double) * LIN_AW * p.d : 0);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -920,7 +953,7 @@ static cudaError_t launch_split(const OnlineParams& p, double* tab, double* regr
   const bool io = p.in.reward_z || p.in.ctrl_z || p.in.first_arm || p.out.reward_z || p.out.ctrl_z || p.out.first_arm;
   auto kern = io ? online_ctrl_kernel<DMAX, KIND, true> : online_ctrl_kernel<DMAX, KIND, false>;
   using Cons = typename WsKernel<DMAX, KIND, false, true>::Cons;
-  const size_t smem = sizeof(Cons) * WS_NCONS + (KIND == K_LINUCB2 ? sizeof(double) * 2 * p.d : 0);
+  const size_t smem = sizeof(Cons) * WS_NCONS + (KIND == K_LINUCB2 ? sizeof(double) * LIN_AW * p.d : 0);
   const int N = p.N, H = p.H;
   const bool mat = p.ctx_a != nullptr;
   const bool reg_fused = mat && regret_out && expand_is_fast(p);   // regret sums in the expander; otherwise a pass over cum_means

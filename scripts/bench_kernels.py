@@ -70,7 +70,7 @@ def main():
             m, mn = timeit(lambda: kernels.darkroom_rollin(goals, 10, H, "expert", 3, 0, None, 1), R)
             report("darkroom_rollin expert N=%d H=%d dim=10" % (N, H), N * H, 40, m, mn)
     if want("online"):
-        arms = np.random.RandomState(1234).normal(size=(10, 2)) / np.sqrt(2)
+        arms = torch.tensor(np.random.RandomState(1234).normal(size=(10, 2)) / np.sqrt(2), dtype=torch.float64, device="cuda")   # resident: no H2D copy per pass
         for kind, N, H, d, par in [("opt", 100000, 500, 5, {}), ("emp", 100000, 500, 5, dict(p0=1.0)), ("ucb", 100000, 500, 5, dict(p0=1.0)),
                                    ("thompson", 100000, 500, 5, dict(p0=0.3, p1=0.5, p2=1 / 12.0)),
                                    ("thompson", 100000, 200, 10, dict(p0=0.3, p1=0.0, p2=1.0)),

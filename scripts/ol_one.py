@@ -16,7 +16,7 @@ if __name__ == "__main__":
     passes = int(sys.argv[5]) if len(sys.argv) > 5 else 3
     par = dict(PAR[kind])
     if kind == "linucb":
-        par["arms"] = np.random.RandomState(1234).normal(size=(d, 2)) / np.sqrt(2)
+        par["arms"] = torch.tensor(np.random.RandomState(1234).normal(size=(d, 2)) / np.sqrt(2), dtype=torch.float64, device="cuda")
     means, _, _ = kernels.bandit_sample_means(N, d, 0, 0)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(passes):

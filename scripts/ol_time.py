@@ -15,7 +15,7 @@ if __name__ == "__main__":
     passes = int(sys.argv[5]) if len(sys.argv) > 5 else 10
     par = dict(PAR[kind])
     if kind == "linucb":
-        par["arms"] = np.random.RandomState(1234).normal(size=(d, 2)) / np.sqrt(2)
+        par["arms"] = torch.tensor(np.random.RandomState(1234).normal(size=(d, 2)) / np.sqrt(2), dtype=torch.float64, device="cuda")
     means, _, _ = kernels.bandit_sample_means(N, d, 0, 0)
     for _ in range(3):
         kernels.online_loop(kind, means, H, 0.3, 2, 0, **par)

@@ -21,7 +21,7 @@ if __name__ == "__main__":
     kind, N, H, d = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     par = dict(PAR[kind])
     if kind == "linucb":
-        par["arms"] = np.random.RandomState(1234).normal(size=(d, 2)) / np.sqrt(2)
+        par["arms"] = torch.tensor(np.random.RandomState(1234).normal(size=(d, 2)) / np.sqrt(2), dtype=torch.float64, device="cuda")
     means, _, _ = kernels.bandit_sample_means(N, d, 0, 0)
     buf = (ctypes.c_ulonglong * 128)()
     for i in range(4):
