@@ -167,7 +167,11 @@ struct WsKernel {
   using Tile = WsTile<DMAX>;
   static constexpr int BWQ = Tile::BWQ, WT = Tile::WT, WQ = Tile::WQ;
   static __device__ __forceinline__ int swz(int e) { return swz_t<WQ>(e); }
-  static constexpr int NB2 = (2 * DMAX + 3) / 4;   // Philox blocks of control normals per step pair (Thompson)
+  // Thompson's control normals are drawn for ZSPAN steps at a time: a whole step quad at d <= 5 (20 normals = exactly 5 Philox
+  // blocks; per step pair it was 3 blocks for 10 normals, one sixth of the words unused), a step pair at d <= 10 (5 blocks, 40
+  // live floats per quad would not fit the registers).  Block index on STREAM_CTRL: (step / ZSPAN) * NBZ + block.
+  static constexpr int ZSPAN = DMAX <= 5 ? 4 : 2;
+  static constexpr int NBZ = (ZSPAN * DMAX + 3) / 4;
 
   // ------------------------------------------------------------------------------- drain one staging tile
   static __device__ __forceinline__ void flush(const OnlineParams& p, const Tile& tl, const float4* s_nib, int env0, int nl, int h0, int T,
@@ -271,7 +275,7 @@ struct WsKernel {
       }
       sl.fill_p += 32;
     }
-    float zc[KIND == K_THOMPSON ? 2 * DMAX : 1];                  // control normals of the current step pair
+    float zc[KIND == K_THOMPSON ? ZSPAN * DMAX : 1];              // control normals of the current ZSPAN steps
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (!FULL && u >= nsteps) break;
@@ -287,28 +291,28 @@ struct WsKernel {
           if (S.st0[j] > best) best = S.st0[j], a = j;                  // np.argmax: first maximum  :106 | :369-370
         if ((KIND == K_UCB || p.p0 != 0.0) && S.untried) a = __ffs(S.untried) - 1;   // np.argmin(counts) when min == 0  :110-113 | :373-375
       } else if (KIND == K_THOMPSON) {
-        if ((u & 1) == 0) {               // control normals of steps hh, hh + 1: NB2 Philox blocks per step pair
+        if ((u % ZSPAN) == 0) {           // control normals of steps hh .. hh + ZSPAN - 1: NBZ Philox blocks
           if (IO && p.in.ctrl_z) {
 #pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2)
+            for (int s2 = 0; s2 < ZSPAN; ++s2)
 #pragma unroll
               for (int j = 0; j < DMAX; ++j)
                 zc[s2 * DMAX + j] = (live && j < d && hh + s2 < H) ? p.in.ctrl_z[((size_t)(hh + s2) * N + env) * d + j] : 0.f;
           } else {
 #pragma unroll
-            for (int bk = 0; bk < NB2; ++bk) {
+            for (int bk = 0; bk < NBZ; ++bk) {
               float z4n[4];
-              normals4(philox_words(p.key, gid, (uint32_t)((hh >> 1) * NB2 + bk), STREAM_CTRL), z4n);
+              normals4(philox_words(p.key, gid, (uint32_t)((hh / ZSPAN) * NBZ + bk), STREAM_CTRL), z4n);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                if (4 * bk + k < 2 * DMAX) zc[4 * bk + k] = z4n[k];
+                if (4 * bk + k < ZSPAN * DMAX) zc[4 * bk + k] = z4n[k];
             }
           }
         }
         double best = -INFINITY;
 #pragma unroll
         for (int j = 0; j < DMAX; ++j) {
-          const float zj = zc[(u & 1) * DMAX + j];
+          const float zj = zc[(u % ZSPAN) * DMAX + j];
           if (IO && p.out.ctrl_z && live && j < d) p.out.ctrl_z[((size_t)hh * N + env) * d + j] = zj;
           const double v = fma(S.st1[j], (double)zj, S.st0[j]);         // np.random.normal(means, sqrt(variances)) :234
           if (v > best) best = v, a = j;                                // (padding arms: mean -inf, std 0)
