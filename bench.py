@@ -242,6 +242,27 @@ def other_workloads(kernels, torch):
         ms = t(lambda: kernels.online_loop(kind, means5, 500, 0.3, 1, 0, **kw))
         out["config4_%s_online_100k_envs_H500_d5" % kind] = {"ms": ms, "env_steps_per_s": 5e7 / (ms * 1e-3), "trajs_per_s": 1e5 / (ms * 1e-3),
                                                              "frac_of_hbm_peak": 5e7 * 36 / (ms * 1e-3) / 1e9 / peak}
+    # the no-grad half of an explorer / exploiter episode (train_explorer_exploiter.py:110-166), 2 000 envs x K = 100
+    # steps, two GPT-2 (embd 32, 4 layers) models: ONE fused launch against the step-by-step form (2 decode launches + torch ops per step)
+    try:
+        from dpt_b200.envs.gpu_bandit_env import GPUBanditEnv
+        from dpt_b200.models.net import Transformer
+        torch.manual_seed(1)
+        cfg = {"horizon": 100, "state_dim": 1, "action_dim": 5, "n_layer": 4, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True}
+        ex, xp = Transformer(cfg), Transformer(cfg)
+        genv = GPUBanditEnv(5, 2000, 100, var=0.3, seed=3)
+        for fused, name in ((True, "fused"), (False, "step_by_step")):
+            genv.rollout_explorer_exploiter(ex, xp, fused=fused)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                genv.rollout_explorer_exploiter(ex, xp, fused=fused)
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) * 1e3 / 3
+            out["explorer_exploiter_rollout_2000_envs_K100_%s" % name] = {"ms": ms, "env_steps_per_s": 2e5 / (ms * 1e-3),
+                                                                          "timing": "wall clock around GPUBanditEnv.rollout_explorer_exploiter"}
+    except Exception as e:   # noqa: BLE001
+        out["explorer_exploiter_rollout"] = {"error": repr(e)}
     # darkroom online evaluation (evals/eval_darkroom.py:20-84), the reference's shape: 100 envs x 40 episodes
     # of 100 steps on a 10 x 10 grid, context H = 100, GPT-2 embd 32 / 4 layers: per episode ONE dense forward over the 100
     # query states of every env (fp32 CUDA-core kernel, or tcgen05 with precision 1) + ONE rollout launch

@@ -60,6 +60,15 @@ class Gpt2OnlineDump(Structure):
     _fields_ = [("reward_z", c_void_p), ("ctrl_u", c_void_p), ("logits", c_void_p)]
 
 
+class ExploreInject(Structure):
+    _fields_ = [("ctrl_u", c_void_p), ("random_arm", c_void_p), ("reward_z", c_void_p)]
+
+
+class ExploreDump(Structure):
+    _fields_ = [("ctrl_u", c_void_p), ("random_arm", c_void_p), ("reward_z", c_void_p), ("logits_explorer", c_void_p),
+                ("logits_exploiter", c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol include/dpt_b200.h declares
 PROTOTYPES = {
     "dpt_version": (c_int, []),
@@ -111,6 +120,9 @@ PROTOTYPES = {
     "dpt_gpt2_online_loop": (c_int, [c_void_p, c_void_p, c_double, c_int, c_int, c_uint64, c_uint64, c_int, c_int, c_int,
                                      c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      POINTER(Gpt2OnlineInject), POINTER(Gpt2OnlineDump), c_void_p]),
+    "dpt_gpt2_explore_exploit_rollout": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_int, c_uint64, c_uint64, c_int, c_int,
+                                                 c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                 POINTER(ExploreInject), POINTER(ExploreDump), c_void_p]),
 }
 
 _lib = None

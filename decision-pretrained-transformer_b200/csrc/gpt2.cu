@@ -912,6 +912,123 @@ __global__ void __launch_bounds__(WS ? GW_THREADS : (TMA ? TMA_WARPS * 32 : G_TH
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused explorer / exploiter rollout (the no-grad half of an episode of train_explorer_exploiter.py:110-166): ONE launch for all
+// K steps.  One warp per env, two models with their own K/V caches.  Per step t both models score the context so far (token t =
+// query token at t = 0, else transition t - 1), the explorer's sampled arm is what gets RECORDED in the context (:131-136, :155)
+// while the env is stepped with a uniformly random arm (:137-152), and the advantage of step t - 1 is the change of the
+// exploiter's cross-entropy against the optimal arm (:158-164).  The exploiter's own sample (:141-146) is never used by the
+// reference and is not drawn.  Draws: Philox block (step t, STREAM_CTRL): words x, y -> the 53-bit uniform of the explorer's
+// categorical draw (same float64 cdf rule as the online loop), word z -> the random arm (z * du) >> 32; reward noise as in the
+// online loop (one block per step pair on STREAM_ENV_REWARD).
+// ---------------------------------------------------------------------------------------------
+struct ExploreParams {
+  Gpt2Dev me, mx;   // explorer, exploiter
+  const float* means;
+  double var;
+  int rtype;
+  Key key;
+  uint64_t env_id0;
+  int N, K, Tpad;
+  void *kv_e, *kv_x;
+  float *ctx_s, *ctx_a, *ctx_ns, *ctx_r;
+  float* adv;       // [N, K - 1]
+  dpt_explore_inject_t in;
+  dpt_explore_dump_t out;
+};
+
+__global__ void __launch_bounds__(G_THREADS, DPT_GPT2_MINB_F32) gpt2_explore_exploit_kernel(const ExploreParams p) {
+  extern __shared__ __align__(128) float g_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int env = blockIdx.x * G_WARPS + warp;
+  if (env >= p.N) return;
+  const Gpt2Dev& me = p.me;
+  const Gpt2Dev& mx = p.mx;
+  const WarpScratch ws = warp_scratch(g_smem, warp, p.Tpad);
+  const size_t kv_stride_e = (size_t)me.L * 2 * G_E * p.Tpad * 4, kv_stride_x = (size_t)mx.L * 2 * G_E * p.Tpad * 4;
+  char* kve = reinterpret_cast<char*>(p.kv_e) + (size_t)env * kv_stride_e;
+  char* kvx = reinterpret_cast<char*>(p.kv_x) + (size_t)env * kv_stride_x;
+  const int du = me.du, K = p.K, N = p.N;
+  const uint64_t gid = p.env_id0 + (uint64_t)env;
+  const float mean_l = lane < du ? p.means[(size_t)env * du + lane] : -INFINITY;
+  const float mmax = warp_max(mean_l);
+  const int target = __ffs(__ballot_sync(0xffffffffu, lane < du && mean_l == mmax)) - 1;   // opt_a_index: first maximum
+  for (int h = lane; h < K; h += 32) {
+    p.ctx_s[(size_t)env * K + h] = 1.0f;
+    p.ctx_ns[(size_t)env * K + h] = 1.0f;
+  }
+  // constant parts of a token, per model: bias + state (== 1) column (+ next_state column for transition tokens)
+  const float ee_state = __ldg(me.embed_wT + lane), ee_next = __ldg(me.embed_wT + (1 + du) * G_E + lane);
+  const float ee_rew = __ldg(me.embed_wT + (2 + du) * G_E + lane), ee_bias = __ldg(me.embed_b + lane);
+  const float ex_state = __ldg(mx.embed_wT + lane), ex_next = __ldg(mx.embed_wT + (1 + du) * G_E + lane);
+  const float ex_rew = __ldg(mx.embed_wT + (2 + du) * G_E + lane), ex_bias = __ldg(mx.embed_b + lane);
+  int a_prev = 0;
+  float r_prev = 0.f, z_next = 0.f, loss_prev = 0.f;
+  for (int h = 0; h < K; ++h) {
+    // ---- explorer: logits at position h, sampled arm (recorded) -----------------------------
+    float x = ee_bias + ee_state + __ldg(me.wpe + (size_t)h * G_E + lane);
+    if (h > 0) x += __ldg(me.embed_wT + (1 + a_prev) * G_E + lane) + ee_next + ee_rew * r_prev;
+    x = token_forward<false, false>(me, x, h, kve, p.Tpad, ws.sx, ws.sh, ws.ssc, lane);
+    const float lge = head_logits(me, x, ws.sx, lane);
+    if (p.out.logits_explorer && lane < du) p.out.logits_explorer[((size_t)h * N + env) * du + lane] = lge;
+    const uint4 w = philox_words(p.key, gid, (uint32_t)h, STREAM_CTRL);
+    int a;
+    {
+      const float lm = warp_max(lane < du ? lge : -INFINITY);
+      const double pe = lane < du ? exp((double)lge - (double)lm) : 0.0;
+      double tot = 0.0;
+      for (int j = 0; j < du; ++j) tot = __dadd_rn(tot, __shfl_sync(0xffffffffu, pe, j));
+      const double pj = __ddiv_rn(pe, tot);
+      double acc = 0.0, cdf = 0.0;
+      for (int j = 0; j < du; ++j) {
+        const double v = __shfl_sync(0xffffffffu, pj, j);
+        acc = (j == 0) ? v : __dadd_rn(acc, v);
+        if (j == lane) cdf = acc;
+      }
+      const double last = __shfl_sync(0xffffffffu, cdf, du - 1);
+      cdf = __ddiv_rn(cdf, last);
+      const double u = p.in.ctrl_u ? p.in.ctrl_u[(size_t)h * N + env]
+                                   : ((double)(w.x >> 5) * 67108864.0 + (double)(w.y >> 6)) * (1.0 / 9007199254740992.0);
+      if (p.out.ctrl_u && lane == 0) p.out.ctrl_u[(size_t)h * N + env] = u;
+      a = __popc(__ballot_sync(0xffffffffu, lane < du - 1 && cdf <= u));
+    }
+    // ---- exploiter: logits at position h, cross-entropy against the optimal arm --------------
+    float y = ex_bias + ex_state + __ldg(mx.wpe + (size_t)h * G_E + lane);
+    if (h > 0) y += __ldg(mx.embed_wT + (1 + a_prev) * G_E + lane) + ex_next + ex_rew * r_prev;
+    y = token_forward<false, false>(mx, y, h, kvx, p.Tpad, ws.sx, ws.sh, ws.ssc, lane);
+    const float lgx = head_logits(mx, y, ws.sx, lane);
+    if (p.out.logits_exploiter && lane < du) p.out.logits_exploiter[((size_t)h * N + env) * du + lane] = lgx;
+    const float lmx = warp_max(lane < du ? lgx : -INFINITY);
+    const float loss = lmx + logf(warp_sum(lane < du ? expf(lgx - lmx) : 0.f)) - __shfl_sync(0xffffffffu, lgx, target);
+    if (h > 0 && lane == 0) p.adv[(size_t)env * (K - 1) + (h - 1)] = loss - loss_prev;   // :160-164
+    loss_prev = loss;
+    // ---- env step with a uniformly random arm -----------------------------------------------
+    const int ar = p.in.random_arm ? p.in.random_arm[(size_t)h * N + env] : (int)bounded(w.z, (uint32_t)du);
+    float z;
+    if (p.in.reward_z) {
+      z = p.in.reward_z[(size_t)h * N + env];
+    } else if ((h & 1) == 0) {
+      const uint4 wr = philox_words(p.key, gid, (uint32_t)(h >> 1), STREAM_ENV_REWARD);
+      if (p.rtype == DPT_REWARD_GAUSSIAN)
+        box_muller(wr.z, wr.w, z, z_next);
+      else
+        z = u24(wr.z), z_next = u24(wr.w);
+    } else {
+      z = z_next;
+    }
+    const float ma = __shfl_sync(0xffffffffu, mean_l, ar);
+    const float r = p.rtype == DPT_REWARD_GAUSSIAN ? (float)((double)ma + (0.0 + p.var * (double)z)) : (z < ma ? 1.f : 0.f);
+    if (lane == 0) {
+      if (p.out.reward_z) p.out.reward_z[(size_t)h * N + env] = z;
+      if (p.out.random_arm) p.out.random_arm[(size_t)h * N + env] = ar;
+      p.ctx_r[(size_t)env * K + h] = r;
+    }
+    if (lane < du) p.ctx_a[((size_t)env * K + h) * du + lane] = (lane == a) ? 1.f : 0.f;   // the EXPLORER's arm is recorded (:155)
+    a_prev = a;
+    r_prev = r;
+  }
+}
+
 __global__ void transpose_kernel(const float* src, float* dst, int rows, int cols) {  // dst[c][r] = src[r][c]
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < rows * cols) dst[(i % cols) * rows + i / cols] = src[i];
@@ -1180,6 +1297,42 @@ extern "C" int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, double va
     gpt2_online_kernel<true, false><<<(N + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
   else
     gpt2_online_kernel<false, false><<<(N + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
+  DPT_LAUNCH_CHECK();
+  return DPT_OK;
+}
+
+extern "C" int dpt_gpt2_explore_exploit_rollout(dpt_gpt2_t* explorer, dpt_gpt2_t* exploiter, const float* means, double var, int reward_type,
+                                                uint64_t seed, uint64_t env_id0, int N, int K, void* kv_explorer, void* kv_exploiter,
+                                                uint64_t kv_bytes_each, float* ctx_states, float* ctx_actions, float* ctx_next_states,
+                                                float* ctx_rewards, float* advantages, const dpt_explore_inject_t* inject,
+                                                const dpt_explore_dump_t* dump, void* stream) {
+  DPT_CHECK_ARG(explorer && exploiter, "dpt_gpt2_explore_exploit_rollout: null model");
+  DPT_CHECK_ARG(reward_type == DPT_REWARD_GAUSSIAN || reward_type == DPT_REWARD_BERNOULLI,
+                "dpt_gpt2_explore_exploit_rollout: unknown reward_type %d (0 uniform/gaussian, 1 bernoulli)", reward_type);
+  DPT_CHECK_ARG(explorer->dev.dx == 1 && exploiter->dev.dx == 1 && explorer->dev.du == exploiter->dev.du,
+                "dpt_gpt2_explore_exploit_rollout: both models need state_dim == 1 and the same action_dim");
+  DPT_CHECK_ARG(N >= 0 && K >= 0, "dpt_gpt2_explore_exploit_rollout: N=%d K=%d", N, K);
+  DPT_CHECK_ARG(K <= explorer->dev.n_pos && K <= exploiter->dev.n_pos, "dpt_gpt2_explore_exploit_rollout: K=%d exceeds n_positions", K);
+  if (N == 0 || K == 0) return DPT_OK;
+  const uint64_t need = std::max(dpt_gpt2_online_kv_bytes(explorer, N, K, 0), dpt_gpt2_online_kv_bytes(exploiter, N, K, 0));
+  DPT_CHECK_ARG(means && kv_explorer && kv_exploiter && kv_explorer != kv_exploiter && kv_bytes_each >= need,
+                "dpt_gpt2_explore_exploit_rollout: null means, or K/V caches missing / shared / too small");
+  DPT_CHECK_ARG(ctx_states && ctx_actions && ctx_next_states && ctx_rewards && (advantages || K < 2),
+                "dpt_gpt2_explore_exploit_rollout: null output pointer");
+  ExploreParams p{};
+  p.me = explorer->dev, p.mx = exploiter->dev;
+  p.means = means, p.var = var, p.rtype = reward_type;
+  p.key = Key{(uint32_t)seed, (uint32_t)(seed >> 32)};
+  p.env_id0 = env_id0;
+  p.N = N, p.K = K, p.Tpad = tpad_for(K, 0);
+  p.kv_e = kv_explorer, p.kv_x = kv_exploiter;
+  p.ctx_s = ctx_states, p.ctx_a = ctx_actions, p.ctx_ns = ctx_next_states, p.ctx_r = ctx_rewards, p.adv = advantages;
+  if (inject) p.in = *inject;
+  if (dump) p.out = *dump;
+  const size_t smem = (size_t)G_WARPS * (G_E + G_FF + p.Tpad) * sizeof(float);
+  int rc = launch_smem((const void*)gpt2_explore_exploit_kernel, smem);
+  if (rc != DPT_OK) return rc;
+  gpt2_explore_exploit_kernel<<<(N + G_WARPS - 1) / G_WARPS, G_THREADS, smem, (cudaStream_t)stream>>>(p);
   DPT_LAUNCH_CHECK();
   return DPT_OK;
 }

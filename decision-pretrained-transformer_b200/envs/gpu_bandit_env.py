@@ -103,13 +103,20 @@ class GPUBanditEnv(BaseEnv):
                 "logits": out["noise"]["logits"], "target": self.opt_a_index}
 
     @torch.no_grad()
-    def rollout_explorer_exploiter(self, explorer, exploiter, K=None):
+    def rollout_explorer_exploiter(self, explorer, exploiter, K=None, fused=True, inject=None, dump=False):
         """The replay-buffer fill of train_explorer_exploiter.py:110-166 (the no-grad half of an episode): at every step
-        both models score the context so far (K/V-cached ``Transformer.decoder``, one per model), the explorer's sampled
-        arm is what gets RECORDED in the context while the env is stepped with a uniformly random arm (:141-152, as in
-        the reference), and the advantage of step t-1 is the change of the exploiter's cross-entropy against the optimal
-        arm (:160-164).  Returns the context tensors [n_envs,K,.], ``advantages`` [n_envs,K-1,1], both models' logits
-        per step [K,n_envs,du] and ``target``.  Sampling uses torch's device generator like the reference."""
+        both models score the context so far (K/V-cached), the explorer's sampled arm is what gets RECORDED in the
+        context while the env is stepped with a uniformly random arm (:141-152, as in the reference), and the advantage
+        of step t-1 is the change of the exploiter's cross-entropy against the optimal arm (:160-164).  Returns the
+        context tensors [n_envs,K,.], ``advantages`` [n_envs,K-1,1], both models' logits per step [K,n_envs,du] and
+        ``target``.
+
+        ``fused=True`` (default): ONE launch for all K steps (``dpt_gpt2_explore_exploit_rollout``; Philox draws addressed
+        by (env, step); ``inject`` / ``dump``: ctrl_u f64 [K,n], random_arm int32 [K,n], reward_z fp32 [K,n]).
+        ``fused=False``: the step-by-step form over ``Transformer.decoder`` + ``step`` with torch's device generator, as the
+        reference samples."""
+        if fused:
+            return self._rollout_explorer_exploiter_fused(explorer, exploiter, self.H if K is None else K, inject, dump)
         K = self.H if K is None else K
         n, du, dev = self.n_envs, self.du, self._device
         dec_e, dec_x = explorer.decoder(n, K), exploiter.decoder(n, K)
@@ -140,3 +147,50 @@ class GPUBanditEnv(BaseEnv):
             prev_loss = loss
         return dict(ctx, advantages=advantages, explorer_logits=torch.stack(logits_e), exploiter_logits=torch.stack(logits_x),
                     target=target)
+
+    def _rollout_explorer_exploiter_fused(self, explorer, exploiter, K, inject, dump):
+        import ctypes
+        from .. import _lib
+        n, du, dev = self.n_envs, self.du, self._device
+        assert explorer.precision == 0 and exploiter.precision == 0, "the fused explorer / exploiter rollout is fp32"
+        with torch.cuda.device(dev):
+            he, hx = explorer.handle(), exploiter.handle()
+            lib = _lib.lib()
+            out = {"context_states": torch.empty((n, K, self.dx), device=dev), "context_actions": torch.empty((n, K, du), device=dev),
+                   "context_next_states": torch.empty((n, K, self.dx), device=dev), "context_rewards": torch.empty((n, K, 1), device=dev),
+                   "advantages": torch.zeros((n, max(K - 1, 0), 1), device=dev)}
+            kv_bytes = max(lib.dpt_gpt2_online_kv_bytes(he, n, K, 0), lib.dpt_gpt2_online_kv_bytes(hx, n, K, 0))
+            kv_e = torch.empty((max(int(kv_bytes), 1),), dtype=torch.uint8, device=dev)
+            kv_x = torch.empty((max(int(kv_bytes), 1),), dtype=torch.uint8, device=dev)
+            inj_p, keep = None, []
+            if inject is not None:
+                si = _lib.ExploreInject()
+                for k, dt in (("ctrl_u", torch.float64), ("random_arm", torch.int32), ("reward_z", torch.float32)):
+                    if inject.get(k) is not None:
+                        t = kernels._as(inject[k], dt, dev)
+                        keep.append(t)
+                        setattr(si, k, kernels.ptr(t))
+                inj_p = ctypes.byref(si)
+            sd = _lib.ExploreDump()
+            out["explorer_logits"] = torch.empty((K, n, du), device=dev)
+            out["exploiter_logits"] = torch.empty((K, n, du), device=dev)
+            sd.logits_explorer, sd.logits_exploiter = kernels.ptr(out["explorer_logits"]), kernels.ptr(out["exploiter_logits"])
+            if dump:
+                out["noise"] = {"ctrl_u": torch.empty((K, n), dtype=torch.float64, device=dev),
+                                "random_arm": torch.empty((K, n), dtype=torch.int32, device=dev),
+                                "reward_z": torch.empty((K, n), dtype=torch.float32, device=dev)}
+                for k, t in out["noise"].items():
+                    setattr(sd, k, kernels.ptr(t))
+            key = (self._key ^ 0x6A09E667F3BCC909) + 0x9E3779B97F4A7C15 * self._rollouts & 0xFFFFFFFFFFFFFFFF
+            kernels.check(lib.dpt_gpt2_explore_exploit_rollout(
+                he, hx, kernels.ptr(self.means), float(self.var), kernels.REWARD_TYPES[self.type], key, self._env_id0, n, K,
+                kernels.ptr(kv_e), kernels.ptr(kv_x), kv_e.numel(), kernels.ptr(out["context_states"]),
+                kernels.ptr(out["context_actions"]), kernels.ptr(out["context_next_states"]), kernels.ptr(out["context_rewards"]),
+                kernels.ptr(out["advantages"]), inj_p, ctypes.byref(sd), kernels.stream_ptr()), "dpt_gpt2_explore_exploit_rollout")
+        self._draws += K
+        self._rollouts += 1
+        self.reset()
+        self._step = K                     # the episode of K steps is over (envs/gpu_bandit_env.py:59-61)
+        self.current_step = self.current_step + K
+        out["target"] = self.opt_a_index.to(dev)
+        return out

@@ -322,6 +322,37 @@ int dpt_gpt2_online_loop(dpt_gpt2_t* m, const float* means, double var, int rewa
 int dpt_gpt2_decode_step(dpt_gpt2_t* m, const float* tokens, int N, int pos, int T_max, int precision, void* kv_cache,
                          uint64_t kv_bytes, float* logits, void* stream);
 
+/* ---------------------------------------------------------------- (f)4: explorer / exploiter rollout ----
+ * The no-grad half of an episode of train_explorer_exploiter.py:110-166 in ONE launch (fp32, K/V-cached, one cache per
+ * model): per step t both models score the context so far; the explorer's sampled arm is RECORDED in the context
+ * (:131-136, :155) while the env is stepped with a uniformly random arm (:137-152); advantages[n, t-1] =
+ * CE(exploiter logits_t, optimal arm) - CE(exploiter logits_{t-1}, optimal arm) (:158-164).  As published the reference
+ * raises IndexError at t = 0 (its test=False models return preds[:, 1:, :] of an empty context); here, as in
+ * GPUBanditEnv.rollout_explorer_exploiter's step-by-step form, position 0 is the query token.  Outputs: ctx_* fp32
+ * [N,K,.], advantages fp32 [N,K-1].  Draws are Philox (global env id, step); inject / dump: ctrl_u f64 [K,N] (the
+ * explorer's categorical uniforms), random_arm int32 [K,N], reward_z fp32 [K,N]; dump only: both models' logits [K,N,du].
+ * kv_explorer / kv_exploiter: two distinct scratch buffers of >= max over the models of
+ * dpt_gpt2_online_kv_bytes(model, N, K, 0) bytes each. */
+typedef struct {
+  const double* ctrl_u;
+  const int32_t* random_arm;
+  const float* reward_z;
+} dpt_explore_inject_t;
+
+typedef struct {
+  double* ctrl_u;
+  int32_t* random_arm;
+  float* reward_z;
+  float* logits_explorer;
+  float* logits_exploiter;
+} dpt_explore_dump_t;
+
+int dpt_gpt2_explore_exploit_rollout(dpt_gpt2_t* explorer, dpt_gpt2_t* exploiter, const float* means, double var, int reward_type,
+                                     uint64_t seed, uint64_t env_id0, int N, int K, void* kv_explorer, void* kv_exploiter,
+                                     uint64_t kv_bytes_each, float* ctx_states, float* ctx_actions, float* ctx_next_states,
+                                     float* ctx_rewards, float* advantages, const dpt_explore_inject_t* inject,
+                                     const dpt_explore_dump_t* dump, void* stream);
+
 /* ---------------------------------------------------------------- bring-up / regression ----
  * D[128,N] = A[128,K] * B[N,K]^T through tcgen05.mma (bf16 operands, fp32 accumulate in tensor memory):
  * the self-test of the UMMA helpers (descriptors, 128 B swizzle, TMEM loads) used by the dense forward. */

@@ -513,7 +513,7 @@ def test_explorer_exploiter_rollout(dpt):
     from dpt_b200.models.net import Transformer
     from dpt_b200.envs.gpu_bandit_env import GPUBanditEnv
     torch.manual_seed(9)
-    K, d, N = 12, 5, 64
+    K, d, N = 12, 5, 70
     cfg = {"horizon": K, "state_dim": 1, "action_dim": d, "n_layer": 2, "n_embd": 32, "n_head": 1, "dropout": 0.0, "test": True}
     explorer, exploiter = Transformer(cfg), Transformer(cfg)
     with torch.no_grad():
@@ -521,22 +521,48 @@ def test_explorer_exploiter_rollout(dpt):
             for k, p in mdl.named_parameters():
                 if "wte" not in k:
                     p.add_(0.2 * torch.randn_like(p))
-    env = GPUBanditEnv(d, N, K, var=0.3, seed=4)
-    out = env.rollout_explorer_exploiter(explorer, exploiter)
-    assert out["context_actions"].shape == (N, K, d) and float(out["context_actions"].sum(-1).min()) == 1.0
-    assert out["advantages"].shape == (N, K - 1, 1) and out["explorer_logits"].shape == (K, N, d)
-    names = ("context_states", "context_actions", "context_next_states", "context_rewards")
-    losses = []
-    for t in range(K):
-        b = {k: out[k][:, :t] for k in names}
-        b["query_states"] = torch.ones(N, 1, device="cuda")
-        _close(_np(out["exploiter_logits"][t]), _np(exploiter(b)), 1e-5)
-        _close(_np(out["explorer_logits"][t]), _np(explorer(b)), 1e-5)
-        losses.append(torch.nn.functional.cross_entropy(out["exploiter_logits"][t], out["target"], reduction="none"))
-    for t in range(1, K):
-        assert torch.allclose(out["advantages"][:, t - 1, 0], losses[t] - losses[t - 1], atol=1e-6)
-    with pytest.raises(ValueError):
-        env.step(out["context_actions"][:, 0])       # the episode of K steps is over (:59-61)
+    for fused in (True, False):
+        env = GPUBanditEnv(d, N, K, var=0.3, seed=4)
+        out = env.rollout_explorer_exploiter(explorer, exploiter, fused=fused, dump=fused)
+        assert out["context_actions"].shape == (N, K, d) and float(out["context_actions"].sum(-1).min()) == 1.0
+        assert out["advantages"].shape == (N, K - 1, 1) and out["explorer_logits"].shape == (K, N, d)
+        assert bool((out["context_states"] == 1).all()) and bool((out["context_next_states"] == 1).all())
+        names = ("context_states", "context_actions", "context_next_states", "context_rewards")
+        losses = []
+        for t in range(K):
+            b = {k: out[k][:, :t] for k in names}
+            b["query_states"] = torch.ones(N, 1, device="cuda")
+            _close(_np(out["exploiter_logits"][t]), _np(exploiter(b)), 1e-5)
+            _close(_np(out["explorer_logits"][t]), _np(explorer(b)), 1e-5)
+            losses.append(torch.nn.functional.cross_entropy(out["exploiter_logits"][t], out["target"], reduction="none"))
+        for t in range(1, K):
+            assert torch.allclose(out["advantages"][:, t - 1, 0], losses[t] - losses[t - 1], atol=1e-5 if fused else 1e-6)
+        with pytest.raises(ValueError):
+            env.step(out["context_actions"][:, 0])       # the episode of K steps is over (:59-61)
+        if not fused:
+            continue
+        # the fused launch: recorded arm = categorical draw from the explorer's logits on the dumped uniform (float64 softmax
+        # cdf, searchsorted 'right'), reward = means[random arm] + var * z, and a replay on the dumped draws is identical
+        nz = {k: _np(v) for k, v in out["noise"].items()}
+        means = _np(env.means).astype(np.float64)
+        assert nz["random_arm"].min() >= 0 and nz["random_arm"].max() < d and len(np.unique(nz["random_arm"])) == d
+        for t in range(K):
+            lg = _np(out["explorer_logits"][t]).astype(np.float64)
+            pr = np.exp(lg - lg.max(1, keepdims=True))
+            pr /= pr.sum(1, keepdims=True)
+            cdf = np.cumsum(pr, 1)
+            cdf /= cdf[:, -1:]
+            arm = (cdf[:, :-1] <= nz["ctrl_u"][t][:, None]).sum(1)
+            assert np.array_equal(_np(out["context_actions"][:, t]).argmax(1), arm), t
+            want_r = means[np.arange(N), nz["random_arm"][t]] + 0.3 * nz["reward_z"][t].astype(np.float64)
+            assert np.allclose(_np(out["context_rewards"][:, t, 0]), want_r, atol=1e-6)
+        env2 = GPUBanditEnv(d, N, K, var=0.3, seed=4)
+        rep = env2.rollout_explorer_exploiter(explorer, exploiter, inject=out["noise"])
+        for k in names + ("advantages", "explorer_logits", "exploiter_logits"):
+            assert torch.equal(rep[k], out[k]), k
+        # a re-used env object does not replay its noise
+        again = env2.rollout_explorer_exploiter(explorer, exploiter)
+        assert not torch.equal(again["context_rewards"], rep["context_rewards"])
     # the single-model fused rollout also serves bernoulli envs now
     benv = GPUBanditEnv(d, N, K, var=0.3, type="bernoulli", seed=4)
     r = benv.rollout(explorer, K)
