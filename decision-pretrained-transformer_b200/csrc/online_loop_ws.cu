@@ -136,6 +136,24 @@ __device__ __forceinline__ void lin_arm_load(uint32_t sa, double* A) {   // the 
   asm("ld.shared.f64 %0, [%1+32];" : "=d"(A[4]) : "r"(sa));
 }
 
+// First-maximum argmax (np.argmax) of v[LO..HI) as a balanced tournament: the right half wins only when strictly greater, so ties
+// go to the lower index exactly as in the sequential scan, but the dependent compare / select chain is log2(n) deep instead of n
+// (the controller kernels run 5 warps per scheduler; a step's latency chain matters as much as its instruction count)
+template <int LO, int HI>
+__device__ __forceinline__ void argmax_tree(const double* v, double& best, int& idx) {
+  if constexpr (HI - LO == 1) {
+    best = v[LO], idx = LO;
+  } else {
+    constexpr int MID = LO + (HI - LO + 1) / 2;
+    double bl, br;
+    int il, ir;
+    argmax_tree<LO, MID>(v, bl, il);
+    argmax_tree<MID, HI>(v, br, ir);
+    const bool right = br > bl;
+    best = right ? br : bl, idx = right ? ir : il;
+  }
+}
+
 // the env step's reward in float64, as the reference forms it; shared by the controller (statistics) and the expander (context rows)
 __device__ __forceinline__ double reward_f64(float ma, float z, double var, int rtype) {
   return rtype == DPT_REWARD_GAUSSIAN ? (double)ma + (0.0 + var * (double)z)   // envs/bandit_env.py:59
@@ -285,10 +303,8 @@ struct WsKernel {
       if (KIND == K_OPT) {
         a = opt;                                                        // ctrl_bandit.py:35-37
       } else if (KIND == K_EMP || KIND == K_UCB) {
-        double best = -INFINITY;   // padding arms j >= d carry -inf and are never picked
-#pragma unroll
-        for (int j = 0; j < DMAX; ++j)
-          if (S.st0[j] > best) best = S.st0[j], a = j;                  // np.argmax: first maximum  :106 | :369-370
+        double best;               // padding arms j >= d carry -inf and are never picked
+        argmax_tree<0, DMAX>(S.st0, best, a);                           // np.argmax: first maximum  :106 | :369-370
         if ((KIND == K_UCB || p.p0 != 0.0) && S.untried) a = __ffs(S.untried) - 1;   // np.argmin(counts) when min == 0  :110-113 | :373-375
       } else if (KIND == K_THOMPSON) {
         if ((u % ZSPAN) == 0) {           // control normals of steps hh .. hh + ZSPAN - 1: NBZ Philox blocks
@@ -309,13 +325,24 @@ struct WsKernel {
             }
           }
         }
-        double best = -INFINITY;
+        if constexpr (DMAX <= 5) {
+          double vs[DMAX], best;
 #pragma unroll
-        for (int j = 0; j < DMAX; ++j) {
-          const float zj = zc[(u % ZSPAN) * DMAX + j];
-          if (IO && p.out.ctrl_z && live && j < d) p.out.ctrl_z[((size_t)hh * N + env) * d + j] = zj;
-          const double v = fma(S.st1[j], (double)zj, S.st0[j]);         // np.random.normal(means, sqrt(variances)) :234
-          if (v > best) best = v, a = j;                                // (padding arms: mean -inf, std 0)
+          for (int j = 0; j < DMAX; ++j) {
+            const float zj = zc[(u % ZSPAN) * DMAX + j];
+            if (IO && p.out.ctrl_z && live && j < d) p.out.ctrl_z[((size_t)hh * N + env) * d + j] = zj;
+            vs[j] = fma(S.st1[j], (double)zj, S.st0[j]);                // np.random.normal(means, sqrt(variances)) :234
+          }                                                             // (padding arms: mean -inf, std 0)
+          argmax_tree<0, DMAX>(vs, best, a);
+        } else {   // d = 10: 10 live samples do not fit beside the 40 cached statistics (tournament: 0.50 -> 0.70 ms, spills)
+          double best = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < DMAX; ++j) {
+            const float zj = zc[(u % ZSPAN) * DMAX + j];
+            if (IO && p.out.ctrl_z && live && j < d) p.out.ctrl_z[((size_t)hh * N + env) * d + j] = zj;
+            const double v = fma(S.st1[j], (double)zj, S.st0[j]);
+            if (v > best) best = v, a = j;
+          }
         }
       } else if (KIND == K_LINUCB2) {
         if (hh == 0) {                                                  // :496-500 uniform random first arm
