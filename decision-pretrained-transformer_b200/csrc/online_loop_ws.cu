@@ -7,7 +7,7 @@
 //   per step   pick arm -> reward -> O(1) statistics update -> stage the arm (as a byte and as a bit of the step quad's
 //       one-hot bit string) and the reward in shared memory, store cum_means[h, env] (coalesced across the warp).
 //       The per-arm (sum, count) live in shared memory (only the pulled arm is touched), the cached decision
-//       statistics in registers: 64 registers per thread, so that 32 warps are resident per SM and 100k envs
+//       statistics in registers: 80 registers per thread, 24 warps resident per SM, so that 100k envs
 //       (21.1 warps per SM) are ONE wave.  Everything that depends on a count only (1/n, the UCB bonus, Thompson's
 //       1/(var + n prior_var) and posterior std) comes from a [2][H+1] float64 table, so a step has no float64
 //       division or square root.  float64 like the reference: the arm is the reference's arm.
@@ -17,6 +17,8 @@
 //       table lookup -- in batches of four independent load / lookup / store chains.
 //   The per-step regret sums [H,4] are NOT accumulated here: regret_pass_kernel (below) streams cum_means [H,N]
 //   once afterwards.
+// This single fused kernel is what Thompson / LinUCB use at large batches; Opt / EmpMean / UCB and small batches run the split
+// pipeline in the second half of this file (controller kernel + context-expansion kernel), see launch_online_ws / dpt_online_loop.
 // Measured dead end kept in DESIGN.md: the warp-specialised form of this kernel (3 controller warps + 1 flush / noise
 // warp per CTA, tiles handed over through mbarriers) -- the single helper warp runs ~50-230 dependent instructions
 // per step for its three controllers and becomes the bottleneck (controllers stalled 12 % of their time on the
@@ -553,20 +555,23 @@ __global__ void __launch_bounds__(WS_NCONS * 32, ws_min_blocks<DMAX, KIND>()) on
 }
 
 // =============================================================================================
-// Split pipeline (round 2, second half): controller chunks || context expansion || regret pass
+// Split pipeline (round 2, second half): controller kernel -> context expansion (+ regret sums)
 // =============================================================================================
 // The fused kernel above is bound by its context stores: every 32 steps an env's rows leave as 640 B + 128 B pieces scattered over
 // 100k rows, drained by the same warps whose controller chains are the critical path (store-stream elimination in DESIGN.md section 4:
 // 0.10 ms of controller against 0.46 ms of stores at 100k x 500).  Here the sequential part does only what is sequential:
-//   online_ctrl_kernel     lane = env, steps [h_lo, h_hi): arm, reward (for its statistics), cum_means[h, env] and ONE coalesced
-//                          4-byte word of arms per env and step quad into a scratch [H/4][N] (1 B per env-step, stays in L2);
-//   online_expand_kernel   fully parallel over (env, step quad), launched per chunk behind the controller chunk that produced its
-//                          arms: re-derives the rewards from the same Philox block and the same float64 expression and writes the
-//                          one-hot rows and rewards as contiguous 128-step runs (16 B per lane, 512 B per warp and instruction);
-//   ones_fill_kernel       the constant state columns, one streaming fill that runs beside the first controller chunk;
-//   regret_pass_kernel     per chunk, the float64 cumulative regret carried between chunks.
-// The three run on three internal streams forked from / joined to the caller's stream with events (graph-capturable), the
-// controller stream at high priority: HBM-bound expansion and latency-bound control share the SMs.
+//   online_ctrl_kernel     lane = env, all H steps: arm, reward (for its statistics), cum_means[h, env], ONE coalesced 4-byte word
+//                          of arms per env and step quad into a scratch [H/4][N] (1 B per env-step), the constant state columns in
+//                          512 B pieces per step quad (the warp's 32 envs are one contiguous run per array) and, every 128 steps,
+//                          the env's cumulative regret (float64 carries for the expander / the regret pass);
+//   online_expand_kernel   fully parallel over (env, step quad), behind the controller kernel on the same stream: re-derives the
+//                          rewards from the same Philox block and the same float64 expression, writes rewards and one-hot rows as
+//                          contiguous 128-step runs (16 B per lane, 512 B per warp and instruction) and accumulates the [H,3] regret
+//                          sums in thread-local float64 registers;
+//   ones_fill_kernel       the constant state columns when the shapes are not 16 B-friendly (otherwise the controller writes them);
+//   regret_pass_kernel     the regret sums from cum_means when the context is not materialised (and after the fused kernel).
+// Everything runs on the caller's stream.  Measured and dropped (dead ends): controller chunks in time running
+// beside expansion chunks on internal streams -- co-running kernels are issue-bound together, 128-step pieces lose DRAM locality.
 // resident CTAs per SM the controller kernel is compiled for: 6 (80 registers, no spills; 100k envs = 5.3 CTAs per SM are still one
 // wave), Thompson at d = 10 (40 float64 statistics in registers) 4
 template <int DMAX, int KIND>
