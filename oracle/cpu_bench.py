@@ -137,15 +137,22 @@ def _work_impl(args):
     return n * H, n, dt, float(np.sum(cum))
 
 
+def _cpu_only():
+    """Pool initializer: the workers are the CPU arm.  The reference picks ``torch.device('cuda' if available)`` at import
+    (ctrls/ctrl_bandit.py:8, models/net.py), so on a GPU box its transformer controllers would otherwise run their forwards on
+    the GPU from 16 processes -- hide the device before anything imports torch in the worker."""
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+
+
 class CpuPool:
-    """Persistent spawn pool (safe next to an initialised CUDA context), one worker per host core."""
+    """Persistent spawn pool (safe next to an initialised CUDA context), one worker per host core, no GPU visible."""
 
     def __init__(self, cores=None, kind=None):
         import multiprocessing as mp
         from oracle import ref_loader
         self.cores = cores or host_cores()
         self.kind = kind or ("reference" if ref_loader.available() else "port")
-        self.pool = mp.get_context("spawn").Pool(self.cores)
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_only)
         self.pool.map(_work, [(self.kind, "bandit", i, 1, 8, {"dim": 5, "var": 0.3}) for i in range(self.cores)])   # start-up + imports
 
     def run(self, workload, n_per_core, H, seed0=0, kind=None, **extra):
